@@ -1,0 +1,105 @@
+"""Pin the oracle to the reference's own known-answer tests (SURVEY §8c goldens 1-7)."""
+import json
+import os
+
+import numpy as np
+
+import orc
+
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bm25_goldens.json")))
+
+
+def _fmt(x):
+    """sqllogic prints fp32 with the shortest round-trip representation."""
+    return np.format_float_positional(np.float32(x), unique=True, trim="-")
+
+
+def test_ranking_alien_golden():
+    g = G["ranking_alien"]
+    st = orc.bm25_stats(g["docs_with_field"], g["total_term_freq"], g["docs_with_term"], g["k"], g["b"])
+    s = orc.bm25_score([g["freq"]], None, st, k=g["k"])  # no norm column => norm = 1
+    assert _fmt(s[0]) == g["expected"]
+
+
+def test_multiterm_goldens():
+    g = G["multiterm"]
+    for c in g["cases"]:
+        st = orc.bm25_stats(g["docs_with_field"], g["total_term_freq"], c["docs_with_term"], g["k"], g["b"])
+        s = orc.bm25_score([c["freq"]], [c["norm"]], st, k=g["k"])
+        assert _fmt(s[0]) == c["expected"]
+        # NB: the printed score is NOT bit-equal to idf (0.8266786): the golden pins the fp32 op order.
+
+
+def test_collector_goldens():
+    for c, hi in zip(G["collector"]["cases"], (20, 100)):
+        docs = np.arange(2, hi + 1, 2, dtype=np.uint32)
+        hits, total, thr = orc.collect_nth(docs.astype(np.float32), docs, c["k"])
+        assert total == len(docs)
+        assert len(hits) >= c["k"]
+        assert list(hits["doc"][:3]) == c["top"]
+        assert 0 < thr < c["top"][2]  # threshold = (k+1)-th best at the last nth_element
+
+
+def _wtf_segment():
+    g = G["wand_table_filter"]
+    rows = g["rows"]
+    vocab = {"term": 0, "fill": 1, "rare": 2}
+    n = len(rows)
+    seg = orc.Segment(n, has_wand=True)
+    toks = [r["body"].split() for r in rows]
+    seg.set_norms([len(t) for t in toks])
+    for w in ("term", "fill", "rare"):
+        docs = [i + 1 for i, t in enumerate(toks) if w in t]
+        freqs = [t.count(w) for t in toks if w in t]
+        seg.add_term(docs, freqs)
+    seg.add_column(7, np.array([r["n"] for r in rows], np.int32))
+    total_tf = sum(len(t) for t in toks)
+    return seg, vocab, n, total_tf, rows
+
+
+def _term(seg, t, n_docs, total_tf, k=1.2, b=0.75):
+    m = seg.term_meta(t)
+    st = orc.bm25_stats(n_docs, total_tf, m.docs_count, k, b)
+    q = orc.BM25Term()
+    q.idf, q.norm_const, q.norm_length, q.boost, q.term = st.idf, st.norm_const, st.norm_length, 1.0, t
+    return q
+
+
+def test_wand_table_filter_golden():
+    """Hybrid BM25 + `.col` filter + top-k: n in {30,40} / {40,50} (inverted_index_wand_table_filter.test:78-110)."""
+    g = G["wand_table_filter"]
+    seg, vocab, n, total_tf, rows = _wtf_segment()
+    filt = orc.make_pred(7, "GT", 20)
+    for case in ("case1", "case2"):
+        terms = [_term(seg, vocab[w], n, total_tf) for w in g[case]["terms"]]
+        for mode in (0, 1, 2):
+            hits, total, _ = orc.bm25_topk([seg], "OR", terms, g["k"], filt=filt, mode=mode)
+            got = [rows[d - 1]["n"] for d in hits["doc"]]
+            assert got == g[case]["expected_n"], (case, mode, got)
+            assert total == 3
+
+
+def test_scan_10k_goldens():
+    """filter/COUNT/SUM exact values over 3 segments (search_table_scan_10k.test:34-95)."""
+    segs = []
+    for s in range(3):
+        x = np.arange(8000 * s, 8000 * (s + 1), dtype=np.int64)
+        seg = orc.Segment(8000, has_wand=False)
+        seg.add_column(1, x)
+        if s == 0:
+            seg.add_column(3, np.zeros(8000, np.int64), validity=np.zeros(125, np.uint64))  # n IS NULL
+        else:
+            seg.add_column(3, x)
+        segs.append(seg)
+    P = orc.make_pred
+    assert orc.filter_count_sum(segs, [], 1)[0] == 24000
+    assert orc.filter_count_sum(segs, [P(1, "GE", 20000)], 1)[0] == 4000
+    assert orc.filter_count_sum(segs, [P(1, "LT", 0)], 1)[0] == 0
+    assert orc.filter_count_sum(segs, [P(3, "IS_NULL")], 1)[0] == 8000
+    assert orc.filter_count_sum(segs, [P(3, "IS_NOT_NULL")], 1)[0] == 16000
+    cnt, s, _ = orc.filter_count_sum(segs, [P(1, "BETWEEN", 12000, 12099)], 1)
+    assert (cnt, s) == (100, 1204950)
+    cnt, s, _ = orc.filter_count_sum(segs, [P(1, "BETWEEN", 12000, 12099)], 1, threads=4)
+    assert (cnt, s) == (100, 1204950)
+    # conjunction of pushed filters: x >= 8000 AND n IS NOT NULL  (x % 2 = 0 is an expression filter, out of scope)
+    assert orc.filter_count_sum(segs, [P(1, "GE", 8000), P(3, "IS_NOT_NULL")], 1)[0] == 16000
