@@ -1,0 +1,190 @@
+/* include/sdbg.h -- C ABI of libsdbg.so: the B200 (sm_100a) implementation of SereneDB's
+ * query-time hot path. Plain pointers and sizes only; no C++/torch types cross this boundary.
+ *
+ * What each entry point replaces in the reference (paths relative to /root/reference, "irs/" =
+ * libs/iresearch/include/iresearch/):
+ *
+ *   sdbg_stage_postings   the per-segment open of the ".doc" stream + term metas that
+ *                         PostingsReaderBase::prepare / ::decode perform
+ *                         (irs/formats/posting/reader.hpp:100-226) -- index-load time.
+ *   sdbg_stage_norms      NormColumnReader (irs/formats/column/norm_column_reader.hpp:43-108).
+ *   sdbg_stage_column     ColumnReader open of a `.col` column (irs/formats/column/column_reader.hpp:90-256).
+ *   sdbg_bm25_topk        the body of DocIterator::Collect for the WAND iterators built in
+ *                         PostingsReaderImpl::WandIterator (irs/formats/posting/reader.hpp:457-501),
+ *                         driven by irs::ExecuteTopK (irs/search/doc_collector.hpp:88-136) and by
+ *                         CollectSegmentTopK (server/connector/duckdb_search_full_scan.cpp:1868-1921);
+ *                         with `filt` it is TableFilterDocIterator::Collect
+ *                         (irs/index/table_filter_iterator.cpp:450-475).
+ *   sdbg_filter_bitmap    ColFilterChain::FilterWindow (irs/index/table_filter_iterator.cpp:147-264).
+ *   sdbg_filter_count_sum RunCountScan / UNGROUPED_AGGREGATE over iresearch_scan
+ *                         (server/connector/duckdb_search_full_scan.cpp:2201-2239).
+ *   sdbg_filter_groupby   RunColScan + FullScanner::Scan feeding DuckDB's HASH_GROUP_BY
+ *                         (duckdb_search_full_scan.cpp:2405-2433, server/connector/full_scanner.cpp:81-147).
+ *
+ * Conventions: every function returns 0 on success and a negative SDBG_E* code otherwise; it never
+ * throws. The caller owns all host buffers. Handles are opaque. A context owns one CUDA device and
+ * one stream; calls on one context are serialised by the caller (one context per worker thread,
+ * like one DocIterator per (segment, query, worker) in the reference). There is NO CPU fallback:
+ * without a CUDA device sdbg_init fails with SDBG_ENODEVICE.
+ */
+#ifndef SDBG_H_
+#define SDBG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDBG_OK 0
+#define SDBG_EINVAL (-1)    /* bad argument */
+#define SDBG_ENODEVICE (-2) /* no CUDA device / wrong architecture */
+#define SDBG_ECUDA (-3)     /* CUDA runtime error (see sdbg_last_error) */
+#define SDBG_EFORMAT (-4)   /* corrupt posting stream */
+#define SDBG_ENOTFOUND (-5) /* unknown field */
+#define SDBG_ECAPACITY (-6) /* output buffer too small */
+#define SDBG_EUNSUPPORTED (-7)
+
+typedef struct sdbg_ctx sdbg_ctx;
+typedef struct sdbg_segment sdbg_segment;
+
+/* ---- lifecycle ---- */
+int sdbg_init(int device, sdbg_ctx** out);
+void sdbg_destroy(sdbg_ctx*);
+const char* sdbg_last_error(const sdbg_ctx*);
+const char* sdbg_version(void);
+/* Device-side timing on the context's stream (CUDA events), so callers never guess the stream. */
+int sdbg_timer_start(sdbg_ctx*);
+int sdbg_timer_stop(sdbg_ctx*, float* ms);
+int sdbg_sync(sdbg_ctx*);
+/* Number of kernels this context has launched since creation (bench's gpu_launches claim). */
+uint64_t sdbg_launch_count(const sdbg_ctx*);
+/* Writes `bytes` of device memory (> L2) to evict cached inputs between timed iterations. */
+int sdbg_flush_l2(sdbg_ctx*);
+
+/* ---- staging (index-load time): host bytes are copied to HBM; the caller may free them ---- */
+typedef struct {
+  uint32_t docs_count;   /* TermMetaImpl::docs_count */
+  uint32_t freq;         /* total term frequency */
+  uint64_t doc_start;    /* offset of the term's stream in the .doc bytes handed in */
+  uint64_t e_skip_start; /* e_single_doc when docs_count == 1 (same union as reader.hpp:213-217) */
+} sdbg_term_meta;
+
+int sdbg_segment_create(sdbg_ctx*, uint32_t docs_count, sdbg_segment** out);
+void sdbg_segment_destroy(sdbg_segment*);
+/* doc_file: the ".doc" stream (posting blocks + skip data, format "1_5simd"); has_wand != 0 when
+ * the field was indexed with block-max data (optimize_top_k). Builds the per-block offset table
+ * and copies 16-byte-aligned block payloads to HBM. */
+int sdbg_stage_postings(sdbg_segment*, const uint8_t* doc_file, size_t n, const sdbg_term_meta* terms,
+                        size_t n_terms, int has_wand);
+typedef struct { uint8_t byte_size; uint32_t row_count; uint64_t file_offset; } sdbg_norm_rg; /* norm_writer.hpp:41-48 */
+/* Row groups of fixed-width (1/2/4 B) little-endian field lengths; row = doc - 1. */
+int sdbg_stage_norms(sdbg_segment*, const uint8_t* bytes, size_t n, const sdbg_norm_rg* rgs, size_t n_rg);
+typedef enum { SDBG_I64 = 0, SDBG_F64 = 1, SDBG_I32 = 2 } sdbg_type;
+/* validity may be NULL (NOT NULL column); otherwise bit r of validity[r/64] set => row r is valid. */
+int sdbg_stage_column(sdbg_segment*, uint64_t field, sdbg_type t, const void* values,
+                      const uint64_t* validity, uint64_t rows);
+/* Same, but `d_values` already lives in device memory (borrowed, not copied, not freed). */
+int sdbg_stage_column_device(sdbg_segment*, uint64_t field, sdbg_type t, const void* d_values, uint64_t rows);
+/* Device address of a staged column (for callers that generate data in place). */
+int sdbg_column_device_ptr(sdbg_segment*, uint64_t field, void** d_values, uint64_t* rows);
+/* Bytes of HBM held by the segment's postings (payload + tables) and how many blocks were staged. */
+int sdbg_segment_posting_stats(const sdbg_segment*, uint64_t* payload_bytes, uint64_t* table_bytes,
+                               uint64_t* n_blocks, uint64_t* n_postings);
+
+/* ---- predicates (pushed TableFilterSet entries; NULL never passes) ---- */
+enum { SDBG_OP_LT = 0, SDBG_OP_LE, SDBG_OP_GT, SDBG_OP_GE, SDBG_OP_EQ, SDBG_OP_NE, SDBG_OP_BETWEEN,
+       SDBG_OP_IS_NULL, SDBG_OP_IS_NOT_NULL };
+typedef struct {
+  uint64_t field;
+  int32_t op;
+  int32_t is_float;
+  int64_t lo_i, hi_i;
+  double lo_f, hi_f;
+} sdbg_col_pred;
+
+/* ---- BM25 top-k (boundary B2, irs::DocIterator::Collect) ---- */
+enum { SDBG_QUERY_OR = 0, SDBG_QUERY_AND = 1 };
+typedef struct { float idf, norm_const, norm_length, boost; uint32_t term; } sdbg_bm25_term; /* BM25Stats (bm25.hpp:49-56) + boost */
+typedef struct { float score; uint32_t doc; uint32_t seg; } sdbg_hit;                          /* irs::ScoreDoc (iterators.hpp:93-101) */
+
+/* BM25::collect mirror (irs/search/bm25.cpp:279-310): corpus-wide statistics -> BM25Stats. idf is
+ * computed in double and narrowed, avg_dl divides two floats, norm_const = k - k*b. boost is set to 1. */
+int sdbg_bm25_collect(uint64_t docs_with_field, uint64_t total_term_freq, uint64_t docs_with_term, float k,
+                      float b, sdbg_bm25_term* out);
+
+/* One query over the segments of this GPU. Accepts docs with score > threshold_in (seed it with
+ * FLT_MIN like doc_collector.hpp:102, or with the cross-worker threshold). out has room for k hits,
+ * returned sorted by (score desc, seg asc, doc asc); *threshold_out = k-th score if k hits exist. */
+int sdbg_bm25_topk(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25_term* terms,
+                   size_t n_terms, float k1, const sdbg_col_pred* filt, uint32_t k, float threshold_in,
+                   sdbg_hit* out, uint32_t* n_out, uint64_t* total_matches, float* threshold_out);
+/* A batch of independent queries in one launch set (the benchmark-game / many-workers shape).
+ * Query q uses terms[term_off[q] .. term_off[q+1]); out holds n_queries*k hits, n_out/total per query. */
+int sdbg_bm25_topk_batch(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25_term* terms,
+                         const uint32_t* term_off, size_t n_queries, float k1, const sdbg_col_pred* filt,
+                         uint32_t k, float threshold_in, sdbg_hit* out, uint32_t* n_out,
+                         uint64_t* total_matches);
+/* Multi-GPU: leave each query's top-k on the device as sortable 64-bit keys + a base ordinal so a
+ * collective can gather them; merge gathered keys from `n_ranks` ranks. */
+int sdbg_bm25_topk_batch_device(sdbg_segment* const* segs, size_t n_segs, int kind,
+                                const sdbg_bm25_term* terms, const uint32_t* term_off, size_t n_queries,
+                                float k1, const sdbg_col_pred* filt, uint32_t k, float threshold_in,
+                                uint32_t rank, void* d_keys /* n_queries*k u64 */,
+                                void* d_totals /* n_queries u64 */);
+int sdbg_topk_merge_gathered(sdbg_ctx*, const void* d_keys_all /* n_ranks*n_queries*k u64 */,
+                             uint32_t n_ranks, size_t n_queries, uint32_t k, sdbg_hit* out, uint32_t* n_out);
+/* Test probe: decode+score one whole posting list (exhaustive, no top-k). Buffers sized docs_count. */
+int sdbg_decode_score_term(sdbg_segment*, uint32_t term, float c0, float norm_const, float norm_length,
+                           uint32_t* docs, uint32_t* freqs, float* scores);
+
+/* ---- columnar filter / aggregate (boundary B3, iresearch_scan) ---- */
+int sdbg_filter_bitmap(sdbg_segment*, const sdbg_col_pred* preds, size_t n_preds, uint64_t* mask_out);
+int sdbg_filter_count_sum(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred* preds,
+                          size_t n_preds, uint64_t sum_field, uint64_t* count, int64_t sum_i128[2],
+                          double* sum_f64);
+typedef struct { int64_t key; uint64_t count; int64_t sum_i128[2]; double sum_f64; uint64_t cnt_f64; } sdbg_group_row;
+/* SELECT key, COUNT(*), SUM(sum_int_field), SUM(avg_f64_field)/cnt_f64 ... GROUP BY key.
+ * Rows come back sorted by key. Pass UINT64_MAX for an aggregate field that is not wanted. */
+int sdbg_filter_groupby(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred* preds,
+                        size_t n_preds, uint64_t key_field, uint32_t n_groups_hint,
+                        uint64_t sum_int_field, uint64_t avg_f64_field, sdbg_group_row* out, uint64_t cap,
+                        uint64_t* n_out);
+/* Multi-GPU split of the same: partial dense aggregates stay on the device in two flat buffers that
+ * a SUM all-reduce can merge (int64 limbs + counts, and float64 sums), then finalize on any rank.
+ * d_i64: 4*span int64 = [count | sum_lo | sum_hi | cnt_f64]; d_f64: span float64. */
+int sdbg_filter_groupby_partial(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred* preds,
+                                size_t n_preds, uint64_t key_field, int64_t key_min, uint64_t key_span,
+                                uint64_t sum_int_field, uint64_t avg_f64_field, void* d_i64, void* d_f64);
+int sdbg_groupby_finalize(sdbg_ctx*, int64_t key_min, uint64_t key_span, const void* d_i64,
+                          const void* d_f64, sdbg_group_row* out, uint64_t cap, uint64_t* n_out);
+/* min/max of a staged int column (zonemap-style statistics gathered at staging). */
+int sdbg_column_minmax_i64(sdbg_segment*, uint64_t field, int64_t* mn, int64_t* mx);
+
+/* ---- host-side writer mirror + deterministic synthetic inputs (index-build side; not timed) ---- */
+/* PostingsWriter mirror (irs/formats/posting/writer.hpp): builds a ".doc" stream on the host. */
+typedef struct sdbg_writer sdbg_writer;
+int sdbg_writer_create(uint32_t segment_docs, int has_wand, float wand_b, const uint32_t* norms /* per doc, may be NULL */,
+                       sdbg_writer** out);
+void sdbg_writer_destroy(sdbg_writer*);
+int sdbg_writer_add_term(sdbg_writer*, const uint32_t* docs, const uint32_t* freqs, uint32_t n);
+int sdbg_writer_finish(sdbg_writer*, const uint8_t** doc_file, size_t* n, const sdbg_term_meta** terms, size_t* n_terms);
+/* Synthetic corpus shard of SURVEY §8d: docs (doc0, doc0+n], terms [t0, t0+nt); fills norms (u8,
+ * dl<=255) and stages everything into `seg`. Returns per-term docs_count and the shard's sum of dl. */
+int sdbg_synth_corpus(sdbg_segment* seg, uint64_t doc0, uint32_t n_docs, uint32_t t0, uint32_t nt,
+                      int threads, uint32_t* docs_count_out /* nt */, uint64_t* sum_dl_out);
+/* Synthetic table column generated directly in HBM: kind as in SURVEY §8d (0 k,1 a,2 b,3 v,4 w,5+ raw),
+ * or 6 = int32 n = h % 1000000 (hybrid INCLUDE column, stream 2). */
+int sdbg_synth_column(sdbg_segment* seg, uint64_t field, uint64_t stream, int kind, uint64_t row0, uint64_t rows);
+uint64_t sdbg_synth_hash(uint64_t stream, uint64_t index);
+/* Host-only probe of the staging parser (no device): block table of a ".doc" stream, for tests. */
+int sdbg_debug_stage_host(const uint8_t* doc_file, size_t n, const sdbg_term_meta* terms, size_t n_terms, int has_wand,
+                          uint32_t cap, uint32_t* n_blocks, uint32_t* term_blk_begin, uint32_t* last_doc,
+                          uint32_t* prev_last, uint32_t* packed, uint32_t* max_freq, uint32_t* max_norm,
+                          uint64_t* arena_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDBG_H_ */

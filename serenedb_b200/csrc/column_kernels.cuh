@@ -1,0 +1,406 @@
+// column_kernels.cuh -- sm_100a kernels for the columnar filter / aggregate path.
+//
+// Reference behaviour (paths relative to /root/reference):
+//   scan+filter   server/connector/full_scanner.cpp:81-147 (FullScanner::Scan: FilterWindow narrows a
+//                 selection vector, survivors' columns are gathered, 2048 rows per call)
+//                 libs/iresearch/include/iresearch/index/table_filter_iterator.cpp:147-264
+//   NULL logic    server/connector/duckdb_search_full_scan.cpp:1785-1786 (NULL never passes)
+//   aggregates    DuckDB HASH_GROUP_BY / UNGROUPED_AGGREGATE above the scan (not in the tree):
+//                 COUNT u64, SUM(BIGINT) exact 128-bit, SUM/AVG(DOUBLE) double sum + one division.
+//
+// All kernels are HBM-streaming: every referenced column byte is read exactly once with 16-byte
+// no-allocate loads, predicates are evaluated in registers, and only aggregates leave the SM
+// (warp-shuffle + block reduction for ungrouped, L2-resident RED atomics for grouped).
+#pragma once
+
+#include "device_common.cuh"
+
+namespace sdbg {
+
+constexpr int kMaxPreds = 4;
+
+struct ColDev {
+  const void* values;        // 8-byte (i64/f64) or 4-byte (i32) elements
+  const uint64_t* validity;  // null => NOT NULL
+  int32_t type;              // 0 i64, 1 f64, 2 i32
+  int32_t pad;
+};
+struct PredDev {
+  ColDev col;
+  int32_t op;
+  int32_t pad;
+  int64_t lo_i, hi_i;
+  double lo_f, hi_f;
+};
+struct PredSet {
+  PredDev p[kMaxPreds];
+  int32_t n;
+  int32_t pad;
+};
+
+__device__ __forceinline__ bool col_valid(const ColDev& c, uint64_t r) {
+  return c.validity == nullptr || ((__ldg(c.validity + (r >> 6)) >> (r & 63)) & 1ull);
+}
+__device__ __forceinline__ bool cmp_i64(int op, long long v, long long lo, long long hi) {
+  switch (op) {
+    case 0: return v < lo; case 1: return v <= lo; case 2: return v > lo; case 3: return v >= lo;
+    case 4: return v == lo; case 5: return v != lo; default: return v >= lo && v <= hi;
+  }
+}
+__device__ __forceinline__ bool cmp_f64(int op, double v, double lo, double hi) {
+  switch (op) {
+    case 0: return v < lo; case 1: return v <= lo; case 2: return v > lo; case 3: return v >= lo;
+    case 4: return v == lo; case 5: return v != lo; default: return v >= lo && v <= hi;
+  }
+}
+
+// Evaluates predicate `p` on rows r, r+1 (r even). Returns a 2-bit mask. 8-byte columns are read
+// with one 16-byte streaming load; i32 columns with one 8-byte load.
+__device__ __forceinline__ uint32_t pred2(const PredDev& p, uint64_t r, uint64_t rows) {
+  uint32_t valid = 3u;
+  if (p.col.validity) valid = (col_valid(p.col, r) ? 1u : 0u) | ((r + 1 < rows && col_valid(p.col, r + 1)) ? 2u : 0u);
+  if (p.op == 7) return (~valid) & 3u;
+  if (p.op == 8) return valid;
+  uint32_t m = 0;
+  if (p.col.type == 2) {
+    const int2 v = *reinterpret_cast<const int2*>(static_cast<const int*>(p.col.values) + r);
+    m = (cmp_i64(p.op, v.x, p.lo_i, p.hi_i) ? 1u : 0u) | (cmp_i64(p.op, v.y, p.lo_i, p.hi_i) ? 2u : 0u);
+  } else {
+    const uint4 raw = ld_stream_v4(static_cast<const char*>(p.col.values) + r * 8);
+    if (p.col.type == 1) {
+      const double a = __longlong_as_double((static_cast<long long>(raw.y) << 32) | raw.x);
+      const double b = __longlong_as_double((static_cast<long long>(raw.w) << 32) | raw.z);
+      m = (cmp_f64(p.op, a, p.lo_f, p.hi_f) ? 1u : 0u) | (cmp_f64(p.op, b, p.lo_f, p.hi_f) ? 2u : 0u);
+    } else {
+      const long long a = (static_cast<long long>(raw.y) << 32) | raw.x;
+      const long long b = (static_cast<long long>(raw.w) << 32) | raw.z;
+      m = (cmp_i64(p.op, a, p.lo_i, p.hi_i) ? 1u : 0u) | (cmp_i64(p.op, b, p.lo_i, p.hi_i) ? 2u : 0u);
+    }
+  }
+  return m & valid;
+}
+
+// All predicates on a row pair. Rows are padded to even counts by the host allocation (8-byte
+// columns are allocated with 16 bytes of slack), the (r+1 < rows) test masks the phantom row.
+__device__ __forceinline__ uint32_t preds2(const PredSet& ps, uint64_t r, uint64_t rows) {
+  uint32_t m = (r + 1 < rows) ? 3u : 1u;
+#pragma unroll
+  for (int i = 0; i < kMaxPreds; ++i) {
+    if (i < ps.n) m &= pred2(ps.p[i], r, rows);
+  }
+  return m;
+}
+
+__device__ __forceinline__ void load2_i64(const ColDev& c, uint64_t r, long long& a, long long& b) {
+  if (c.type == 2) {
+    const int2 v = *reinterpret_cast<const int2*>(static_cast<const int*>(c.values) + r);
+    a = v.x; b = v.y;
+  } else {
+    const uint4 raw = ld_stream_v4(static_cast<const char*>(c.values) + r * 8);
+    a = (static_cast<long long>(raw.y) << 32) | raw.x;
+    b = (static_cast<long long>(raw.w) << 32) | raw.z;
+  }
+}
+__device__ __forceinline__ void load2_f64(const ColDev& c, uint64_t r, double& a, double& b) {
+  const uint4 raw = ld_stream_v4(static_cast<const char*>(c.values) + r * 8);
+  a = __longlong_as_double((static_cast<long long>(raw.y) << 32) | raw.x);
+  b = __longlong_as_double((static_cast<long long>(raw.w) << 32) | raw.z);
+}
+
+// ------------------------------------------------------------------------------------------
+// Filter bitmap (parity probe, and the FilterWindow analogue). One thread per 2 rows, a warp
+// produces one 64-bit mask word.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+filter_bitmap_kernel(const PredSet ps, uint64_t rows, unsigned long long* __restrict__ mask_out) {
+  const uint64_t words = (rows + 63) / 64;
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint64_t w = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; w < words;
+       w += (uint64_t(gridDim.x) * blockDim.x) >> 5) {
+    const uint64_t r = w * 64 + 2ull * lane;
+    const uint32_t m = r < rows ? preds2(ps, r, rows) : 0u;
+    const uint32_t b0 = __ballot_sync(kFull, m & 1u);
+    const uint32_t b1 = __ballot_sync(kFull, m & 2u);
+    if (lane == 0) {
+      // interleave: bit 2l = row pair l first row, bit 2l+1 = second row
+      unsigned long long x = 0;
+      for (int l = 0; l < 32; ++l) {
+        x |= static_cast<unsigned long long>((b0 >> l) & 1u) << (2 * l);
+        x |= static_cast<unsigned long long>((b1 >> l) & 1u) << (2 * l + 1);
+      }
+      mask_out[w] = x;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// filter -> COUNT(*), SUM(col).  Block partials are combined by the last block to finish
+// (fixed order => deterministic double sum for a given grid).
+// ------------------------------------------------------------------------------------------
+struct CountSumOut {  // one per block, plus the final result in slot [gridDim.x]
+  unsigned long long count;
+  unsigned long long sum_lo;  // 128-bit two's complement
+  long long sum_hi;
+  double sum_f;
+};
+
+__device__ __forceinline__ void add128(unsigned long long& lo, long long& hi, long long v) {
+  const unsigned long long nlo = lo + static_cast<unsigned long long>(v);
+  hi += (v < 0 ? -1ll : 0ll) + (nlo < lo ? 1ll : 0ll);
+  lo = nlo;
+}
+__device__ __forceinline__ void add128u(unsigned long long& lo, long long& hi, unsigned long long alo, long long ahi) {
+  const unsigned long long nlo = lo + alo;
+  hi += ahi + (nlo < lo ? 1ll : 0ll);
+  lo = nlo;
+}
+
+__global__ void __launch_bounds__(256)
+filter_count_sum_kernel(const PredSet ps, const ColDev sum_col, int has_sum, uint64_t rows,
+                        CountSumOut* __restrict__ partials, unsigned int* __restrict__ done_counter) {
+  unsigned long long cnt = 0, lo = 0;
+  long long hi = 0;
+  double sf = 0.0;
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x * 2ull;
+  for (uint64_t r = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 2ull; r < rows; r += stride) {
+    const uint32_t m = preds2(ps, r, rows);
+    if (has_sum) {
+      uint32_t mv = m;
+      if (sum_col.validity) mv &= (col_valid(sum_col, r) ? 1u : 0u) | ((r + 1 < rows && col_valid(sum_col, r + 1)) ? 2u : 0u);
+      if (sum_col.type == 1) {
+        double a, b; load2_f64(sum_col, r, a, b);
+        if (mv & 1u) sf += a;
+        if (mv & 2u) sf += b;
+      } else {
+        long long a, b; load2_i64(sum_col, r, a, b);
+        if (mv & 1u) add128(lo, hi, a);
+        if (mv & 2u) add128(lo, hi, b);
+      }
+    }
+    cnt += __popc(m);
+  }
+  // warp reduce (128-bit add is associative; carry handled per step)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(kFull, cnt, o);
+    const unsigned long long olo = __shfl_xor_sync(kFull, lo, o);
+    const long long ohi = __shfl_xor_sync(kFull, hi, o);
+    add128u(lo, hi, olo, ohi);
+    sf += __shfl_xor_sync(kFull, sf, o);
+  }
+  __shared__ CountSumOut s[8];
+  __shared__ bool s_last;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  if (lane == 0) { s[warp].count = cnt; s[warp].sum_lo = lo; s[warp].sum_hi = hi; s[warp].sum_f = sf; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    CountSumOut t = s[0];
+    for (uint32_t w = 1; w < blockDim.x / 32u; ++w) {
+      t.count += s[w].count; add128u(t.sum_lo, t.sum_hi, s[w].sum_lo, s[w].sum_hi); t.sum_f += s[w].sum_f;
+    }
+    partials[blockIdx.x] = t;
+    __threadfence();
+    s_last = atomicAdd(done_counter, 1u) == gridDim.x - 1u;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    CountSumOut t = {0, 0, 0, 0.0};
+    for (uint32_t b = 0; b < gridDim.x; ++b) {
+      const volatile CountSumOut* p = partials + b;
+      t.count += p->count; add128u(t.sum_lo, t.sum_hi, p->sum_lo, p->sum_hi); t.sum_f += p->sum_f;
+    }
+    partials[gridDim.x] = t;
+    *done_counter = 0u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused filter -> GROUP BY key -> COUNT(*), SUM(int), SUM(double)/COUNT(double).
+// Dense group table indexed by key - key_min (DuckDB's perfect-hash aggregate when column
+// statistics bound the key range; the min/max come from the staged column's zonemap). The table is
+// 32 bytes per group = one L2 sector, updated with fire-and-forget RED atomics; at 1e5 groups it is
+// 3.2 MB and stays L2-resident while the 40 B/row column stream goes by.
+// ------------------------------------------------------------------------------------------
+struct GroupSlot {            // 32 bytes, one sector
+  unsigned long long count;   // COUNT(*)
+  long long sum_lo;           // SUM(int): low limb  (narrow mode: the whole sum)
+  long long sum_hi;           // SUM(int): high limb (wide mode: sum of v >> 32); cnt_f64 when avg col is nullable
+  double sum_f;               // SUM(double)
+};
+static_assert(sizeof(GroupSlot) == 32, "one L2 sector per group");
+
+struct GroupByParams {
+  PredSet ps;
+  ColDev key, sum_i, sum_f;
+  int32_t has_sum_i, has_sum_f;
+  int32_t wide_int;      // 1: values may exceed 32 bits => two limbs (lo = v & 0xFFFFFFFF, hi = v >> 32)
+  int32_t count_f;       // 1: avg column nullable => cnt_f64 kept in a side array
+  int64_t key_min;
+  uint64_t key_span;
+  uint64_t rows;
+  GroupSlot* table;
+  unsigned long long* cnt_f;   // [span] only when count_f
+  unsigned long long* out_of_range;  // rows whose key fell outside [key_min, key_min+span): must stay 0
+};
+
+__device__ __forceinline__ void group_update(const GroupByParams& P, long long key, long long v, bool v_ok,
+                                             double w, bool w_ok) {
+  const unsigned long long idx = static_cast<unsigned long long>(key - P.key_min);
+  if (idx >= P.key_span) { atomicAdd(P.out_of_range, 1ull); return; }
+  GroupSlot* g = P.table + idx;
+  atomicAdd(&g->count, 1ull);
+  if (P.has_sum_i && v_ok) {
+    if (P.wide_int) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(&g->sum_lo), static_cast<unsigned long long>(v) & 0xFFFFFFFFull);
+      atomicAdd(reinterpret_cast<unsigned long long*>(&g->sum_hi), static_cast<unsigned long long>(v >> 32));
+    } else {
+      atomicAdd(reinterpret_cast<unsigned long long*>(&g->sum_lo), static_cast<unsigned long long>(v));
+    }
+  }
+  if (P.has_sum_f && w_ok) {
+    atomicAdd(&g->sum_f, w);
+    if (P.count_f) atomicAdd(P.cnt_f + idx, 1ull);
+  }
+}
+
+template <int kUnroll>
+__global__ void __launch_bounds__(256)
+filter_groupby_kernel(const GroupByParams P) {
+  const uint64_t tile = uint64_t(blockDim.x) * 2ull * kUnroll;
+  for (uint64_t base = uint64_t(blockIdx.x) * tile; base < P.rows; base += uint64_t(gridDim.x) * tile) {
+    uint32_t m[kUnroll];
+    long long k0[kUnroll], k1[kUnroll], v0[kUnroll], v1[kUnroll];
+    double w0[kUnroll], w1[kUnroll];
+    // Issue every load of the tile before the first use (kUnroll * 5 independent 16-byte loads).
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint64_t r = base + (uint64_t(u) * blockDim.x + threadIdx.x) * 2ull;
+      m[u] = 0; k0[u] = k1[u] = v0[u] = v1[u] = 0; w0[u] = w1[u] = 0.0;
+      if (r < P.rows) {
+        m[u] = preds2(P.ps, r, P.rows);
+        load2_i64(P.key, r, k0[u], k1[u]);
+        if (P.has_sum_i) load2_i64(P.sum_i, r, v0[u], v1[u]);
+        if (P.has_sum_f) load2_f64(P.sum_f, r, w0[u], w1[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      if (!m[u]) continue;
+      const uint64_t r = base + (uint64_t(u) * blockDim.x + threadIdx.x) * 2ull;
+      bool vi0 = true, vi1 = true, wf0 = true, wf1 = true;
+      if (P.has_sum_i && P.sum_i.validity) { vi0 = col_valid(P.sum_i, r); vi1 = r + 1 < P.rows && col_valid(P.sum_i, r + 1); }
+      if (P.has_sum_f && P.sum_f.validity) { wf0 = col_valid(P.sum_f, r); wf1 = r + 1 < P.rows && col_valid(P.sum_f, r + 1); }
+      if (m[u] & 1u) group_update(P, k0[u], v0[u], vi0, w0[u], wf0);
+      if (m[u] & 2u) group_update(P, k1[u], v1[u], vi1, w1[u], wf1);
+    }
+  }
+}
+
+// Dense table -> flat partial buffers for a SUM all-reduce:
+// d_i64 = [count | sum_lo | sum_hi | cnt_f64] (4*span int64), d_f64 = [sum_f] (span float64).
+__global__ void __launch_bounds__(256)
+groupby_pack_kernel(const GroupSlot* __restrict__ table, const unsigned long long* __restrict__ cnt_f,
+                    uint64_t span, long long* __restrict__ d_i64, double* __restrict__ d_f64) {
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < span; i += uint64_t(gridDim.x) * blockDim.x) {
+    const GroupSlot g = table[i];
+    d_i64[i] = static_cast<long long>(g.count);
+    d_i64[span + i] = g.sum_lo;
+    d_i64[2 * span + i] = g.sum_hi;
+    d_i64[3 * span + i] = cnt_f ? static_cast<long long>(cnt_f[i]) : static_cast<long long>(g.count);
+    d_f64[i] = g.sum_f;
+  }
+}
+
+// Compact non-empty groups (ascending key) into rows {key, count, sum_i128, sum_f64, cnt_f64}.
+// wide: total = hi * 2^32 + lo (each limb sum exact in int64 for < 2^31 rows per group).
+struct GroupRowDev { long long key; unsigned long long count; unsigned long long sum_lo; long long sum_hi; double sum_f; unsigned long long cnt_f; };
+__global__ void __launch_bounds__(256)
+groupby_compact_kernel(const long long* __restrict__ d_i64, const double* __restrict__ d_f64, uint64_t span,
+                       long long key_min, int wide_int, GroupRowDev* __restrict__ out,
+                       unsigned long long* __restrict__ n_out, uint64_t cap) {
+  // Ordered compaction: one CTA walks the span in tiles and keeps a running offset (span is small:
+  // the dense path is only taken for bounded key ranges).
+  __shared__ unsigned long long s_base;
+  __shared__ uint32_t s_warp[8];
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  for (uint64_t t0 = 0; t0 < span; t0 += blockDim.x) {
+    const uint64_t i = t0 + threadIdx.x;
+    const bool live = i < span && d_i64[i] != 0;
+    const uint32_t bal = __ballot_sync(kFull, live);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+    for (uint32_t w = 0; w < blockDim.x / 32u; ++w) { if (w < warp) before += s_warp[w]; total += s_warp[w]; }
+    if (live) {
+      const unsigned long long pos = s_base + before + __popc(bal & ((1u << lane) - 1u));
+      if (pos < cap) {
+        GroupRowDev r;
+        r.key = key_min + static_cast<long long>(i);
+        r.count = static_cast<unsigned long long>(d_i64[i]);
+        const long long lo = d_i64[span + i], hi = d_i64[2 * span + i];
+        if (wide_int) {
+          // total = hi * 2^32 + lo as a 128-bit two's-complement value
+          unsigned long long rlo = static_cast<unsigned long long>(hi) << 32;
+          long long rhi = hi >> 32;
+          add128u(rlo, rhi, static_cast<unsigned long long>(lo), lo < 0 ? -1ll : 0ll);
+          r.sum_lo = rlo; r.sum_hi = rhi;
+        } else {
+          r.sum_lo = static_cast<unsigned long long>(lo); r.sum_hi = lo < 0 ? -1ll : 0ll;
+        }
+        r.sum_f = d_f64[i];
+        r.cnt_f = static_cast<unsigned long long>(d_i64[3 * span + i]);
+        out[pos] = r;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_base += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_out = s_base;
+}
+
+// min/max of an integer column (statistics gathered at staging: the reference keeps them per
+// column block in ColumnBlockMeta::statistics, column_reader.hpp:90-96).
+__global__ void __launch_bounds__(256)
+minmax_i64_kernel(const ColDev col, uint64_t rows, long long* __restrict__ out /* [2] = {min, max} */) {
+  long long mn = 0x7FFFFFFFFFFFFFFFll, mx = -0x7FFFFFFFFFFFFFFFll - 1;
+  for (uint64_t r = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < rows; r += uint64_t(gridDim.x) * blockDim.x) {
+    if (!col_valid(col, r)) continue;
+    const long long v = col.type == 2 ? static_cast<long long>(static_cast<const int*>(col.values)[r])
+                                      : static_cast<const long long*>(col.values)[r];
+    mn = min(mn, v); mx = max(mx, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(kFull, mn, o)); mx = max(mx, __shfl_xor_sync(kFull, mx, o)); }
+  if ((threadIdx.x & 31u) == 0) { atomicMin(out, mn); atomicMax(out + 1, mx); }
+}
+
+// ------------------------------------------------------------------------------------------
+// Synthetic column generator: splitmix64 finaliser over seed ^ (stream << 48) ^ index.
+// ------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ unsigned long long synth_hash(unsigned long long stream, unsigned long long index) {
+  unsigned long long z = (0x5EDB2026ull ^ (stream << 48) ^ index) + 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(256)
+synth_column_kernel(unsigned long long stream, int kind, uint64_t row0, uint64_t rows, void* __restrict__ out) {
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < rows; i += uint64_t(gridDim.x) * blockDim.x) {
+    const unsigned long long h = synth_hash(stream, row0 + i);
+    switch (kind) {
+      case 0: static_cast<long long*>(out)[i] = static_cast<long long>(h % 100000ull); break;
+      case 1: static_cast<long long*>(out)[i] = static_cast<long long>(h % 1000000ull); break;
+      case 2: static_cast<double*>(out)[i] = static_cast<double>(h >> 11) * 0x1.0p-53; break;
+      case 3: static_cast<long long*>(out)[i] = static_cast<long long>(h % 2001ull) - 1000ll; break;
+      case 4: static_cast<double*>(out)[i] = static_cast<double>(h >> 11) * 0x1.0p-53 * 1000.0; break;
+      case 6: static_cast<int*>(out)[i] = static_cast<int>(h % 1000000ull); break;
+      default: static_cast<long long*>(out)[i] = static_cast<long long>(h); break;
+    }
+  }
+}
+
+}  // namespace sdbg

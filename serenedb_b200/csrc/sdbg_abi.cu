@@ -1,0 +1,1079 @@
+// sdbg_abi.cu -- the C ABI of libsdbg.so (include/sdbg.h): contexts, staging into HBM, query
+// preparation and kernel launches. Host code only orchestrates; all per-posting / per-row work is
+// in bm25_kernels.cuh and column_kernels.cuh. There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/sdbg.h"
+#include "bm25_kernels.cuh"
+#include "column_kernels.cuh"
+#include "posting_format.hpp"
+
+using namespace sdbg;
+
+// ------------------------------------------------------------------------------------------
+// context / segment objects
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct DevBuf {  // grow-only device scratch
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct ColumnObj {
+  void* d_values = nullptr;
+  uint64_t* d_validity = nullptr;
+  int type = 0;
+  uint64_t rows = 0;
+  bool owned = true;
+  bool has_minmax = false;
+  int64_t mn = 0, mx = 0;
+};
+
+}  // namespace
+
+struct sdbg_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  DevBuf scratch[12];
+  void* h_pinned = nullptr;  // pinned host staging for small transfers
+  size_t h_pinned_cap = 0;
+  void* flush = nullptr;
+  size_t flush_bytes = 0;
+  bool topk_attr_set = false;
+  bool merge_attr_set = false;
+};
+
+struct sdbg_segment {
+  sdbg_ctx* ctx = nullptr;
+  uint32_t n_docs = 0;
+  // postings
+  void* d_arena = nullptr;
+  void* d_blocks = nullptr;
+  void* d_blkmax = nullptr;
+  std::vector<uint32_t> term_blk_begin, term_docs;
+  std::vector<MaxPair> term_max;
+  uint64_t arena_bytes = 0, n_blocks = 0, n_postings = 0;
+  bool has_wand = false;
+  // norms
+  void* d_norms = nullptr;
+  uint32_t norm_width = 0;
+  // columns
+  std::map<uint64_t, ColumnObj> cols;
+};
+
+struct sdbg_writer {
+  std::unique_ptr<PostingWriter> w;
+  std::vector<sdbg_term_meta> metas;
+};
+
+namespace {
+
+int fail(sdbg_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+#define CU(ctx, expr)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e_ = (expr);                                                                            \
+    if (e_ != cudaSuccess)                                                                              \
+      return fail((ctx), SDBG_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));              \
+  } while (0)
+
+int ensure(sdbg_ctx* c, DevBuf& b, size_t bytes) {
+  if (b.cap >= bytes) return SDBG_OK;
+  if (b.p) { cudaStreamSynchronize(c->stream); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+  const size_t want = std::max(bytes, size_t(1) << 20);
+  CU(c, cudaMalloc(&b.p, want));
+  b.cap = want;
+  return SDBG_OK;
+}
+int ensure_pinned(sdbg_ctx* c, size_t bytes) {
+  if (c->h_pinned_cap >= bytes) return SDBG_OK;
+  if (c->h_pinned) { cudaStreamSynchronize(c->stream); cudaFreeHost(c->h_pinned); c->h_pinned = nullptr; c->h_pinned_cap = 0; }
+  const size_t want = std::max(bytes, size_t(1) << 20);
+  CU(c, cudaMallocHost(&c->h_pinned, want));
+  c->h_pinned_cap = want;
+  return SDBG_OK;
+}
+
+__global__ void fill_u64_kernel(unsigned long long* p, size_t n, unsigned long long v) {
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) p[i] = v;
+}
+__global__ void flush_kernel(uint4* p, size_t n, uint32_t v) {
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+    p[i] = make_uint4(v, v, v, v);
+}
+
+uint32_t next_pow2(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
+
+int env_int(const char* name, int dflt) {
+  const char* s = std::getenv(name);
+  return s && *s ? std::atoi(s) : dflt;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// lifecycle
+// ------------------------------------------------------------------------------------------
+extern "C" const char* sdbg_version(void) { return "serenedb-b200 0.1 (sm_100a)"; }
+
+extern "C" int sdbg_init(int device, sdbg_ctx** out) {
+  if (!out) return SDBG_EINVAL;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return SDBG_ENODEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SDBG_ENODEVICE;
+  if (prop.major != 10) return SDBG_ENODEVICE;  // kernels are built for sm_100a only
+  auto* c = new sdbg_ctx;
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+    delete c;
+    return SDBG_ECUDA;
+  }
+  *out = c;
+  return SDBG_OK;
+}
+
+extern "C" void sdbg_destroy(sdbg_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& b : c->scratch) if (b.p) cudaFree(b.p);
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  if (c->flush) cudaFree(c->flush);
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+extern "C" const char* sdbg_last_error(const sdbg_ctx* c) { return c ? c->err.c_str() : "null context"; }
+extern "C" int sdbg_timer_start(sdbg_ctx* c) { CU(c, cudaSetDevice(c->device)); CU(c, cudaEventRecord(c->ev0, c->stream)); return SDBG_OK; }
+extern "C" int sdbg_timer_stop(sdbg_ctx* c, float* ms) {
+  CU(c, cudaEventRecord(c->ev1, c->stream));
+  CU(c, cudaEventSynchronize(c->ev1));
+  CU(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
+  return SDBG_OK;
+}
+extern "C" int sdbg_sync(sdbg_ctx* c) { CU(c, cudaStreamSynchronize(c->stream)); return SDBG_OK; }
+extern "C" uint64_t sdbg_launch_count(const sdbg_ctx* c) { return c ? c->launches : 0; }
+extern "C" int sdbg_flush_l2(sdbg_ctx* c) {
+  CU(c, cudaSetDevice(c->device));
+  if (!c->flush) { c->flush_bytes = size_t(256) << 20; CU(c, cudaMalloc(&c->flush, c->flush_bytes)); }
+  static uint32_t tick = 0;
+  flush_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(static_cast<uint4*>(c->flush), c->flush_bytes / 16, ++tick);
+  CU(c, cudaGetLastError());
+  return SDBG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// staging
+// ------------------------------------------------------------------------------------------
+extern "C" int sdbg_segment_create(sdbg_ctx* c, uint32_t docs_count, sdbg_segment** out) {
+  if (!c || !out) return SDBG_EINVAL;
+  auto* s = new sdbg_segment;
+  s->ctx = c; s->n_docs = docs_count;
+  *out = s;
+  return SDBG_OK;
+}
+
+namespace {
+void free_postings(sdbg_segment* s) {
+  if (s->d_arena) cudaFree(s->d_arena);
+  if (s->d_blocks) cudaFree(s->d_blocks);
+  if (s->d_blkmax) cudaFree(s->d_blkmax);
+  s->d_arena = s->d_blocks = s->d_blkmax = nullptr;
+}
+void free_column(ColumnObj& c) {
+  if (c.owned && c.d_values) cudaFree(c.d_values);
+  if (c.d_validity) cudaFree(c.d_validity);
+  c.d_values = nullptr; c.d_validity = nullptr;
+}
+}  // namespace
+
+extern "C" void sdbg_segment_destroy(sdbg_segment* s) {
+  if (!s) return;
+  cudaSetDevice(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  free_postings(s);
+  if (s->d_norms) cudaFree(s->d_norms);
+  for (auto& kv : s->cols) free_column(kv.second);
+  delete s;
+}
+
+namespace {
+int upload_postings(sdbg_segment* s, const StagedPostings& sp) {
+  sdbg_ctx* c = s->ctx;
+  CU(c, cudaSetDevice(c->device));
+  free_postings(s);
+  CU(c, cudaMalloc(&s->d_arena, std::max<size_t>(sp.arena.size(), 16)));
+  CU(c, cudaMalloc(&s->d_blocks, std::max<size_t>(sp.blocks.size() * sizeof(BlockDesc), 16)));
+  CU(c, cudaMalloc(&s->d_blkmax, std::max<size_t>(sp.blk_max.size() * sizeof(MaxPair), 16)));
+  CU(c, cudaMemcpyAsync(s->d_arena, sp.arena.data(), sp.arena.size(), cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(s->d_blocks, sp.blocks.data(), sp.blocks.size() * sizeof(BlockDesc), cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(s->d_blkmax, sp.blk_max.data(), sp.blk_max.size() * sizeof(MaxPair), cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  s->term_blk_begin = sp.term_blk_begin;
+  s->term_docs = sp.term_docs;
+  s->term_max = sp.term_max;
+  s->arena_bytes = sp.arena.size();
+  s->n_blocks = sp.blocks.size();
+  s->n_postings = sp.n_postings;
+  s->has_wand = sp.has_wand;
+  return SDBG_OK;
+}
+}  // namespace
+
+extern "C" int sdbg_stage_postings(sdbg_segment* s, const uint8_t* doc_file, size_t n, const sdbg_term_meta* terms,
+                                   size_t n_terms, int has_wand) {
+  if (!s || (!doc_file && n) || (!terms && n_terms)) return SDBG_EINVAL;
+  static_assert(sizeof(sdbg_term_meta) == sizeof(TermMeta), "ABI term meta mirrors the host struct");
+  StagedPostings sp;
+  const std::string e = stage_postings(doc_file, n, reinterpret_cast<const TermMeta*>(terms), n_terms, has_wand != 0, &sp);
+  if (!e.empty()) return fail(s->ctx, SDBG_EFORMAT, e);
+  for (size_t t = 0; t < n_terms; ++t)
+    if (terms[t].docs_count && sp.blocks[sp.term_blk_begin[t + 1] - 1].last_doc > s->n_docs)
+      return fail(s->ctx, SDBG_EFORMAT, "doc id beyond segment size");
+  return upload_postings(s, sp);
+}
+
+extern "C" int sdbg_stage_norms(sdbg_segment* s, const uint8_t* bytes, size_t n, const sdbg_norm_rg* rgs, size_t n_rg) {
+  if (!s || !bytes || !rgs || !n_rg) return SDBG_EINVAL;
+  sdbg_ctx* c = s->ctx;
+  // Row groups may differ in width (norm_column_reader.hpp:43-48); HBM holds one uniform width per
+  // segment (the widest) so a gather is a single indexed load.
+  uint32_t width = 1; uint64_t rows = 0;
+  for (size_t i = 0; i < n_rg; ++i) {
+    if (rgs[i].byte_size != 1 && rgs[i].byte_size != 2 && rgs[i].byte_size != 4) return fail(c, SDBG_EINVAL, "norm width must be 1, 2 or 4");
+    if (rgs[i].file_offset + uint64_t(rgs[i].row_count) * rgs[i].byte_size > n) return fail(c, SDBG_EINVAL, "norm row group beyond buffer");
+    width = std::max<uint32_t>(width, rgs[i].byte_size);
+    rows += rgs[i].row_count;
+  }
+  if (rows != s->n_docs) return fail(c, SDBG_EINVAL, "norm rows != segment docs");
+  std::vector<uint8_t> flat;
+  const uint8_t* src = bytes + rgs[0].file_offset;
+  if (!(n_rg == 1 && rgs[0].byte_size == width)) {
+    flat.resize(rows * width);
+    uint64_t r = 0;
+    for (size_t i = 0; i < n_rg; ++i)
+      for (uint32_t j = 0; j < rgs[i].row_count; ++j, ++r) {
+        uint32_t v = 0;
+        std::memcpy(&v, bytes + rgs[i].file_offset + size_t(j) * rgs[i].byte_size, rgs[i].byte_size);
+        std::memcpy(flat.data() + r * width, &v, width);
+      }
+    src = flat.data();
+  }
+  CU(c, cudaSetDevice(c->device));
+  if (s->d_norms) { cudaFree(s->d_norms); s->d_norms = nullptr; }
+  CU(c, cudaMalloc(&s->d_norms, rows * width + 16));
+  CU(c, cudaMemcpyAsync(s->d_norms, src, rows * width, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  s->norm_width = width;
+  return SDBG_OK;
+}
+
+namespace {
+size_t type_width(int t) { return t == SDBG_I32 ? 4 : 8; }
+}
+
+extern "C" int sdbg_stage_column(sdbg_segment* s, uint64_t field, sdbg_type t, const void* values,
+                                 const uint64_t* validity, uint64_t rows) {
+  if (!s || !values || t < 0 || t > 2) return SDBG_EINVAL;
+  sdbg_ctx* c = s->ctx;
+  CU(c, cudaSetDevice(c->device));
+  ColumnObj& col = s->cols[field];
+  const size_t bytes = rows * type_width(t);
+  if (!(col.owned && col.d_values && col.rows == rows && col.type == t)) {
+    free_column(col);
+    col = ColumnObj{};
+    CU(c, cudaMalloc(&col.d_values, bytes + 64));  // slack: row pairs are loaded as one 16-byte vector
+    CU(c, cudaMemsetAsync(static_cast<char*>(col.d_values) + bytes, 0, 64, c->stream));
+  }
+  col.type = t; col.rows = rows; col.owned = true; col.has_minmax = false;
+  CU(c, cudaMemcpyAsync(col.d_values, values, bytes, cudaMemcpyHostToDevice, c->stream));
+  if (validity) {
+    const size_t vb = ((rows + 63) / 64) * 8;
+    if (!col.d_validity) CU(c, cudaMalloc(reinterpret_cast<void**>(&col.d_validity), vb + 16));
+    CU(c, cudaMemcpyAsync(col.d_validity, validity, vb, cudaMemcpyHostToDevice, c->stream));
+  } else if (col.d_validity) {
+    cudaFree(col.d_validity); col.d_validity = nullptr;
+  }
+  return SDBG_OK;  // asynchronous on the context stream; consumers run on the same stream
+}
+
+extern "C" int sdbg_stage_column_device(sdbg_segment* s, uint64_t field, sdbg_type t, const void* d_values, uint64_t rows) {
+  if (!s || !d_values || t < 0 || t > 2) return SDBG_EINVAL;
+  if (rows & 1) return fail(s->ctx, SDBG_EINVAL, "borrowed device columns need an even row count (16-byte row pairs)");
+  ColumnObj& col = s->cols[field];
+  free_column(col);
+  col = ColumnObj{};
+  col.d_values = const_cast<void*>(d_values); col.type = t; col.rows = rows; col.owned = false;
+  return SDBG_OK;
+}
+
+extern "C" int sdbg_column_device_ptr(sdbg_segment* s, uint64_t field, void** d_values, uint64_t* rows) {
+  if (!s) return SDBG_EINVAL;
+  auto it = s->cols.find(field);
+  if (it == s->cols.end()) return fail(s->ctx, SDBG_ENOTFOUND, "unknown column");
+  if (d_values) *d_values = it->second.d_values;
+  if (rows) *rows = it->second.rows;
+  return SDBG_OK;
+}
+
+extern "C" int sdbg_segment_posting_stats(const sdbg_segment* s, uint64_t* payload_bytes, uint64_t* table_bytes,
+                                          uint64_t* n_blocks, uint64_t* n_postings) {
+  if (!s) return SDBG_EINVAL;
+  if (payload_bytes) *payload_bytes = s->arena_bytes;
+  if (table_bytes) *table_bytes = s->n_blocks * (sizeof(BlockDesc) + sizeof(MaxPair));
+  if (n_blocks) *n_blocks = s->n_blocks;
+  if (n_postings) *n_postings = s->n_postings;
+  return SDBG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// BM25 top-k
+// ------------------------------------------------------------------------------------------
+namespace {
+
+PostingsDev postings_view(const sdbg_segment* s, uint32_t ordinal_base) {
+  PostingsDev p;
+  p.arena = static_cast<const uint4*>(s->d_arena);
+  p.blocks = static_cast<const uint4*>(s->d_blocks);
+  p.blk_max = static_cast<const uint2*>(s->d_blkmax);
+  p.norms = static_cast<const uint8_t*>(s->d_norms);
+  p.norm_width = s->norm_width;
+  p.n_docs = s->n_docs;
+  p.ordinal_base = ordinal_base;
+  return p;
+}
+
+int filter_view(sdbg_segment* s, const sdbg_col_pred* f, FilterDev* out) {
+  std::memset(out, 0, sizeof *out);
+  if (!f) return SDBG_OK;
+  auto it = s->cols.find(f->field);
+  if (it == s->cols.end()) return fail(s->ctx, SDBG_ENOTFOUND, "filter column not staged");
+  if (it->second.rows < s->n_docs) return fail(s->ctx, SDBG_EINVAL, "filter column shorter than segment");
+  out->values = it->second.d_values; out->validity = it->second.d_validity; out->type = it->second.type;
+  out->op = f->op; out->lo_i = f->lo_i; out->hi_i = f->hi_i; out->lo_f = f->lo_f; out->hi_f = f->hi_f;
+  return SDBG_OK;
+}
+
+struct TopkPlan {
+  uint32_t W, n_windows_max, G, lists, cap, k;
+  size_t smem;
+};
+
+// Device-side result of a batch: keys_out[Q][k] (sorted desc, 0 = empty), n_out[Q], total[Q].
+struct TopkDevOut { unsigned long long* keys; uint32_t* n_out; unsigned long long* total; };
+
+int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25_term* terms, const uint32_t* term_off,
+             size_t nq, float k1, const sdbg_col_pred* filt, uint32_t k, float threshold_in, TopkDevOut* dev) {
+  if (!segs || !n_segs || !terms || !term_off || !nq || !k) return SDBG_EINVAL;
+  sdbg_ctx* c = segs[0]->ctx;
+  if (k > 8192) return fail(c, SDBG_EUNSUPPORTED, "k > 8192");
+  if (nq > 65535) return fail(c, SDBG_EUNSUPPORTED, "more than 65535 queries per batch");
+  CU(c, cudaSetDevice(c->device));
+  const uint32_t total_terms = term_off[nq];
+  for (size_t q = 0; q < nq; ++q) {
+    const uint32_t nt = term_off[q + 1] - term_off[q];
+    if (nt == 0 || nt > kMaxQueryTerms) return fail(c, SDBG_EUNSUPPORTED, "a query needs 1..16 terms");
+  }
+  uint64_t ord = 0;
+  for (size_t si = 0; si < n_segs; ++si) {
+    if (segs[si]->ctx != c) return fail(c, SDBG_EINVAL, "segments of one call must share a context");
+    if (!segs[si]->d_blocks) return fail(c, SDBG_EINVAL, "segment has no staged postings");
+    ord += segs[si]->n_docs;
+  }
+  if (ord >= 0xFFFFFFFFull) return fail(c, SDBG_EUNSUPPORTED, "more than 2^32-1 docs per GPU");
+
+  TopkPlan pl;
+  pl.k = k;
+  pl.W = uint32_t(env_int("SDBG_TOPK_WINDOW", 8192));
+  if (pl.W < 256 || (pl.W & 63)) return fail(c, SDBG_EINVAL, "SDBG_TOPK_WINDOW must be a multiple of 64, >= 256");
+  pl.cap = next_pow2(k + 1024);
+  uint32_t max_docs = 0;
+  for (size_t si = 0; si < n_segs; ++si) max_docs = std::max(max_docs, segs[si]->n_docs);
+  pl.n_windows_max = (max_docs + pl.W - 1) / pl.W;
+  const uint32_t target_ctas = uint32_t(c->sm_count) * 6u;
+  pl.G = uint32_t(std::max<size_t>(1, (target_ctas + nq - 1) / nq));
+  pl.G = std::min(pl.G, std::max(1u, pl.n_windows_max));
+  pl.G = std::min(pl.G, uint32_t(env_int("SDBG_TOPK_MAX_CHAINS", 296)));
+  pl.lists = pl.G * uint32_t(n_segs);
+  pl.smem = size_t(pl.W) * 4 + (kind == SDBG_QUERY_AND ? pl.W : 0) + pl.W / 8 + size_t(pl.cap) * 8;
+  if (pl.smem > 200 * 1024) return fail(c, SDBG_EUNSUPPORTED, "window + candidate buffer exceed shared memory");
+
+  // host-side query descriptors, per segment, sorted by ascending docs_count (conjunction.hpp:520-523)
+  const size_t qt_bytes = size_t(total_terms) * sizeof(QTermDev) * n_segs;
+  const size_t off_bytes = (nq + 1) * sizeof(uint32_t);
+  int rc = ensure_pinned(c, qt_bytes + off_bytes);
+  if (rc) return rc;
+  auto* h_qt = static_cast<QTermDev*>(c->h_pinned);
+  auto* h_off = reinterpret_cast<uint32_t*>(static_cast<char*>(c->h_pinned) + qt_bytes);
+  std::memcpy(h_off, term_off, off_bytes);
+  for (size_t si = 0; si < n_segs; ++si) {
+    const sdbg_segment* s = segs[si];
+    QTermDev* dst = h_qt + si * total_terms;
+    for (size_t q = 0; q < nq; ++q) {
+      const uint32_t b = term_off[q], e = term_off[q + 1];
+      for (uint32_t i = b; i < e; ++i) {
+        const sdbg_bm25_term& t = terms[i];
+        if (t.term + 1 >= s->term_blk_begin.size()) return fail(c, SDBG_EINVAL, "term id out of range");
+        QTermDev& d = dst[i];
+        d.blk_begin = s->term_blk_begin[t.term];
+        d.nblk = s->term_blk_begin[t.term + 1] - d.blk_begin;
+        d.c0 = t.boost * (k1 + 1) * t.idf;  // bm25.cpp:224
+        d.norm_const = t.norm_const; d.norm_length = t.norm_length;
+        d.docs_count = s->term_docs[t.term];
+        d.pad0 = d.pad1 = 0;
+      }
+      std::stable_sort(dst + b, dst + e, [](const QTermDev& x, const QTermDev& y) { return x.docs_count < y.docs_count; });
+    }
+  }
+  DevBuf& b_qt = c->scratch[0]; DevBuf& b_theta = c->scratch[1]; DevBuf& b_cand = c->scratch[2];
+  DevBuf& b_candn = c->scratch[3]; DevBuf& b_keys = c->scratch[4]; DevBuf& b_small = c->scratch[5];
+  if ((rc = ensure(c, b_qt, qt_bytes + off_bytes))) return rc;
+  if ((rc = ensure(c, b_theta, nq * 16))) return rc;  // theta[nq] | total[nq]
+  if ((rc = ensure(c, b_cand, nq * size_t(pl.lists) * pl.cap * 8))) return rc;
+  if ((rc = ensure(c, b_candn, nq * size_t(pl.lists) * 4))) return rc;
+  if ((rc = ensure(c, b_keys, nq * size_t(k) * 8))) return rc;
+  if ((rc = ensure(c, b_small, nq * 4))) return rc;
+  CU(c, cudaMemcpyAsync(b_qt.p, c->h_pinned, qt_bytes + off_bytes, cudaMemcpyHostToDevice, c->stream));
+  auto* d_theta = static_cast<unsigned long long*>(b_theta.p);
+  auto* d_total = d_theta + nq;
+  uint32_t thr_bits; std::memcpy(&thr_bits, &threshold_in, 4);
+  if (!(threshold_in >= 0.f)) thr_bits = 0;  // negative / NaN seeds accept every positive score
+  fill_u64_kernel<<<64, 256, 0, c->stream>>>(d_theta, nq, (static_cast<unsigned long long>(thr_bits) << 32) | 0xFFFFFFFFull);
+  ++c->launches;
+  CU(c, cudaMemsetAsync(d_total, 0, nq * 8, c->stream));
+
+  if (!c->topk_attr_set) {
+    CU(c, cudaFuncSetAttribute(bm25_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(c, cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    c->topk_attr_set = true;
+  }
+  uint32_t base = 0;
+  for (size_t si = 0; si < n_segs; ++si) {
+    sdbg_segment* s = segs[si];
+    TopkParams P;
+    P.seg = postings_view(s, base);
+    if ((rc = filter_view(s, filt, &P.filt))) return rc;
+    P.qterms = static_cast<const QTermDev*>(b_qt.p) + si * total_terms;
+    P.qterm_off = reinterpret_cast<const uint32_t*>(static_cast<const char*>(b_qt.p) + qt_bytes);
+    P.theta = d_theta; P.total = d_total;
+    P.cand = static_cast<unsigned long long*>(b_cand.p);
+    P.cand_n = static_cast<uint32_t*>(b_candn.p);
+    P.lists = pl.lists; P.list_base = uint32_t(si) * pl.G;
+    P.W = pl.W; P.n_windows = (s->n_docs + pl.W - 1) / pl.W;
+    P.k = k; P.cap = pl.cap; P.conjunction = kind == SDBG_QUERY_AND ? 1 : 0;
+    bm25_topk_kernel<<<dim3(pl.G, unsigned(nq)), kTopkThreads, pl.smem, c->stream>>>(P);
+    ++c->launches;
+    CU(c, cudaGetLastError());
+    base += s->n_docs;
+  }
+  MergeParams M;
+  M.cand = static_cast<const unsigned long long*>(b_cand.p);
+  M.cand_n = static_cast<const uint32_t*>(b_candn.p);
+  M.G = pl.lists; M.stride = pl.cap; M.k = k; M.cap = pl.cap;
+  M.keys_out = static_cast<unsigned long long*>(b_keys.p);
+  M.n_out = static_cast<uint32_t*>(b_small.p);
+  topk_merge_kernel<<<unsigned(nq), kTopkThreads, size_t(pl.cap) * 8, c->stream>>>(M);
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  dev->keys = M.keys_out; dev->n_out = M.n_out; dev->total = d_total;
+  return SDBG_OK;
+}
+
+// keys -> hits on the host. `bases` = first ordinal of each segment.
+void keys_to_hits(const unsigned long long* keys, uint32_t n, const std::vector<uint64_t>& bases, sdbg_hit* out) {
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t bits = uint32_t(keys[i] >> 32);
+    const uint32_t ordinal = ~uint32_t(keys[i]);
+    size_t seg = std::upper_bound(bases.begin(), bases.end(), uint64_t(ordinal) - 1) - bases.begin() - 1;
+    std::memcpy(&out[i].score, &bits, 4);
+    out[i].seg = uint32_t(seg);
+    out[i].doc = uint32_t(ordinal - bases[seg]);
+  }
+}
+
+}  // namespace
+
+extern "C" int sdbg_bm25_collect(uint64_t docs_with_field, uint64_t total_term_freq, uint64_t docs_with_term, float k, float b,
+                                 sdbg_bm25_term* out) {
+  if (!out || docs_with_term > docs_with_field) return SDBG_EINVAL;
+  // bm25.cpp:288-309, operation for operation (host code is built with -ffp-contract=off)
+  out->idf = float(std::log1p((double(docs_with_field - docs_with_term) + 0.5) / (double(docs_with_term) + 0.5)));
+  const float kb = k * b;
+  out->norm_const = k - kb;
+  if (total_term_freq && docs_with_field) {
+    const float avg_dl = float(total_term_freq) / float(docs_with_field);
+    out->norm_length = kb / avg_dl;
+  } else {
+    out->norm_length = kb;
+  }
+  out->boost = 1.f;
+  return SDBG_OK;
+}
+
+extern "C" int sdbg_bm25_topk_batch(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25_term* terms,
+                                    const uint32_t* term_off, size_t nq, float k1, const sdbg_col_pred* filt,
+                                    uint32_t k, float threshold_in, sdbg_hit* out, uint32_t* n_out,
+                                    uint64_t* total_matches) {
+  if (!out || !n_out) return SDBG_EINVAL;
+  TopkDevOut dev{};
+  int rc = topk_run(segs, n_segs, kind, terms, term_off, nq, k1, filt, k, threshold_in, &dev);
+  if (rc) return rc;
+  sdbg_ctx* c = segs[0]->ctx;
+  const size_t kb = nq * size_t(k) * 8, nb = nq * 4, tb = nq * 8;
+  // results come back through a dedicated pinned block (the query descriptors are done with by now)
+  if ((rc = ensure_pinned(c, kb + nb + tb + 64))) return rc;
+  char* h = static_cast<char*>(c->h_pinned);
+  CU(c, cudaMemcpyAsync(h, dev.keys, kb, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(h + kb, dev.total, tb, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(h + kb + tb, dev.n_out, nb, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  std::vector<uint64_t> bases(n_segs);
+  uint64_t b = 0;
+  for (size_t si = 0; si < n_segs; ++si) { bases[si] = b; b += segs[si]->n_docs; }
+  const auto* keys = reinterpret_cast<const unsigned long long*>(h);
+  const auto* tot = reinterpret_cast<const unsigned long long*>(h + kb);
+  const auto* cnt = reinterpret_cast<const uint32_t*>(h + kb + tb);
+  for (size_t q = 0; q < nq; ++q) {
+    n_out[q] = cnt[q];
+    keys_to_hits(keys + q * k, cnt[q], bases, out + q * k);
+    if (total_matches) total_matches[q] = tot[q];
+  }
+  return SDBG_OK;
+}
+
+extern "C" int sdbg_bm25_topk(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25_term* terms,
+                              size_t n_terms, float k1, const sdbg_col_pred* filt, uint32_t k, float threshold_in,
+                              sdbg_hit* out, uint32_t* n_out, uint64_t* total_matches, float* threshold_out) {
+  const uint32_t off[2] = {0, uint32_t(n_terms)};
+  uint64_t tot = 0;
+  const int rc = sdbg_bm25_topk_batch(segs, n_segs, kind, terms, off, 1, k1, filt, k, threshold_in, out, n_out, &tot);
+  if (rc) return rc;
+  if (total_matches) *total_matches = tot;
+  if (threshold_out) *threshold_out = (*n_out == k) ? out[k - 1].score : threshold_in;
+  return SDBG_OK;
+}
+
+namespace {
+__global__ void shift_keys_kernel(const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out, size_t n,
+                                  uint32_t add) {
+  // Re-bases ordinals for a cross-rank gather: ordinal' = ordinal + add (keys keep their order within a rank).
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    const unsigned long long k = in[i];
+    out[i] = k ? ((k & 0xFFFFFFFF00000000ull) | static_cast<unsigned long long>(~(~uint32_t(k) + add))) : 0ull;
+  }
+}
+}  // namespace
+
+extern "C" int sdbg_bm25_topk_batch_device(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25_term* terms,
+                                           const uint32_t* term_off, size_t nq, float k1, const sdbg_col_pred* filt,
+                                           uint32_t k, float threshold_in, uint32_t rank, void* d_keys, void* d_totals) {
+  if (!d_keys) return SDBG_EINVAL;
+  TopkDevOut dev{};
+  int rc = topk_run(segs, n_segs, kind, terms, term_off, nq, k1, filt, k, threshold_in, &dev);
+  if (rc) return rc;
+  sdbg_ctx* c = segs[0]->ctx;
+  // Each rank owns a 2^28-ordinal slot in the merged key space: rank r's docs sort after rank r-1's on ties.
+  uint64_t docs = 0;
+  for (size_t si = 0; si < n_segs; ++si) docs += segs[si]->n_docs;
+  if (docs >= (1ull << 28) || rank >= 15) return fail(c, SDBG_EUNSUPPORTED, "rank slot overflow (>= 2^28 docs per rank)");
+  shift_keys_kernel<<<256, 256, 0, c->stream>>>(dev.keys, static_cast<unsigned long long*>(d_keys), nq * size_t(k), rank << 28);
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  if (d_totals) CU(c, cudaMemcpyAsync(d_totals, dev.total, nq * 8, cudaMemcpyDeviceToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return SDBG_OK;
+}
+
+extern "C" int sdbg_topk_merge_gathered(sdbg_ctx* c, const void* d_keys_all, uint32_t n_ranks, size_t nq, uint32_t k,
+                                        sdbg_hit* out, uint32_t* n_out) {
+  if (!c || !d_keys_all || !out || !n_out || !n_ranks || !nq || !k) return SDBG_EINVAL;
+  CU(c, cudaSetDevice(c->device));
+  // gathered layout [rank][query][k]; the merge kernel wants [query][list][stride] -> stride trick:
+  // treat each rank's block as a list with a rank-major base pointer. Re-pack with a tiny kernel-free
+  // copy: n_ranks strided memcpy2D calls.
+  DevBuf& b_in = c->scratch[6]; DevBuf& b_keys = c->scratch[7]; DevBuf& b_small = c->scratch[8];
+  int rc;
+  if ((rc = ensure(c, b_in, nq * size_t(n_ranks) * k * 8))) return rc;
+  if ((rc = ensure(c, b_keys, nq * size_t(k) * 8))) return rc;
+  if ((rc = ensure(c, b_small, nq * 4))) return rc;
+  for (uint32_t r = 0; r < n_ranks; ++r)
+    CU(c, cudaMemcpy2DAsync(static_cast<char*>(b_in.p) + size_t(r) * k * 8, size_t(n_ranks) * k * 8,
+                            static_cast<const char*>(d_keys_all) + size_t(r) * nq * k * 8, size_t(k) * 8, size_t(k) * 8, nq,
+                            cudaMemcpyDeviceToDevice, c->stream));
+  const uint32_t cap = next_pow2(k + 1024);
+  if (!c->topk_attr_set) {
+    CU(c, cudaFuncSetAttribute(bm25_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(c, cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    c->topk_attr_set = true;
+  }
+  MergeParams M;
+  M.cand = static_cast<const unsigned long long*>(b_in.p); M.cand_n = nullptr;
+  M.G = n_ranks; M.stride = k; M.k = k; M.cap = cap;
+  M.keys_out = static_cast<unsigned long long*>(b_keys.p); M.n_out = static_cast<uint32_t*>(b_small.p);
+  topk_merge_kernel<<<unsigned(nq), kTopkThreads, size_t(cap) * 8, c->stream>>>(M);
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  const size_t kb = nq * size_t(k) * 8, nb = nq * 4;
+  if ((rc = ensure_pinned(c, kb + nb))) return rc;
+  char* h = static_cast<char*>(c->h_pinned);
+  CU(c, cudaMemcpyAsync(h, M.keys_out, kb, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(h + kb, M.n_out, nb, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  const auto* keys = reinterpret_cast<const unsigned long long*>(h);
+  const auto* cnt = reinterpret_cast<const uint32_t*>(h + kb);
+  for (size_t q = 0; q < nq; ++q) {
+    n_out[q] = cnt[q];
+    for (uint32_t i = 0; i < cnt[q]; ++i) {
+      const unsigned long long key = keys[q * k + i];
+      const uint32_t bits = uint32_t(key >> 32), ordinal = ~uint32_t(key);
+      sdbg_hit& h2 = out[q * k + i];
+      std::memcpy(&h2.score, &bits, 4);
+      h2.seg = ordinal >> 28;             // rank slot
+      h2.doc = ordinal & ((1u << 28) - 1);  // ordinal within the rank (segment base + doc)
+    }
+  }
+  return SDBG_OK;
+}
+
+extern "C" int sdbg_decode_score_term(sdbg_segment* s, uint32_t term, float c0, float nc, float nl, uint32_t* docs,
+                                      uint32_t* freqs, float* scores) {
+  if (!s || !docs || !freqs || !scores) return SDBG_EINVAL;
+  sdbg_ctx* c = s->ctx;
+  if (term + 1 >= s->term_blk_begin.size()) return fail(c, SDBG_EINVAL, "term id out of range");
+  CU(c, cudaSetDevice(c->device));
+  const uint32_t b0 = s->term_blk_begin[term], nblk = s->term_blk_begin[term + 1] - b0;
+  const uint32_t n = s->term_docs[term];
+  if (!n) return SDBG_OK;
+  const size_t slots = size_t(nblk) * 128;
+  int rc;
+  if ((rc = ensure(c, c->scratch[9], slots * 12))) return rc;
+  auto* d_docs = static_cast<uint32_t*>(c->scratch[9].p);
+  auto* d_freqs = d_docs + slots;
+  auto* d_scores = reinterpret_cast<float*>(d_freqs + slots);
+  const unsigned grid = unsigned(std::min<uint32_t>((nblk + kTopkWarps - 1) / kTopkWarps, uint32_t(c->sm_count) * 8u));
+  decode_score_kernel<<<grid, kTopkThreads, 0, c->stream>>>(postings_view(s, 0), b0, nblk, c0, nc, nl, d_docs, d_freqs, d_scores);
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  CU(c, cudaMemcpyAsync(docs, d_docs, size_t(n) * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(freqs, d_freqs, size_t(n) * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(scores, d_scores, size_t(n) * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return SDBG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// columnar
+// ------------------------------------------------------------------------------------------
+namespace {
+
+int col_view(sdbg_segment* s, uint64_t field, ColDev* out, uint64_t* rows) {
+  auto it = s->cols.find(field);
+  if (it == s->cols.end()) return fail(s->ctx, SDBG_ENOTFOUND, "column " + std::to_string(field) + " not staged");
+  out->values = it->second.d_values; out->validity = it->second.d_validity; out->type = it->second.type; out->pad = 0;
+  if (rows) *rows = it->second.rows;
+  return SDBG_OK;
+}
+
+int pred_set(sdbg_segment* s, const sdbg_col_pred* preds, size_t n, PredSet* ps, uint64_t* rows) {
+  if (n > size_t(kMaxPreds)) return fail(s->ctx, SDBG_EUNSUPPORTED, "more than 4 pushed predicates");
+  std::memset(ps, 0, sizeof *ps);
+  ps->n = int(n);
+  for (size_t i = 0; i < n; ++i) {
+    uint64_t r = 0;
+    const int rc = col_view(s, preds[i].field, &ps->p[i].col, &r);
+    if (rc) return rc;
+    if (*rows == 0) *rows = r;
+    if (r != *rows) return fail(s->ctx, SDBG_EINVAL, "columns of one segment differ in length");
+    if (preds[i].op < 0 || preds[i].op > 8) return fail(s->ctx, SDBG_EINVAL, "bad predicate op");
+    ps->p[i].op = preds[i].op;
+    ps->p[i].lo_i = preds[i].lo_i; ps->p[i].hi_i = preds[i].hi_i;
+    ps->p[i].lo_f = preds[i].lo_f; ps->p[i].hi_f = preds[i].hi_f;
+  }
+  return SDBG_OK;
+}
+
+int column_minmax(sdbg_segment* s, uint64_t field, int64_t* mn, int64_t* mx) {
+  sdbg_ctx* c = s->ctx;
+  auto it = s->cols.find(field);
+  if (it == s->cols.end()) return fail(c, SDBG_ENOTFOUND, "column not staged");
+  ColumnObj& col = it->second;
+  if (col.type == SDBG_F64) return fail(c, SDBG_EINVAL, "min/max statistics are kept for integer columns");
+  if (!col.has_minmax) {
+    int rc;
+    if ((rc = ensure(c, c->scratch[10], 16))) return rc;
+    const long long init[2] = {INT64_MAX, INT64_MIN};
+    CU(c, cudaMemcpyAsync(c->scratch[10].p, init, 16, cudaMemcpyHostToDevice, c->stream));
+    ColDev cd; cd.values = col.d_values; cd.validity = col.d_validity; cd.type = col.type; cd.pad = 0;
+    minmax_i64_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(cd, col.rows, static_cast<long long*>(c->scratch[10].p));
+    ++c->launches;
+    CU(c, cudaGetLastError());
+    long long res[2];
+    CU(c, cudaMemcpyAsync(res, c->scratch[10].p, 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    col.mn = res[0]; col.mx = res[1]; col.has_minmax = true;
+  }
+  *mn = col.mn; *mx = col.mx;
+  return SDBG_OK;
+}
+
+}  // namespace
+
+extern "C" int sdbg_column_minmax_i64(sdbg_segment* s, uint64_t field, int64_t* mn, int64_t* mx) {
+  if (!s || !mn || !mx) return SDBG_EINVAL;
+  CU(s->ctx, cudaSetDevice(s->ctx->device));
+  return column_minmax(s, field, mn, mx);
+}
+
+extern "C" int sdbg_filter_bitmap(sdbg_segment* s, const sdbg_col_pred* preds, size_t n_preds, uint64_t* mask_out) {
+  if (!s || !mask_out || (!preds && n_preds)) return SDBG_EINVAL;
+  sdbg_ctx* c = s->ctx;
+  CU(c, cudaSetDevice(c->device));
+  PredSet ps; uint64_t rows = 0;
+  int rc = pred_set(s, preds, n_preds, &ps, &rows);
+  if (rc) return rc;
+  if (!rows) rows = s->n_docs;
+  const size_t words = (rows + 63) / 64;
+  if ((rc = ensure(c, c->scratch[9], words * 8))) return rc;
+  const unsigned grid = unsigned(std::min<size_t>((words * 32 + 255) / 256, size_t(c->sm_count) * 8));
+  filter_bitmap_kernel<<<std::max(grid, 1u), 256, 0, c->stream>>>(ps, rows, static_cast<unsigned long long*>(c->scratch[9].p));
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  CU(c, cudaMemcpyAsync(mask_out, c->scratch[9].p, words * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return SDBG_OK;
+}
+
+extern "C" int sdbg_filter_count_sum(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred* preds, size_t n_preds,
+                                     uint64_t sum_field, uint64_t* count, int64_t sum_i128[2], double* sum_f64) {
+  if (!segs || !n_segs || !count || (!preds && n_preds)) return SDBG_EINVAL;
+  sdbg_ctx* c = segs[0]->ctx;
+  CU(c, cudaSetDevice(c->device));
+  const unsigned grid = unsigned(c->sm_count) * 4u;
+  int rc;
+  if ((rc = ensure(c, c->scratch[9], (size_t(grid) + 1) * sizeof(CountSumOut) * n_segs + 64))) return rc;
+  if ((rc = ensure(c, c->scratch[10], 16))) return rc;
+  CU(c, cudaMemsetAsync(c->scratch[10].p, 0, 16, c->stream));
+  if ((rc = ensure_pinned(c, n_segs * sizeof(CountSumOut)))) return rc;
+  for (size_t si = 0; si < n_segs; ++si) {
+    sdbg_segment* s = segs[si];
+    PredSet ps; uint64_t rows = 0;
+    if ((rc = pred_set(s, preds, n_preds, &ps, &rows))) return rc;
+    ColDev sc{}; int has_sum = 0;
+    if (sum_field != UINT64_MAX) {
+      uint64_t r = 0;
+      if ((rc = col_view(s, sum_field, &sc, &r))) return rc;
+      if (!rows) rows = r;
+      has_sum = 1;
+    }
+    if (!rows) rows = s->n_docs;
+    auto* part = static_cast<CountSumOut*>(c->scratch[9].p) + si * (size_t(grid) + 1);
+    filter_count_sum_kernel<<<grid, 256, 0, c->stream>>>(ps, sc, has_sum, rows, part, static_cast<unsigned int*>(c->scratch[10].p));
+    ++c->launches;
+    CU(c, cudaGetLastError());
+    CU(c, cudaMemcpyAsync(static_cast<CountSumOut*>(c->h_pinned) + si, part + grid, sizeof(CountSumOut), cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU(c, cudaStreamSynchronize(c->stream));
+  unsigned __int128 tot = 0; uint64_t cnt = 0; double sf = 0;
+  for (size_t si = 0; si < n_segs; ++si) {
+    const CountSumOut& o = static_cast<const CountSumOut*>(c->h_pinned)[si];
+    cnt += o.count; sf += o.sum_f;
+    tot += (static_cast<unsigned __int128>(static_cast<uint64_t>(o.sum_hi)) << 64) | o.sum_lo;
+  }
+  *count = cnt;
+  if (sum_i128) { sum_i128[0] = int64_t(uint64_t(tot)); sum_i128[1] = int64_t(uint64_t(tot >> 64)); }
+  if (sum_f64) *sum_f64 = sf;
+  return SDBG_OK;
+}
+
+namespace {
+
+struct GroupPlan { int wide_int = 0; int count_f = 0; };
+
+int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred* preds, size_t n_preds, uint64_t key_field,
+                   int64_t key_min, uint64_t span, uint64_t sum_int_field, uint64_t avg_f64_field, void* d_i64, void* d_f64,
+                   GroupPlan* plan_out) {
+  sdbg_ctx* c = segs[0]->ctx;
+  int rc;
+  // table | cnt_f | out_of_range
+  const size_t table_bytes = span * sizeof(GroupSlot);
+  if ((rc = ensure(c, c->scratch[11], table_bytes + span * 8 + 64))) return rc;
+  auto* table = static_cast<GroupSlot*>(c->scratch[11].p);
+  auto* cnt_f = reinterpret_cast<unsigned long long*>(static_cast<char*>(c->scratch[11].p) + table_bytes);
+  auto* oor = cnt_f + span;
+  CU(c, cudaMemsetAsync(c->scratch[11].p, 0, table_bytes + span * 8 + 64, c->stream));
+  GroupPlan plan;
+  uint64_t total_rows = 0;
+  for (size_t si = 0; si < n_segs; ++si) {  // statistics decide the accumulator shape
+    sdbg_segment* s = segs[si];
+    if (sum_int_field != UINT64_MAX) {
+      int64_t mn, mx;
+      if ((rc = column_minmax(s, sum_int_field, &mn, &mx))) return rc;
+      if (mn < INT32_MIN || mx > INT32_MAX) plan.wide_int = 1;
+    }
+    if (avg_f64_field != UINT64_MAX) {
+      auto it = s->cols.find(avg_f64_field);
+      if (it == s->cols.end()) return fail(c, SDBG_ENOTFOUND, "avg column not staged");
+      if (it->second.d_validity) plan.count_f = 1;
+    }
+    auto kit = s->cols.find(key_field);
+    if (kit == s->cols.end()) return fail(c, SDBG_ENOTFOUND, "key column not staged");
+    if (kit->second.d_validity) return fail(c, SDBG_EUNSUPPORTED, "nullable GROUP BY key");
+    if (kit->second.type == SDBG_F64) return fail(c, SDBG_EUNSUPPORTED, "float GROUP BY key");
+    total_rows += kit->second.rows;
+  }
+  if (total_rows >= (1ull << 31)) return fail(c, SDBG_EUNSUPPORTED, ">= 2^31 rows per GPU in one GROUP BY (limb overflow guard)");
+  for (size_t si = 0; si < n_segs; ++si) {
+    sdbg_segment* s = segs[si];
+    GroupByParams P;
+    std::memset(&P, 0, sizeof P);
+    uint64_t rows = 0;
+    if ((rc = pred_set(s, preds, n_preds, &P.ps, &rows))) return rc;
+    uint64_t r = 0;
+    if ((rc = col_view(s, key_field, &P.key, &r))) return rc;
+    if (!rows) rows = r;
+    if (r != rows) return fail(c, SDBG_EINVAL, "key column length differs");
+    if (sum_int_field != UINT64_MAX) {
+      if ((rc = col_view(s, sum_int_field, &P.sum_i, &r))) return rc;
+      if (P.sum_i.type == SDBG_F64) return fail(c, SDBG_EINVAL, "sum_int_field is a float column");
+      P.has_sum_i = 1;
+    }
+    if (avg_f64_field != UINT64_MAX) {
+      if ((rc = col_view(s, avg_f64_field, &P.sum_f, &r))) return rc;
+      if (P.sum_f.type != SDBG_F64) return fail(c, SDBG_EINVAL, "avg_f64_field is not a float column");
+      P.has_sum_f = 1;
+    }
+    P.wide_int = plan.wide_int; P.count_f = plan.count_f;
+    P.key_min = key_min; P.key_span = span; P.rows = rows;
+    P.table = table; P.cnt_f = cnt_f; P.out_of_range = oor;
+    const unsigned grid = unsigned(c->sm_count) * unsigned(env_int("SDBG_GROUPBY_CTAS_PER_SM", 8));
+    filter_groupby_kernel<2><<<grid, 256, 0, c->stream>>>(P);
+    ++c->launches;
+    CU(c, cudaGetLastError());
+  }
+  groupby_pack_kernel<<<c->sm_count * 2, 256, 0, c->stream>>>(table, plan.count_f ? cnt_f : nullptr, span,
+                                                               static_cast<long long*>(d_i64), static_cast<double*>(d_f64));
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  unsigned long long h_oor = 0;
+  CU(c, cudaMemcpyAsync(&h_oor, oor, 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (h_oor) return fail(c, SDBG_EINVAL, "GROUP BY key outside [key_min, key_min + span)");
+  if (plan_out) *plan_out = plan;
+  return SDBG_OK;
+}
+
+}  // namespace
+
+extern "C" int sdbg_filter_groupby_partial(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred* preds, size_t n_preds,
+                                           uint64_t key_field, int64_t key_min, uint64_t key_span, uint64_t sum_int_field,
+                                           uint64_t avg_f64_field, void* d_i64, void* d_f64) {
+  if (!segs || !n_segs || !d_i64 || !d_f64 || !key_span || (!preds && n_preds)) return SDBG_EINVAL;
+  CU(segs[0]->ctx, cudaSetDevice(segs[0]->ctx->device));
+  GroupPlan plan;
+  const int rc = groupby_launch(segs, n_segs, preds, n_preds, key_field, key_min, key_span, sum_int_field, avg_f64_field, d_i64, d_f64, &plan);
+  if (rc) return rc;
+  // Narrow sums are re-expressed as limbs so that every rank's buffers add up the same way.
+  return SDBG_OK;
+}
+
+extern "C" int sdbg_groupby_finalize(sdbg_ctx* c, int64_t key_min, uint64_t span, const void* d_i64, const void* d_f64,
+                                     sdbg_group_row* out, uint64_t cap, uint64_t* n_out) {
+  if (!c || !d_i64 || !d_f64 || !out || !n_out || !span) return SDBG_EINVAL;
+  CU(c, cudaSetDevice(c->device));
+  static_assert(sizeof(GroupRowDev) == sizeof(sdbg_group_row), "device row mirrors the ABI row");
+  int rc;
+  const uint64_t dev_cap = std::min<uint64_t>(cap, span);
+  if ((rc = ensure(c, c->scratch[9], dev_cap * sizeof(GroupRowDev) + 16))) return rc;
+  auto* d_n = reinterpret_cast<unsigned long long*>(static_cast<char*>(c->scratch[9].p) + dev_cap * sizeof(GroupRowDev));
+  // limbs: a narrow sum has hi == 0 everywhere, and hi*2^32 + lo is then just lo => always finalize "wide".
+  groupby_compact_kernel<<<1, 256, 0, c->stream>>>(static_cast<const long long*>(d_i64), static_cast<const double*>(d_f64), span,
+                                                   key_min, 1, static_cast<GroupRowDev*>(c->scratch[9].p), d_n, dev_cap);
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  unsigned long long n = 0;
+  CU(c, cudaMemcpyAsync(&n, d_n, 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  *n_out = n;
+  if (n > cap) return fail(c, SDBG_ECAPACITY, "group output buffer too small");
+  CU(c, cudaMemcpyAsync(out, c->scratch[9].p, n * sizeof(GroupRowDev), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return SDBG_OK;
+}
+
+extern "C" int sdbg_filter_groupby(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred* preds, size_t n_preds,
+                                   uint64_t key_field, uint32_t n_groups_hint, uint64_t sum_int_field, uint64_t avg_f64_field,
+                                   sdbg_group_row* out, uint64_t cap, uint64_t* n_out) {
+  (void)n_groups_hint;
+  if (!segs || !n_segs || !out || !n_out || (!preds && n_preds)) return SDBG_EINVAL;
+  sdbg_ctx* c = segs[0]->ctx;
+  CU(c, cudaSetDevice(c->device));
+  int64_t kmin = INT64_MAX, kmax = INT64_MIN;
+  for (size_t si = 0; si < n_segs; ++si) {
+    int64_t mn, mx;
+    const int rc = column_minmax(segs[si], key_field, &mn, &mx);
+    if (rc) return rc;
+    kmin = std::min(kmin, mn); kmax = std::max(kmax, mx);
+  }
+  if (kmin > kmax) { *n_out = 0; return SDBG_OK; }
+  const unsigned __int128 span128 = static_cast<unsigned __int128>(static_cast<__int128>(kmax) - kmin) + 1;
+  if (span128 > (static_cast<unsigned __int128>(1) << 26))
+    return fail(c, SDBG_EUNSUPPORTED, "GROUP BY key range > 2^26: the hash-table path is not built yet (dense path only)");
+  const uint64_t span = uint64_t(span128);
+  int rc;
+  if ((rc = ensure(c, c->scratch[8], span * 40 + 64))) return rc;
+  void* d_i64 = c->scratch[8].p;
+  void* d_f64 = static_cast<char*>(c->scratch[8].p) + span * 32;
+  GroupPlan plan;
+  if ((rc = groupby_launch(segs, n_segs, preds, n_preds, key_field, kmin, span, sum_int_field, avg_f64_field, d_i64, d_f64, &plan))) return rc;
+  return sdbg_groupby_finalize(c, kmin, span, d_i64, d_f64, out, cap, n_out);
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side writer mirror + synthetic inputs
+// ------------------------------------------------------------------------------------------
+extern "C" int sdbg_writer_create(uint32_t segment_docs, int has_wand, float wand_b, const uint32_t* norms, sdbg_writer** out) {
+  if (!out) return SDBG_EINVAL;
+  auto* w = new sdbg_writer;
+  w->w.reset(new PostingWriter(segment_docs, has_wand != 0, wand_b, norms));
+  *out = w;
+  return SDBG_OK;
+}
+extern "C" void sdbg_writer_destroy(sdbg_writer* w) { delete w; }
+extern "C" int sdbg_writer_add_term(sdbg_writer* w, const uint32_t* docs, const uint32_t* freqs, uint32_t n) {
+  if (!w || (n && (!docs || !freqs))) return SDBG_EINVAL;
+  for (uint32_t i = 1; i < n; ++i) if (docs[i] <= docs[i - 1]) return SDBG_EINVAL;
+  if (n && docs[0] == 0) return SDBG_EINVAL;
+  w->w->add_term(docs, freqs, n);
+  return SDBG_OK;
+}
+extern "C" int sdbg_writer_finish(sdbg_writer* w, const uint8_t** doc_file, size_t* n, const sdbg_term_meta** terms, size_t* n_terms) {
+  if (!w) return SDBG_EINVAL;
+  w->metas.clear();
+  for (const TermMeta& m : w->w->terms()) w->metas.push_back(sdbg_term_meta{m.docs_count, m.freq, m.doc_start, m.e_skip_start});
+  if (doc_file) *doc_file = w->w->bytes().data();
+  if (n) *n = w->w->bytes().size();
+  if (terms) *terms = w->metas.data();
+  if (n_terms) *n_terms = w->metas.size();
+  return SDBG_OK;
+}
+
+extern "C" uint64_t sdbg_synth_hash(uint64_t stream, uint64_t index) { return synth_hash(stream, index); }
+
+extern "C" int sdbg_synth_corpus(sdbg_segment* seg, uint64_t doc0, uint32_t n_docs, uint32_t t0, uint32_t nt, int threads,
+                                 uint32_t* docs_count_out, uint64_t* sum_dl_out) {
+  if (!seg || !n_docs || !nt || n_docs != seg->n_docs) return SDBG_EINVAL;
+  threads = std::max(1, threads);
+  std::vector<uint32_t> dl(n_docs);
+  uint64_t sum_dl = 0;
+  for (uint32_t i = 0; i < n_docs; ++i) { dl[i] = 16 + uint32_t(synth_hash(1, doc0 + 1 + i) % 240); sum_dl += dl[i]; }
+  // one writer per term (terms are independent streams), built by a pool of threads, then
+  // concatenated in term order -- byte-identical to a single sequential writer.
+  std::vector<std::unique_ptr<PostingWriter>> per_term(nt);
+  std::atomic<uint32_t> next{0};
+  const float avg = float(double(sum_dl) / double(n_docs));
+  auto work = [&]() {
+    std::vector<uint32_t> docs, freqs;
+    for (;;) {
+      const uint32_t i = next.fetch_add(1);
+      if (i >= nt) break;
+      const uint32_t t = t0 + i;
+      const double p = std::min(0.5, 0.6 / double(t + 1));
+      const uint64_t thr = uint64_t(std::ldexp(p, 64));
+      docs.clear(); freqs.clear();
+      for (uint32_t d = 0; d < n_docs; ++d) {
+        const uint64_t g = doc0 + 1 + d;
+        if (synth_hash(100 + t, g) >= thr) continue;
+        const uint64_t h2 = synth_hash(1000 + t, g);
+        uint32_t f = 1 + (h2 ? uint32_t(__builtin_ctzll(h2)) : 64);
+        f = std::min(f, dl[d]);
+        docs.push_back(d + 1); freqs.push_back(f);
+      }
+      per_term[i].reset(new PostingWriter(n_docs, true, 0.75f, dl.data(), avg));
+      per_term[i]->add_term(docs.data(), freqs.data(), uint32_t(docs.size()));
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int i = 0; i < threads; ++i) pool.emplace_back(work);
+  for (auto& th : pool) th.join();
+  PostingWriter all(n_docs, true, 0.75f, dl.data(), avg);
+  for (uint32_t i = 0; i < nt; ++i) {
+    all.append(*per_term[i]);
+    if (docs_count_out) docs_count_out[i] = per_term[i]->terms()[0].docs_count;
+    per_term[i].reset();
+  }
+  if (sum_dl_out) *sum_dl_out = sum_dl;
+  int rc = sdbg_stage_postings(seg, all.bytes().data(), all.bytes().size(),
+                               reinterpret_cast<const sdbg_term_meta*>(all.terms().data()), all.terms().size(), 1);
+  if (rc) return rc;
+  std::vector<uint8_t> nb(n_docs);
+  for (uint32_t i = 0; i < n_docs; ++i) nb[i] = uint8_t(dl[i]);
+  const sdbg_norm_rg rg{1, n_docs, 0};
+  return sdbg_stage_norms(seg, nb.data(), nb.size(), &rg, 1);
+}
+
+extern "C" int sdbg_synth_column(sdbg_segment* seg, uint64_t field, uint64_t stream, int kind, uint64_t row0, uint64_t rows) {
+  if (!seg || !rows) return SDBG_EINVAL;
+  sdbg_ctx* c = seg->ctx;
+  CU(c, cudaSetDevice(c->device));
+  const int type = (kind == 2 || kind == 4) ? SDBG_F64 : (kind == 6 ? SDBG_I32 : SDBG_I64);
+  ColumnObj& col = seg->cols[field];
+  free_column(col);
+  col = ColumnObj{};
+  const size_t bytes = rows * type_width(type);
+  CU(c, cudaMalloc(&col.d_values, bytes + 64));
+  CU(c, cudaMemsetAsync(static_cast<char*>(col.d_values) + bytes, 0, 64, c->stream));
+  col.type = type; col.rows = rows; col.owned = true;
+  synth_column_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(stream, kind, row0, rows, col.d_values);
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  return SDBG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Host-only probe of the staging parser (no device needed): lets CPU tests compare the block table
+// built from a ".doc" stream with the oracle's reading of the same bytes.
+// ------------------------------------------------------------------------------------------
+extern "C" int sdbg_debug_stage_host(const uint8_t* doc_file, size_t n, const sdbg_term_meta* terms, size_t n_terms, int has_wand,
+                                     uint32_t cap, uint32_t* n_blocks, uint32_t* term_blk_begin /* n_terms+1 */,
+                                     uint32_t* last_doc, uint32_t* prev_last, uint32_t* packed, uint32_t* max_freq,
+                                     uint32_t* max_norm, uint64_t* arena_bytes) {
+  StagedPostings sp;
+  const std::string e = stage_postings(doc_file, n, reinterpret_cast<const TermMeta*>(terms), n_terms, has_wand != 0, &sp);
+  if (!e.empty()) { std::fprintf(stderr, "sdbg_debug_stage_host: %s\n", e.c_str()); return SDBG_EFORMAT; }
+  if (n_blocks) *n_blocks = uint32_t(sp.blocks.size());
+  if (arena_bytes) *arena_bytes = sp.arena.size();
+  if (term_blk_begin) std::copy(sp.term_blk_begin.begin(), sp.term_blk_begin.end(), term_blk_begin);
+  if (sp.blocks.size() > cap) return SDBG_ECAPACITY;
+  for (size_t i = 0; i < sp.blocks.size(); ++i) {
+    if (last_doc) last_doc[i] = sp.blocks[i].last_doc;
+    if (prev_last) prev_last[i] = sp.blocks[i].prev_last;
+    if (packed) packed[i] = sp.blocks[i].packed;
+    if (max_freq) max_freq[i] = sp.blk_max[i].freq;
+    if (max_norm) max_norm[i] = sp.blk_max[i].norm;
+  }
+  return SDBG_OK;
+}

@@ -1,0 +1,151 @@
+"""GPU parity: columnar filter bitmap / COUNT / SUM / GROUP BY through the C ABI vs the CPU oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import orc
+import serenedb_b200 as sdb
+from gpu_util import ctx
+
+pytestmark = pytest.mark.gpu
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bm25_goldens.json")))
+K, A, B, V, W = 10, 11, 12, 13, 14
+
+
+def _table(rows, row0=0):
+    cols = {K: orc.synth_column(10, 0, row0, rows), A: orc.synth_column(11, 1, row0, rows),
+            B: orc.synth_column(12, 2, row0, rows), V: orc.synth_column(13, 3, row0, rows),
+            W: orc.synth_column(14, 4, row0, rows)}
+    oseg = orc.Segment(rows, has_wand=False)
+    gseg = sdb.Segment(ctx(), rows)
+    for f, v in cols.items():
+        oseg.add_column(f, v)
+        gseg.stage_column(f, v)
+    return oseg, gseg, cols
+
+
+def test_synth_column_kernel_matches_oracle_generator():
+    rows = 100_001
+    g = sdb.Segment(ctx(), rows)
+    import torch
+    for field, (stream, kind) in {K: (10, 0), A: (11, 1), B: (12, 2), V: (13, 3), W: (14, 4), 20: (15, 5), 21: (2, 6)}.items():
+        g.synth_column(field, stream, kind, 7, rows)
+    ctx().sync()
+    exp = {K: orc.synth_column(10, 0, 7, rows), B: orc.synth_column(12, 2, 7, rows), W: orc.synth_column(14, 4, 7, rows)}
+    # read back through a filter-free count/sum: SUM(int) exact, and bitmaps of thresholds exact
+    scan = sdb.IResearchScan([g])
+    cnt, si, _ = scan.count_sum([], K)
+    assert cnt == rows and si == int(exp[K].sum())
+    m = g.filter_bitmap([sdb.pred(B, "LT", 0.25)], rows)
+    assert np.array_equal(np.unpackbits(m.view(np.uint8), bitorder="little")[:rows].astype(bool), exp[B] < 0.25)
+    m = g.filter_bitmap([sdb.pred(W, "GE", 500.0)], rows)
+    assert np.array_equal(np.unpackbits(m.view(np.uint8), bitorder="little")[:rows].astype(bool), exp[W] >= 500.0)
+
+
+@pytest.mark.parametrize("rows", [1, 2, 63, 64, 65, 1000, 1 << 20, (1 << 20) + 3])
+def test_filter_bitmap_and_count_sum(rows):
+    """config 1 shape: single filter + COUNT/SUM over int64 and float64 columns; bit-exact bitmaps."""
+    oseg, gseg, cols = _table(rows)
+    scan = sdb.IResearchScan([gseg])
+    for preds_g, preds_o in [([sdb.pred(A, "LT", 250000)], [orc.make_pred(A, "LT", 250000)]),
+                             ([sdb.pred(B, "LT", 0.25)], [orc.make_pred(B, "LT", 0.25, is_float=True)]),
+                             ([sdb.pred(A, "LT", 500000), sdb.pred(B, "GE", 0.25)],
+                              [orc.make_pred(A, "LT", 500000), orc.make_pred(B, "GE", 0.25, is_float=True)]),
+                             ([sdb.pred(V, "BETWEEN", -10, 10), sdb.pred(A, "NE", 7), sdb.pred(K, "GT", 100), sdb.pred(W, "LE", 999.0)],
+                              [orc.make_pred(V, "BETWEEN", -10, 10), orc.make_pred(A, "NE", 7), orc.make_pred(K, "GT", 100),
+                               orc.make_pred(W, "LE", 999.0, is_float=True)])]:
+        gm = gseg.filter_bitmap(preds_g, rows)
+        om = orc.filter_bitmap(oseg, preds_o, rows)
+        assert np.array_equal(gm, om)
+        c1, s1, _ = scan.count_sum(preds_g, A)
+        c2, s2, _ = orc.filter_count_sum([oseg], preds_o, A)
+        assert (c1, s1) == (c2, s2)
+        c1, _, f1 = scan.count_sum(preds_g, W)
+        c2, _, f2 = orc.filter_count_sum([oseg], preds_o, W)
+        assert c1 == c2 and f1 == pytest.approx(f2, rel=1e-9, abs=1e-9)
+
+
+def test_sum_int64_is_exact_128_bit():
+    rows = 300_000
+    big = np.full(rows, np.iinfo(np.int64).max - 5, np.int64)
+    big[::3] = np.iinfo(np.int64).min + 9
+    oseg = orc.Segment(rows, has_wand=False)
+    gseg = sdb.Segment(ctx(), rows)
+    key = (np.arange(rows) % 7).astype(np.int64)
+    for f, v in ((1, big), (2, key)):
+        oseg.add_column(f, v)
+        gseg.stage_column(f, v)
+    scan = sdb.IResearchScan([gseg])
+    c, s, _ = scan.count_sum([], 1)
+    assert c == rows and s == int(big.astype(object).sum())
+    rows_g = scan.groupby([], 2, sum_int_field=1)
+    exp = {int(k): int(big[key == k].astype(object).sum()) for k in range(7)}
+    assert {int(r["key"]): v for r, v in zip(rows_g, sdb.sum_i128(rows_g))} == exp
+
+
+def test_scan_10k_goldens_on_gpu():
+    segs = []
+    for s in range(3):
+        x = np.arange(8000 * s, 8000 * (s + 1), dtype=np.int64)
+        g = sdb.Segment(ctx(), 8000)
+        g.stage_column(1, x)
+        if s == 0:
+            g.stage_column(3, np.zeros(8000, np.int64), validity=np.zeros(125, np.uint64))
+        else:
+            g.stage_column(3, x)
+        segs.append(g)
+    scan = sdb.IResearchScan(segs)
+    P = sdb.pred
+    assert scan.count_sum([])[0] == 24000
+    assert scan.count_sum([P(1, "GE", 20000)])[0] == 4000
+    assert scan.count_sum([P(1, "LT", 0)])[0] == 0
+    assert scan.count_sum([P(3, "IS_NULL")])[0] == 8000
+    assert scan.count_sum([P(3, "IS_NOT_NULL")])[0] == 16000
+    assert scan.count_sum([P(1, "BETWEEN", 12000, 12099)], 1)[:2] == (100, 1204950)
+    assert scan.count_sum([P(1, "GE", 8000), P(3, "IS_NOT_NULL")])[0] == 16000
+
+
+@pytest.mark.parametrize("rows", [1000, 2_000_001])
+def test_groupby_matches_oracle(rows):
+    """config 2 shape: 2 predicates -> GROUP BY k -> COUNT, SUM(v) exact, AVG(w) within 1e-5 rel."""
+    oseg, gseg, cols = _table(rows)
+    scan = sdb.IResearchScan([gseg])
+    gp = [sdb.pred(A, "LT", 500000), sdb.pred(B, "GE", 0.25)]
+    op = [orc.make_pred(A, "LT", 500000), orc.make_pred(B, "GE", 0.25, is_float=True)]
+    got = scan.groupby(gp, K, sum_int_field=V, avg_f64_field=W, n_groups_hint=100000)
+    exp = orc.filter_groupby([oseg], op, K, V, W, cap=100001)
+    assert np.array_equal(got["key"], exp["key"])
+    assert np.array_equal(got["count"], exp["count"])
+    assert np.array_equal(got["sum_lo"], exp["sum_lo"]) and np.array_equal(got["sum_hi"], exp["sum_hi"])
+    assert np.array_equal(got["cnt_f64"], exp["cnt_f64"])
+    avg_g = got["sum_f64"] / got["cnt_f64"]
+    avg_o = exp["sum_f64"] / exp["cnt_f64"]
+    assert np.allclose(avg_g, avg_o, rtol=1e-5, atol=0)   # north_star tolerance for AVG
+    sel = (cols[A] < 500000) & (cols[B] >= 0.25)
+    assert int(got["count"].sum()) == int(sel.sum())
+
+
+def test_groupby_nulls_and_multisegment():
+    rows = 50_000
+    rng = np.random.default_rng(9)
+    segs_o, segs_g = [], []
+    for s in range(2):
+        key = rng.integers(-50, 50, size=rows).astype(np.int64)
+        v = rng.integers(-2**40, 2**40, size=rows).astype(np.int64)      # needs two limbs
+        w = rng.random(rows)
+        vv = rng.integers(0, 2**63, size=(rows + 63) // 64, dtype=np.int64).astype(np.uint64)  # ~half NULL
+        wv = rng.integers(0, 2**63, size=(rows + 63) // 64, dtype=np.int64).astype(np.uint64)
+        o = orc.Segment(rows, has_wand=False)
+        g = sdb.Segment(ctx(), rows)
+        for f, (vals, valid) in {1: (key, None), 2: (v, vv), 3: (w, wv)}.items():
+            o.add_column(f, vals, valid)
+            g.stage_column(f, vals, valid)
+        segs_o.append(o)
+        segs_g.append(g)
+    got = sdb.IResearchScan(segs_g).groupby([sdb.pred(1, "NE", 0)], 1, sum_int_field=2, avg_f64_field=3)
+    exp = orc.filter_groupby(segs_o, [orc.make_pred(1, "NE", 0)], 1, 2, 3, cap=1000)
+    for f in ("key", "count", "sum_lo", "sum_hi", "cnt_f64"):
+        assert np.array_equal(got[f], exp[f]), f
+    assert np.allclose(got["sum_f64"], exp["sum_f64"], rtol=1e-9)
