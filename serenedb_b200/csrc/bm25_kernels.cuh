@@ -349,10 +349,16 @@ bm25_topk_kernel(const TopkParams P) {
     plan_window(w + G, buf ^ 1u);  // warp 0 plans the next window, then joins the work below
 
     // ---- accumulate: one 128-posting block per warp iteration ----
-    const uint32_t n_items = s_prefix[buf][T];
-    for (uint32_t it = warp; it < n_items; it += kTopkWarps) {
-      uint32_t t = 0;
-      while (t + 1u < T && it >= s_prefix[buf][t + 1u]) ++t;
+    // fp32 addition commutes, so two terms may add into a slot in any order; with three or more
+    // the sum order matters, so terms are processed in phases of ascending cost (the order
+    // ConjunctionScore uses, conjunction.hpp:185-195) to keep scores bit-reproducible.
+    const uint32_t phases = T > 2u ? T : 1u;
+    for (uint32_t ph = 0; ph < phases; ++ph) {
+    const uint32_t it_begin = phases > 1u ? s_prefix[buf][ph] : 0u;
+    const uint32_t it_end = phases > 1u ? s_prefix[buf][ph + 1u] : s_prefix[buf][T];
+    for (uint32_t it = it_begin + warp; it < it_end; it += kTopkWarps) {
+      uint32_t t = ph;
+      if (phases == 1u) { t = 0; while (t + 1u < T && it >= s_prefix[buf][t + 1u]) ++t; }
       const uint32_t b = s_first[buf][t] + (it - s_prefix[buf][t]);
       const uint4 d = ld_ro_v4(P.seg.blocks + qt[t].blk_begin + b);
       uint32_t doc[4], f[4];
@@ -376,6 +382,8 @@ bm25_topk_kernel(const TopkParams P) {
           if (P.conjunction) atomicAdd(reinterpret_cast<uint32_t*>(cnt) + (off >> 2), 1u << (8u * (off & 3u)));
         }
       }
+    }
+    if (ph + 1u < phases) __syncthreads();
     }
     __syncthreads();
 
