@@ -1,0 +1,491 @@
+#!/usr/bin/env python
+"""bench.py -- the hot-path benchmark (contract in the task brief, metric from BASELINE.json).
+
+Headline (N=1): BASELINE.json configs[1] -- 100 M-row, 8-column synthetic table, 2 predicates ->
+GROUP BY (1e5 keys) SUM/AVG/COUNT, in Mrows/s. The same JSON line carries a `bm25` object for
+configs[2] -- 10 M-doc synthetic Zipf corpus, batch of two-term disjunctive BM25 top-1000 queries, in
+Mdocs/s (postings scanned per second) -- because BASELINE.json's metric names both.
+
+  value     whole step with inputs resident in HBM, device-timed on the library's stream
+  e2e       the same metric through the public host API with HOST buffers (H2D of the step's inputs
+            from pinned memory + D2H of the results inside the timed region)
+  roofline  dominant kernel: algorithmic bytes per launch / CUDA-event duration vs MEASURED_PEAKS.json
+  cpu_baseline / --impl reference
+            the CPU oracle (oracle/, a restatement of the reference's operators: the reference itself
+            needs clang-21 + DuckDB + Abseil and cannot be built here) on the box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+K, A, B, V, W_ = 10, 11, 12, 13, 14          # field ids of the referenced columns k, a, b, v, w
+COLS = {K: (10, 0, np.int64), A: (11, 1, np.int64), B: (12, 2, np.float64), V: (13, 3, np.int64), W_: (14, 4, np.float64)}
+UNREFERENCED = {15: (15, 5), 16: (16, 5), 17: (17, 5)}  # c5..c7: part of the 8-column table, never read
+N_TERMS = 256
+TOPK = 1000
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks line sampled while a timed region runs."""
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def __enter__(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device),
+                 "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        try:
+            rows = [l.strip().split(", ") for l in open(self.path) if l.strip()]
+            os.unlink(self.path)
+            sm = [float(r[0]) for r in rows]
+            out["sm_mhz"] = float(np.median(sm)) if sm else None
+            out["sm_max_mhz"] = float(rows[0][1]) if rows else None
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for i, nme in enumerate(names):
+                if any(r[3 + i].strip().lower().startswith("active") for r in rows):
+                    out["reasons"].append(nme)
+            out["samples"] = len(rows)
+        except Exception:
+            pass
+        return out
+
+
+def merge_clocks(a, b):
+    if not a.get("samples"):
+        return b
+    if not b.get("samples"):
+        return a
+    return {"sm_mhz": float(np.median([a["sm_mhz"], b["sm_mhz"]])), "sm_max_mhz": a["sm_max_mhz"],
+            "reasons": sorted(set(a["reasons"]) | set(b["reasons"])), "samples": a["samples"] + b["samples"]}
+
+
+def make_queries(nq):
+    """Two-term disjunctions, pairs drawn from the 256 synthetic terms; query 0 is the named
+    case p = (0.10, 0.01) => terms 5 and 59."""
+    import serenedb_b200._native as N
+    h = N.lib().sdbg_synth_hash
+    qs = [[5, 59]]
+    i = 0
+    while len(qs) < nq:
+        a = h(7, 2 * i) % N_TERMS
+        b = h(7, 2 * i + 1) % N_TERMS
+        i += 1
+        if a != b:
+            qs.append([int(a), int(b)])
+    return qs
+
+
+# --------------------------------------------------------------------------------------------
+# CPU legs (the oracle; the only place bench.py touches oracle/)
+# --------------------------------------------------------------------------------------------
+def cpu_groupby(host_cols, rows, threads, reps):
+    import orc
+    seg = orc.Segment(rows, has_wand=False)
+    for f, arr in host_cols.items():
+        seg.add_column(f, arr[:rows])
+    preds = [orc.make_pred(A, "LT", 500000), orc.make_pred(B, "GE", 0.25, is_float=True)]
+    times = []
+    out = None
+    for _ in range(reps):
+        t = time.perf_counter()
+        out = orc.filter_groupby([seg], preds, K, V, W_, cap=100001, threads=threads)
+        times.append(time.perf_counter() - t)
+    return out, times
+
+
+def cpu_bm25_setup(n_docs, threads):
+    import orc
+    orc.use_simdcomp_ref(True)  # decode 128-value blocks with the reference's own SSE simdcomp when oracle/_ref exists
+    seg, dc, sum_dl = orc.synth_segment_mt(n_docs, 0, N_TERMS, doc0=0, threads=threads)
+    return seg, dc, sum_dl
+
+
+def cpu_bm25(seg, dc, sum_dl, n_docs, queries, threads, mode=2):
+    import orc
+    qt = []
+    for q in queries:
+        ts = []
+        for t in q:
+            st = orc.bm25_stats(n_docs, sum_dl, int(dc[t]))
+            x = orc.BM25Term()
+            x.idf, x.norm_const, x.norm_length, x.boost, x.term = st.idf, st.norm_const, st.norm_length, 1.0, t
+            ts.append(x)
+        qt.append(ts)
+    t = time.perf_counter()
+    hits, n_out, total, scored = orc.bm25_topk_batch([seg], "OR", qt, TOPK, mode=mode, threads=threads)
+    return time.perf_counter() - t, hits, n_out, scored
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# --------------------------------------------------------------------------------------------
+def run_reference(args, rank):
+    """--impl reference: the reference path's CPU implementation (oracle port) on all host cores."""
+    if rank != 0:
+        return
+    cores = host_cores()
+    threads = min(cores, args.cpu_threads or cores)
+    rows = args.cpu_rows
+    cols = {f: None for f in COLS}
+    import orc
+    for f, (stream, kind, _) in COLS.items():
+        cols[f] = orc.synth_column(stream, kind, 0, rows)
+    _, times = cpu_groupby(cols, rows, threads, args.warmup + args.steps)
+    t = times[args.warmup:]
+    ms = 1e3 * float(np.mean(t))
+    val = rows / np.mean(t) / 1e6
+    line = {"impl": "reference", "metric": "filter->GROUP BY throughput (BASELINE.json configs[1])", "value": round(val, 2),
+            "unit": "Mrows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64", "data": "synthetic",
+            "config": {"workload": "groupby: %d-row x 8-col table, a<500000 AND b>=0.25 -> GROUP BY k(1e5) SUM(v),AVG(w),COUNT" % args.rows,
+                       "sample_rows": rows},
+            "cpu_baseline": {"value": round(val, 2), "unit": "Mrows/s", "cores": threads, "kind": "port",
+                             "sample": "%d-row prefix of the same synthetic table per step (oracle restatement; the reference "
+                                       "binary needs clang-21+DuckDB+Abseil and cannot be built here)" % rows},
+            "e2e": {"value": round(val, 2), "unit": "Mrows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if not args.skip_bm25:
+        seg, dc, sum_dl = cpu_bm25_setup(args.docs, threads)
+        qs = make_queries(args.queries)[: args.cpu_queries]
+        postings = sum(int(dc[a]) + int(dc[b]) for a, b in qs)
+        ts = []
+        for i in range(args.warmup + args.steps):
+            dt, _, _, _ = cpu_bm25(seg, dc, sum_dl, args.docs, qs, threads)
+            ts.append(dt)
+        t = ts[args.warmup:]
+        line["bm25"] = {"metric": "BM25 top-1000 postings scanned (BASELINE.json configs[2])", "value": round(postings / np.mean(t) / 1e6, 2),
+                        "unit": "Mdocs/s", "ms_per_step": round(1e3 * float(np.mean(t)), 3),
+                        "cpu_baseline": {"value": round(postings / np.mean(t) / 1e6, 2), "unit": "Mdocs/s", "cores": threads, "kind": "port",
+                                         "sample": "%d of the %d two-term OR queries per step, block-max pruned oracle, simdcomp unpack from oracle/_ref"
+                                                   % (len(qs), args.queries)}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=100_000_000, help="table rows per GPU")
+    ap.add_argument("--docs", type=int, default=10_000_000, help="corpus docs per GPU")
+    ap.add_argument("--queries", type=int, default=4096)
+    ap.add_argument("--skip-bm25", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--cpu-rows", type=int, default=100_000_000)
+    ap.add_argument("--cpu-queries", type=int, default=256)
+    ap.add_argument("--cpu-threads", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        args.cpu_rows = min(args.cpu_rows, args.rows)
+        run_reference(args, rank)
+        return
+
+    import torch
+    import serenedb_b200 as sdb
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    ctx = sdb.Context(local)
+    hbm_peak, peak_src = peaks()
+
+    def barrier():
+        torch.cuda.synchronize()
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ------------------------------------------------------------------ table shard in HBM
+    rows = args.rows
+    row0 = rank * rows
+    seg = sdb.Segment(ctx, rows)
+    for f, (stream, kind, _) in COLS.items():
+        seg.synth_column(f, stream, kind, row0, rows)
+    for f, (stream, kind) in UNREFERENCED.items():
+        seg.synth_column(f, stream, kind, row0, rows)
+    ctx.sync()
+    scan = sdb.IResearchScan([seg])
+    preds = [sdb.pred(A, "LT", 500000), sdb.pred(B, "GE", 0.25)]
+    key_min, span = 0, 100000
+    d_i64 = torch.zeros(4 * span, dtype=torch.int64, device=dev)
+    d_f64 = torch.zeros(span, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+
+    def groupby_step():
+        scan.groupby_partial(preds, K, key_min, span, V, W_, d_i64.data_ptr(), d_f64.data_ptr())
+        if dist is not None:   # one collective per dtype group merges the partial aggregates (NVLink)
+            dist.all_reduce(d_i64)
+            dist.all_reduce(d_f64)
+            torch.cuda.synchronize()
+        return scan.groupby_finalize(key_min, span, d_i64.data_ptr(), d_f64.data_ptr(), span)
+
+    for _ in range(args.warmup):
+        res = groupby_step()
+    barrier()
+    ctx.profile(True)
+    launches0 = ctx.launches
+    with ClockSampler(local) as cs1:
+        barrier()
+        ctx.timer_start()
+        for _ in range(args.steps):
+            res = groupby_step()
+        torch.cuda.synchronize()
+        ms_total = ctx.timer_stop()
+        barrier()
+    gb_ms = max_over_ranks(ms_total) / args.steps
+    k_ms, k_n = ctx.profile_read("groupby")
+    ctx.profile(False)
+    gb_launches = ctx.launches - launches0
+    clocks = cs1.summary()
+    gb_value = world * rows / (gb_ms * 1e-3) / 1e6
+    gb_kernel_ms = k_ms / max(k_n, 1)
+    gb_alg_bytes = rows * 40 + span * 32          # 5 referenced 8-byte columns + the 3.2 MB group table
+    gb_ach = gb_alg_bytes / (gb_kernel_ms * 1e-3) / 1e9
+    n_groups = len(res)
+    n_pass = int(res["count"].sum())
+
+    # ------------------------------------------------------------------ e2e: host columns -> host groups
+    host = {}
+    for f, (_, _, dt) in COLS.items():
+        h = torch.empty(rows, dtype=torch.int64 if dt == np.int64 else torch.float64, pin_memory=True)
+        seg.column_to_host(f, h.data_ptr(), rows)
+        host[f] = h
+    torch.cuda.synchronize()
+    eseg = sdb.Segment(ctx, rows)
+    escan = sdb.IResearchScan([eseg])
+    h2d = rows * 40
+    d2h = None
+
+    def e2e_step():
+        for f, (_, _, dt) in COLS.items():
+            eseg.stage_column(f, (host[f].data_ptr(), dt, rows))
+        if dist is None:
+            return escan.groupby(preds, K, sum_int_field=V, avg_f64_field=W_, cap=span, n_groups_hint=span)
+        escan.groupby_partial(preds, K, key_min, span, V, W_, d_i64.data_ptr(), d_f64.data_ptr())
+        dist.all_reduce(d_i64)
+        dist.all_reduce(d_f64)
+        torch.cuda.synchronize()
+        return escan.groupby_finalize(key_min, span, d_i64.data_ptr(), d_f64.data_ptr(), span)
+
+    e_steps = max(1, min(args.steps, 5))
+    eres = e2e_step()
+    eres = e2e_step()
+    barrier()
+    ctx.timer_start()
+    for _ in range(e_steps):
+        eres = e2e_step()
+    torch.cuda.synchronize()
+    e_ms = max_over_ranks(ctx.timer_stop()) / e_steps
+    barrier()
+    d2h = int(len(eres)) * 48 + 16
+    assert np.array_equal(eres["count"], res["count"]) and np.array_equal(eres["sum_lo"], res["sum_lo"])
+    gb_e2e = world * rows / (e_ms * 1e-3) / 1e6
+    eseg.close()
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)
+    cpu_gb = None
+    cores = host_cores()
+    threads = min(cores, args.cpu_threads or cores)
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        crow = min(args.cpu_rows, rows)
+        cols = {f: host[f].numpy() for f in COLS}
+        cres, ctimes = cpu_groupby(cols, crow, threads, 3)
+        best = min(ctimes)
+        cpu_gb = {"value": round(crow / best / 1e6, 2), "unit": "Mrows/s", "cores": threads, "kind": "port",
+                  "sample": "%d rows of the same table, best of 3 (oracle restatement of the scan+DuckDB aggregate)" % crow}
+        if crow == rows:  # the CPU leg doubles as a full-size parity check of this very run
+            assert np.array_equal(cres["key"], res["key"]) and np.array_equal(cres["count"], res["count"])
+            assert np.array_equal(cres["sum_lo"], res["sum_lo"]) and np.array_equal(cres["sum_hi"], res["sum_hi"])
+            assert np.allclose(cres["sum_f64"] / cres["cnt_f64"], res["sum_f64"] / res["cnt_f64"], rtol=1e-5)
+    del host
+
+    line = {
+        "metric": "filter->GROUP BY throughput (BASELINE.json configs[1]; bm25 object = configs[2])",
+        "value": round(gb_value, 1), "unit": "Mrows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(gb_ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int64+f64", "data": "synthetic",
+        "config": {"workload": "groupby: %d rows/GPU x 8 int64/float64 columns (5 referenced, 40 B/row), a<500000 AND b>=0.25 -> "
+                               "GROUP BY k (1e5 keys) SUM(v), AVG(w), COUNT(*)" % rows,
+                   "rows_per_gpu": rows, "groups": n_groups, "rows_passing": n_pass, "parallelism": "row-range shards x%d" % world,
+                   "l2": "inputs (%.1f GB/GPU) larger than L2; no flush needed" % (rows * 40 / 1e9),
+                   "merge": "none" if world == 1 else "2 NCCL all-reduces (int64 limbs+counts, float64 sums) per step"},
+        "clocks": clocks,
+        "e2e": {"value": round(gb_e2e, 1), "unit": "Mrows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": round(e_ms, 3), "steps": e_steps},
+        "gpu_launches": int(gb_launches),
+        "roofline": {"bound": "hbm", "achieved": round(gb_ach, 1), "peak": hbm_peak, "unit": "GB/s",
+                     "frac": round(gb_ach / hbm_peak, 4), "traffic": None, "kernel": "filter_groupby_kernel",
+                     "kernel_ms": round(gb_kernel_ms, 4), "algorithmic_bytes": gb_alg_bytes, "peak_source": peak_src},
+    }
+    if cpu_gb:
+        line["cpu_baseline"] = cpu_gb
+
+    # ------------------------------------------------------------------ BM25 (configs[2])
+    if not args.skip_bm25:
+        n_docs = args.docs
+        cseg = sdb.Segment(ctx, n_docs)
+        dc, sum_dl = cseg.synth_corpus(rank * n_docs, 0, N_TERMS, threads=min(cores, 64))
+        dct = torch.tensor(dc.astype(np.int64), device=dev)
+        sdl = torch.tensor([sum_dl], dtype=torch.int64, device=dev)
+        if dist is not None:   # corpus-wide statistics: summed once at index-build time (collectors.cpp:36-52)
+            dist.all_reduce(dct)
+            dist.all_reduce(sdl)
+        reader = sdb.IndexReader([cseg], n_docs * world, int(sdl.item()), dct.cpu().numpy())
+        scorer = sdb.BM25(1.2, 0.75)
+        queries = make_queries(args.queries)
+        batch = sdb.PreparedBatch(reader, queries, sdb.OR, scorer, TOPK)
+        nq = len(queries)
+        postings = int(sum(int(dc[a]) + int(dc[b]) for a, b in queries))
+        tb = cseg.term_bytes(N_TERMS)
+        alg_bytes = int(sum(int(tb[a]) + int(tb[b]) + int(dc[a]) + int(dc[b]) for a, b in queries)) + nq * TOPK * 12
+        keys = torch.zeros(nq * TOPK, dtype=torch.int64, device=dev)
+        keys_all = torch.zeros(world * nq * TOPK, dtype=torch.int64, device=dev) if dist is not None else None
+
+        def bm25_step():
+            batch.run_device(rank, keys.data_ptr())
+            if dist is not None:   # one collective: gather every rank's k best keys, then select locally
+                dist.all_gather_into_tensor(keys_all, keys)
+                torch.cuda.synchronize()
+                return sdb.merge_gathered(ctx, keys_all.data_ptr(), world, nq, TOPK)
+            return None
+
+        for _ in range(args.warmup):
+            bm25_step()
+        barrier()
+        ctx.profile(True)
+        l0 = ctx.launches
+        tot_ms = 0.0
+        with ClockSampler(local) as cs2:
+            for _ in range(args.steps):
+                ctx.flush_l2()        # the 256-term index is about L2-sized: evict it between timed steps
+                barrier()
+                ctx.timer_start()
+                bm25_step()
+                torch.cuda.synchronize()
+                tot_ms += max_over_ranks(ctx.timer_stop())
+        bm_ms = tot_ms / args.steps
+        tk_ms, tk_n = ctx.profile_read("topk")
+        mg_ms, mg_n = ctx.profile_read("merge")
+        ctx.profile(False)
+        bm_launches = ctx.launches - l0 - args.steps  # minus the L2-flush launches
+        clocks2 = cs2.summary()
+        # e2e: host query descriptors in, host hits out (index resident: staged at index-load time)
+        batch.run_host()
+        barrier()
+        ctx.timer_start()
+        e_steps2 = max(1, min(args.steps, 5))
+        for _ in range(e_steps2):
+            if dist is None:
+                hits, n_out, total = batch.run_host()
+            else:
+                hits, n_out = bm25_step()
+        be_ms = max_over_ranks(ctx.timer_stop()) / e_steps2
+        barrier()
+        bm = {
+            "metric": "BM25 top-1000, 2-term OR batch: postings scanned per second (BASELINE.json configs[2])",
+            "value": round(world * postings / (bm_ms * 1e-3) / 1e6, 1), "unit": "Mdocs/s", "ms_per_step": round(bm_ms, 3),
+            "corpus_docs_per_s_M": round(world * n_docs * nq / (bm_ms * 1e-3) / 1e6, 1),
+            "config": {"workload": "bm25: %d docs/GPU synthetic Zipf corpus, %d two-term OR queries/step over %d terms, top-%d, exhaustive scan (no block-max skipping yet)"
+                                   % (n_docs, nq, N_TERMS, TOPK), "postings_per_step": postings,
+                       "l2": "256 MB write between timed steps (index ~L2-sized)"},
+            "e2e": {"value": round(world * postings / (be_ms * 1e-3) / 1e6, 1), "unit": "Mdocs/s",
+                    "h2d_bytes_per_step": int(len(batch.off) * 4 + (len(batch.off) - 1) * 2 * 32),
+                    "d2h_bytes_per_step": nq * TOPK * 8 + nq * 12, "ms_per_step": round(be_ms, 3)},
+            "gpu_launches": int(bm_launches),
+            "roofline": {"bound": "hbm", "achieved": round(alg_bytes / (tk_ms / max(tk_n, 1) * 1e-3) / 1e9, 1), "peak": hbm_peak, "unit": "GB/s",
+                         "frac": round(alg_bytes / (tk_ms / max(tk_n, 1) * 1e-3) / 1e9 / hbm_peak, 4), "traffic": None,
+                         "kernel": "bm25_topk_kernel", "kernel_ms": round(tk_ms / max(tk_n, 1), 3), "merge_kernel_ms": round(mg_ms / max(mg_n, 1), 3),
+                         "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
+                         "note": "touched bytes = encoded doc+freq blocks of every list scanned + 1 B norm per posting + 12 B per hit"},
+            "clocks": clocks2,
+        }
+        clocks = merge_clocks(clocks, clocks2)
+        line["clocks"] = clocks
+        if rank == 0 and world == 1 and not args.skip_cpu:
+            oseg, odc, osdl = cpu_bm25_setup(n_docs, threads)
+            assert np.array_equal(odc, dc) and osdl == sum_dl
+            cq = queries[: args.cpu_queries]
+            dt, ohits, on, scored = cpu_bm25(oseg, odc, osdl, n_docs, cq, threads, mode=2)
+            cp = sum(int(dc[a]) + int(dc[b]) for a, b in cq)
+            bm["cpu_baseline"] = {"value": round(cp / dt / 1e6, 2), "unit": "Mdocs/s", "cores": threads, "kind": "port",
+                                  "sample": "%d of the %d queries, block-max pruned oracle (scored %.0f%% of postings), simdcomp unpack via oracle/_ref"
+                                            % (len(cq), nq, 100.0 * scored / max(cp, 1))}
+            # full-size parity of this run's first queries
+            for qi in range(min(8, len(cq))):
+                n = int(on[qi])
+                assert np.array_equal(hits[qi, :n]["doc"], ohits[qi, :n]["doc"]), "bm25 parity (docs) q%d" % qi
+                assert np.array_equal(hits[qi, :n]["score"], ohits[qi, :n]["score"]), "bm25 parity (scores) q%d" % qi
+        line["bm25"] = bm
+        line["gpu_launches"] = int(gb_launches + bm_launches)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

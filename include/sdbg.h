@@ -60,6 +60,12 @@ int sdbg_timer_stop(sdbg_ctx*, float* ms);
 int sdbg_sync(sdbg_ctx*);
 /* Number of kernels this context has launched since creation (bench's gpu_launches claim). */
 uint64_t sdbg_launch_count(const sdbg_ctx*);
+/* Per-kernel device timing for roofline reports: when enabled, a CUDA event pair is recorded on the
+ * context's stream around each hot kernel launch. kernel_id: 0 filter_groupby, 1 bm25_topk,
+ * 2 topk_merge, 3 filter_count_sum. read() synchronises and returns the summed duration and the
+ * number of launches since enable(1); enable() resets the counters. */
+int sdbg_profile_enable(sdbg_ctx*, int on);
+int sdbg_profile_read(sdbg_ctx*, int kernel_id, double* total_ms, uint64_t* launches);
 /* Writes `bytes` of device memory (> L2) to evict cached inputs between timed iterations. */
 int sdbg_flush_l2(sdbg_ctx*);
 
@@ -89,9 +95,14 @@ int sdbg_stage_column(sdbg_segment*, uint64_t field, sdbg_type t, const void* va
 int sdbg_stage_column_device(sdbg_segment*, uint64_t field, sdbg_type t, const void* d_values, uint64_t rows);
 /* Device address of a staged column (for callers that generate data in place). */
 int sdbg_column_device_ptr(sdbg_segment*, uint64_t field, void** d_values, uint64_t* rows);
+/* Copies the first `rows` values of a staged column back to host memory (tests / bench set-up). */
+int sdbg_column_to_host(sdbg_segment*, uint64_t field, void* host_dst, uint64_t rows);
 /* Bytes of HBM held by the segment's postings (payload + tables) and how many blocks were staged. */
 int sdbg_segment_posting_stats(const sdbg_segment*, uint64_t* payload_bytes, uint64_t* table_bytes,
                                uint64_t* n_blocks, uint64_t* n_postings);
+
+/* Encoded bytes (block headers + payloads, as in the .doc stream) of the first n_terms terms. */
+int sdbg_segment_term_bytes(const sdbg_segment*, uint64_t* bytes_out, size_t n_terms);
 
 /* ---- predicates (pushed TableFilterSet entries; NULL never passes) ---- */
 enum { SDBG_OP_LT = 0, SDBG_OP_LE, SDBG_OP_GT, SDBG_OP_GE, SDBG_OP_EQ, SDBG_OP_NE, SDBG_OP_BETWEEN,

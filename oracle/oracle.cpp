@@ -1218,3 +1218,70 @@ uint32_t orc_synth_term(uint32_t t, uint64_t doc0, uint32_t n, const uint32_t* d
 }
 
 }  // extern "C"
+
+// ==========================================================================================
+// CPU-baseline helpers: many queries on all host cores (one query per thread at a time, the way
+// DuckDB workers each drive their own iterator: duckdb_search_full_scan.cpp:1925-1944), and a
+// multi-threaded builder for the synthetic shard.
+// ==========================================================================================
+extern "C" {
+
+int orc_bm25_topk_batch(orc_segment* const* segs, size_t n_segs, int kind, const orc_bm25_term* terms,
+                        const uint32_t* term_off, size_t n_queries, float k1, const orc_pred* filt, uint32_t k,
+                        float threshold_in, int mode, int threads, orc_hit* out, uint32_t* n_out,
+                        uint64_t* total_matches, uint64_t* postings_scored) {
+  threads = std::max(threads, 1);
+  std::atomic<size_t> next{0};
+  std::atomic<uint64_t> scored_all{0};
+  auto work = [&]() {
+    for (;;) {
+      const size_t q = next.fetch_add(1);
+      if (q >= n_queries) break;
+      uint64_t scored = 0, tot = 0;
+      orc_bm25_topk(segs, n_segs, kind, terms + term_off[q], term_off[q + 1] - term_off[q], k1, filt, k, threshold_in,
+                    mode, out + q * size_t(k), n_out + q, &tot, &scored);
+      if (total_matches) total_matches[q] = tot;
+      scored_all += scored;
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; ++t) pool.emplace_back(work);
+  for (auto& t : pool) t.join();
+  if (postings_scored) *postings_scored = scored_all.load();
+  return 0;
+}
+
+// Synthetic shard built with `threads` workers: docs (doc0, doc0+n], terms [t0, t0+nt).
+// Terms are generated in parallel and appended in term order, so the stream equals the sequential one.
+orc_segment* orc_synth_segment(uint64_t doc0, uint32_t n_docs, uint32_t t0, uint32_t nt, int threads,
+                               uint32_t* docs_count_out, uint64_t* sum_dl_out) {
+  threads = std::max(threads, 1);
+  auto* seg = orc_segment_new(n_docs, 1, 0.75f);
+  std::vector<uint32_t> dl(n_docs);
+  orc_synth_doc_lengths(doc0, n_docs, dl.data());
+  orc_segment_set_norms(seg, dl.data());
+  std::vector<std::vector<uint32_t>> docs(nt), freqs(nt);
+  std::atomic<uint32_t> next{0};
+  auto work = [&]() {
+    for (;;) {
+      const uint32_t i = next.fetch_add(1);
+      if (i >= nt) break;
+      docs[i].resize(n_docs); freqs[i].resize(n_docs);
+      const uint32_t c = orc_synth_term(t0 + i, doc0, n_docs, dl.data(), docs[i].data(), freqs[i].data());
+      docs[i].resize(c); freqs[i].resize(c);
+      docs[i].shrink_to_fit(); freqs[i].shrink_to_fit();
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; ++t) pool.emplace_back(work);
+  for (auto& t : pool) t.join();
+  for (uint32_t i = 0; i < nt; ++i) {
+    segment_add_term(*seg, docs[i].data(), freqs[i].data(), uint32_t(docs[i].size()));
+    if (docs_count_out) docs_count_out[i] = uint32_t(docs[i].size());
+    std::vector<uint32_t>().swap(docs[i]); std::vector<uint32_t>().swap(freqs[i]);
+  }
+  if (sum_dl_out) *sum_dl_out = seg->norm_sum;
+  return seg;
+}
+
+}  // extern "C"

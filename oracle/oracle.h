@@ -133,6 +133,12 @@ int orc_bm25_topk(orc_segment* const* segs, size_t n_segs, int kind, const orc_b
                   int mode, orc_hit* out, uint32_t* n_out, uint64_t* total_matches,
                   uint64_t* postings_scored);
 
+/* Many queries on `threads` host cores (one query per thread at a time). out: n_queries*k hits. */
+int orc_bm25_topk_batch(orc_segment* const* segs, size_t n_segs, int kind, const orc_bm25_term* terms,
+                        const uint32_t* term_off, size_t n_queries, float k1, const orc_pred* filt, uint32_t k,
+                        float threshold_in, int mode, int threads, orc_hit* out, uint32_t* n_out,
+                        uint64_t* total_matches, uint64_t* postings_scored);
+
 /* ---------- columnar (full_scanner.cpp:81-147 + DuckDB aggregate; see header note) ---------- */
 int orc_filter_bitmap(const orc_segment*, const orc_pred* preds, size_t n_preds, uint64_t* mask_out);
 /* sum_field type decides which sum is filled. NULL sum inputs are skipped (SQL). threads>=1. */
@@ -155,6 +161,10 @@ void orc_synth_doc_lengths(uint64_t doc0, uint32_t n, uint32_t* out);
  * Returns count; docs/freqs sized n. p_t = min(0.5, 0.6/(t+1)). */
 uint32_t orc_synth_term(uint32_t t, uint64_t doc0, uint32_t n, const uint32_t* dl, uint32_t* docs,
                         uint32_t* freqs);
+
+/* Whole synthetic shard built with `threads` workers (same bytes as term-by-term building). */
+orc_segment* orc_synth_segment(uint64_t doc0, uint32_t n_docs, uint32_t t0, uint32_t nt, int threads,
+                               uint32_t* docs_count_out, uint64_t* sum_dl_out);
 
 #ifdef __cplusplus
 }

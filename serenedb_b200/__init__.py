@@ -7,9 +7,11 @@ import raises -- there is no Python or CPU fallback for any operation.
 """
 from . import _native
 from .engine import (AND, OR, BM25, FLT_MIN, Context, ExecuteTopK, ExecuteTopKBatch, IndexReader,
-                     IResearchScan, PostingsWriter, Segment, pred, stage_parse_host, sum_i128)
+                     IResearchScan, PostingsWriter, PreparedBatch, Segment, merge_gathered, pred,
+                     stage_parse_host, sum_i128)
 
 _native.lib()  # fail loudly at import time when the CUDA extension is missing
 
 __all__ = ["AND", "OR", "BM25", "FLT_MIN", "Context", "ExecuteTopK", "ExecuteTopKBatch", "IndexReader",
-           "IResearchScan", "PostingsWriter", "Segment", "pred", "stage_parse_host", "sum_i128"]
+           "IResearchScan", "PostingsWriter", "PreparedBatch", "Segment", "merge_gathered", "pred",
+           "stage_parse_host", "sum_i128"]

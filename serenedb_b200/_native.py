@@ -54,6 +54,8 @@ SIGNATURES = {
     "sdbg_sync": (C.c_int, [_vp]),
     "sdbg_launch_count": (C.c_uint64, [_vp]),
     "sdbg_flush_l2": (C.c_int, [_vp]),
+    "sdbg_profile_enable": (C.c_int, [_vp, C.c_int]),
+    "sdbg_profile_read": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), _u64p]),
     "sdbg_segment_create": (C.c_int, [_vp, C.c_uint32, C.POINTER(_vp)]),
     "sdbg_segment_destroy": (None, [_vp]),
     "sdbg_stage_postings": (C.c_int, [_vp, _vp, _sz, _vp, _sz, C.c_int]),
@@ -61,7 +63,9 @@ SIGNATURES = {
     "sdbg_stage_column": (C.c_int, [_vp, C.c_uint64, C.c_int, _vp, _vp, C.c_uint64]),
     "sdbg_stage_column_device": (C.c_int, [_vp, C.c_uint64, C.c_int, _vp, C.c_uint64]),
     "sdbg_column_device_ptr": (C.c_int, [_vp, C.c_uint64, C.POINTER(_vp), _u64p]),
+    "sdbg_column_to_host": (C.c_int, [_vp, C.c_uint64, _vp, C.c_uint64]),
     "sdbg_segment_posting_stats": (C.c_int, [_vp, _u64p, _u64p, _u64p, _u64p]),
+    "sdbg_segment_term_bytes": (C.c_int, [_vp, _vp, _sz]),
     "sdbg_bm25_collect": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_float, C.c_float, C.POINTER(BM25Term)]),
     "sdbg_bm25_topk": (C.c_int, [_vp, _sz, C.c_int, _vp, _sz, C.c_float, _vp, C.c_uint32, C.c_float, _vp, _u32p,
                                  _u64p, _f32p]),

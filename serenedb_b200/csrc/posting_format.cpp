@@ -361,7 +361,7 @@ bool read_pair(const uint8_t*& p, const uint8_t* end, MaxPair* m) {  // FreqNorm
 std::string stage_postings(const uint8_t* doc, size_t n, const TermMeta* terms, size_t n_terms, bool has_wand,
                            StagedPostings* sp) {
   sp->arena.clear(); sp->blocks.clear(); sp->blk_max.clear(); sp->term_max.clear();
-  sp->term_blk_begin.assign(1, 0); sp->term_docs.clear();
+  sp->term_blk_begin.assign(1, 0); sp->term_docs.clear(); sp->term_bytes.clear();
   sp->n_postings = 0; sp->has_wand = has_wand;
   Arena arena{sp->arena};
   const uint8_t* const end = doc + n;
@@ -373,6 +373,7 @@ std::string stage_postings(const uint8_t* doc, size_t n, const TermMeta* terms, 
     sp->term_docs.push_back(cnt);
     sp->n_postings += cnt;
     MaxPair root{0, 0};
+    uint64_t enc_bytes = 0;
     const size_t first_block = sp->blocks.size();
     if (cnt == 1) {
       // Single-doc terms live in the term meta (iterator_score.hpp:1015-1030); give them one raw block.
@@ -424,6 +425,7 @@ std::string stage_postings(const uint8_t* doc, size_t n, const TermMeta* terms, 
         sp->blocks.push_back(b);
         sp->blk_max.push_back(MaxPair{0, 0});
         p = fp + 1 + fsz;
+        enc_bytes += 2 + dsz + fsz;
       }
       blk_start[nblk] = uint64_t(p - doc);
       if (cnt == kBlockSize && has_wand && !read_pair(p, end, &root)) return "truncated block-max entry";
@@ -455,6 +457,7 @@ std::string stage_postings(const uint8_t* doc, size_t n, const TermMeta* terms, 
       if (has_wand) for (size_t j = first_block; j < sp->blocks.size(); ++j) if (sp->blk_max[j].freq == 0) sp->blk_max[j] = root;
     }
     sp->term_max.push_back(root);
+    sp->term_bytes.push_back(enc_bytes);
     sp->term_blk_begin.push_back(uint32_t(sp->blocks.size()));
   }
   sp->arena.resize(sp->arena.size() + 1024, 0);  // slack so 16-byte over-reads of the last block stay in bounds

@@ -143,6 +143,7 @@ struct StagedPostings {
   std::vector<uint32_t> term_docs;     // docs_count per term
   std::vector<MaxPair> blk_max;        // per block; blocks without a skip entry carry the term's root pair
   std::vector<MaxPair> term_max;       // per term root pair ({0,0} when !has_wand)
+  std::vector<uint64_t> term_bytes;    // per term: encoded block bytes in the .doc stream (headers + payloads)
   uint64_t n_postings = 0;
   bool has_wand = false;
 };

@@ -59,6 +59,11 @@ struct sdbg_ctx {
   size_t flush_bytes = 0;
   bool topk_attr_set = false;
   bool merge_attr_set = false;
+  // optional per-kernel timing: CUDA events recorded on `stream` around the hot kernels
+  bool profiling = false;
+  struct ProfSpan { int id; cudaEvent_t a, b; };
+  std::vector<ProfSpan> spans;
+  std::vector<cudaEvent_t> event_pool;
 };
 
 struct sdbg_segment {
@@ -70,6 +75,7 @@ struct sdbg_segment {
   void* d_blkmax = nullptr;
   std::vector<uint32_t> term_blk_begin, term_docs;
   std::vector<MaxPair> term_max;
+  std::vector<uint64_t> term_bytes;
   uint64_t arena_bytes = 0, n_blocks = 0, n_postings = 0;
   bool has_wand = false;
   // norms
@@ -121,6 +127,22 @@ __global__ void flush_kernel(uint4* p, size_t n, uint32_t v) {
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
     p[i] = make_uint4(v, v, v, v);
 }
+
+// Kernel ids for sdbg_profile_*: the kernels a roofline is reported for.
+enum { kProfGroupBy = 0, kProfTopk = 1, kProfMerge = 2, kProfCountSum = 3, kProfBitmap = 4, kProfIds = 5 };
+
+struct ProfScope {  // records an event pair around a launch when profiling is on
+  sdbg_ctx* c; int idx = -1;
+  ProfScope(sdbg_ctx* ctx, int id) : c(ctx) {
+    if (!c->profiling) return;
+    auto get = [&]() { cudaEvent_t e; if (!c->event_pool.empty()) { e = c->event_pool.back(); c->event_pool.pop_back(); } else cudaEventCreate(&e); return e; };
+    sdbg_ctx::ProfSpan sp{id, get(), get()};
+    cudaEventRecord(sp.a, c->stream);
+    c->spans.push_back(sp);
+    idx = int(c->spans.size()) - 1;
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(c->spans[size_t(idx)].b, c->stream); }
+};
 
 uint32_t next_pow2(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
 
@@ -186,6 +208,28 @@ extern "C" int sdbg_flush_l2(sdbg_ctx* c) {
   return SDBG_OK;
 }
 
+extern "C" int sdbg_profile_enable(sdbg_ctx* c, int on) {
+  if (!c) return SDBG_EINVAL;
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (auto& sp : c->spans) { c->event_pool.push_back(sp.a); c->event_pool.push_back(sp.b); }
+  c->spans.clear();
+  c->profiling = on != 0;
+  return SDBG_OK;
+}
+extern "C" int sdbg_profile_read(sdbg_ctx* c, int kernel_id, double* total_ms, uint64_t* launches) {
+  if (!c || !total_ms || !launches || kernel_id < 0 || kernel_id >= kProfIds) return SDBG_EINVAL;
+  CU(c, cudaStreamSynchronize(c->stream));
+  double ms = 0; uint64_t n = 0;
+  for (auto& sp : c->spans) {
+    if (sp.id != kernel_id) continue;
+    float t = 0;
+    CU(c, cudaEventElapsedTime(&t, sp.a, sp.b));
+    ms += t; ++n;
+  }
+  *total_ms = ms; *launches = n;
+  return SDBG_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // staging
 // ------------------------------------------------------------------------------------------
@@ -236,6 +280,7 @@ int upload_postings(sdbg_segment* s, const StagedPostings& sp) {
   s->term_blk_begin = sp.term_blk_begin;
   s->term_docs = sp.term_docs;
   s->term_max = sp.term_max;
+  s->term_bytes = sp.term_bytes;
   s->arena_bytes = sp.arena.size();
   s->n_blocks = sp.blocks.size();
   s->n_postings = sp.n_postings;
@@ -340,6 +385,18 @@ extern "C" int sdbg_column_device_ptr(sdbg_segment* s, uint64_t field, void** d_
   return SDBG_OK;
 }
 
+extern "C" int sdbg_column_to_host(sdbg_segment* s, uint64_t field, void* host_dst, uint64_t rows) {
+  if (!s || !host_dst) return SDBG_EINVAL;
+  auto it = s->cols.find(field);
+  if (it == s->cols.end()) return fail(s->ctx, SDBG_ENOTFOUND, "unknown column");
+  if (rows > it->second.rows) return fail(s->ctx, SDBG_EINVAL, "more rows requested than staged");
+  sdbg_ctx* c = s->ctx;
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaMemcpyAsync(host_dst, it->second.d_values, rows * type_width(it->second.type), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return SDBG_OK;
+}
+
 extern "C" int sdbg_segment_posting_stats(const sdbg_segment* s, uint64_t* payload_bytes, uint64_t* table_bytes,
                                           uint64_t* n_blocks, uint64_t* n_postings) {
   if (!s) return SDBG_EINVAL;
@@ -347,6 +404,12 @@ extern "C" int sdbg_segment_posting_stats(const sdbg_segment* s, uint64_t* paylo
   if (table_bytes) *table_bytes = s->n_blocks * (sizeof(BlockDesc) + sizeof(MaxPair));
   if (n_blocks) *n_blocks = s->n_blocks;
   if (n_postings) *n_postings = s->n_postings;
+  return SDBG_OK;
+}
+
+extern "C" int sdbg_segment_term_bytes(const sdbg_segment* s, uint64_t* bytes_out, size_t n_terms) {
+  if (!s || !bytes_out || n_terms > s->term_bytes.size()) return SDBG_EINVAL;
+  std::copy(s->term_bytes.begin(), s->term_bytes.begin() + long(n_terms), bytes_out);
   return SDBG_OK;
 }
 
@@ -485,7 +548,8 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
     P.lists = pl.lists; P.list_base = uint32_t(si) * pl.G;
     P.W = pl.W; P.n_windows = (s->n_docs + pl.W - 1) / pl.W;
     P.k = k; P.cap = pl.cap; P.conjunction = kind == SDBG_QUERY_AND ? 1 : 0;
-    bm25_topk_kernel<<<dim3(pl.G, unsigned(nq)), kTopkThreads, pl.smem, c->stream>>>(P);
+    { ProfScope ps_(c, kProfTopk);
+      bm25_topk_kernel<<<dim3(pl.G, unsigned(nq)), kTopkThreads, pl.smem, c->stream>>>(P); }
     ++c->launches;
     CU(c, cudaGetLastError());
     base += s->n_docs;
@@ -496,7 +560,8 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
   M.G = pl.lists; M.stride = pl.cap; M.k = k; M.cap = pl.cap;
   M.keys_out = static_cast<unsigned long long*>(b_keys.p);
   M.n_out = static_cast<uint32_t*>(b_small.p);
-  topk_merge_kernel<<<unsigned(nq), kTopkThreads, size_t(pl.cap) * 8, c->stream>>>(M);
+  { ProfScope ps_(c, kProfMerge);
+    topk_merge_kernel<<<unsigned(nq), kTopkThreads, size_t(pl.cap) * 8, c->stream>>>(M); }
   ++c->launches;
   CU(c, cudaGetLastError());
   dev->keys = M.keys_out; dev->n_out = M.n_out; dev->total = d_total;
@@ -791,7 +856,8 @@ extern "C" int sdbg_filter_count_sum(sdbg_segment* const* segs, size_t n_segs, c
     }
     if (!rows) rows = s->n_docs;
     auto* part = static_cast<CountSumOut*>(c->scratch[9].p) + si * (size_t(grid) + 1);
-    filter_count_sum_kernel<<<grid, 256, 0, c->stream>>>(ps, sc, has_sum, rows, part, static_cast<unsigned int*>(c->scratch[10].p));
+    { ProfScope ps_(c, kProfCountSum);
+      filter_count_sum_kernel<<<grid, 256, 0, c->stream>>>(ps, sc, has_sum, rows, part, static_cast<unsigned int*>(c->scratch[10].p)); }
     ++c->launches;
     CU(c, cudaGetLastError());
     CU(c, cudaMemcpyAsync(static_cast<CountSumOut*>(c->h_pinned) + si, part + grid, sizeof(CountSumOut), cudaMemcpyDeviceToHost, c->stream));
@@ -870,7 +936,8 @@ int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred
     P.key_min = key_min; P.key_span = span; P.rows = rows;
     P.table = table; P.cnt_f = cnt_f; P.out_of_range = oor;
     const unsigned grid = unsigned(c->sm_count) * unsigned(env_int("SDBG_GROUPBY_CTAS_PER_SM", 8));
-    filter_groupby_kernel<2><<<grid, 256, 0, c->stream>>>(P);
+    { ProfScope ps_(c, kProfGroupBy);
+      filter_groupby_kernel<2><<<grid, 256, 0, c->stream>>>(P); }
     ++c->launches;
     CU(c, cudaGetLastError());
   }

@@ -82,6 +82,16 @@ class Context:
     def flush_l2(self):
         N.check(N.lib().sdbg_flush_l2(self._h), self._h)
 
+    def profile(self, on=True):
+        N.check(N.lib().sdbg_profile_enable(self._h, 1 if on else 0), self._h)
+
+    def profile_read(self, kernel):
+        """kernel: 'groupby' | 'topk' | 'merge' | 'count_sum' -> (total_ms, launches) since profile(True)."""
+        kid = dict(groupby=0, topk=1, merge=2, count_sum=3)[kernel]
+        ms, n = C.c_double(), C.c_uint64()
+        N.check(N.lib().sdbg_profile_read(self._h, kid, C.byref(ms), C.byref(n)), self._h)
+        return ms.value, n.value
+
     @property
     def launches(self):
         return int(N.lib().sdbg_launch_count(self._h))
@@ -201,6 +211,9 @@ class Segment:
         N.check(N.lib().sdbg_column_device_ptr(self._h, int(field), C.byref(p), C.byref(r)), self.ctx._h)
         return p.value, r.value
 
+    def column_to_host(self, field, host_ptr, rows):
+        N.check(N.lib().sdbg_column_to_host(self._h, int(field), C.c_void_p(int(host_ptr)), int(rows)), self.ctx._h)
+
     def synth_corpus(self, doc0, t0, nt, threads=8):
         """SURVEY §8d corpus shard: returns (docs_count per term, sum of doc lengths)."""
         dc = np.zeros(nt, np.uint32)
@@ -218,6 +231,11 @@ class Segment:
         a, b, c, d = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
         N.check(N.lib().sdbg_segment_posting_stats(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
         return dict(payload_bytes=a.value, table_bytes=b.value, n_blocks=c.value, n_postings=d.value)
+
+    def term_bytes(self, n_terms):
+        out = np.zeros(int(n_terms), np.uint64)
+        N.check(N.lib().sdbg_segment_term_bytes(self._h, _ptr(out), int(n_terms)), self.ctx._h)
+        return out
 
     def column_minmax(self, field):
         mn, mx = C.c_int64(), C.c_int64()
@@ -300,6 +318,56 @@ def ExecuteTopKBatch(reader, queries, kind, scorer, k, filt=None, threshold=FLT_
                                          _ptr(off), nq, scorer.k, fp, int(k), float(threshold), _ptr(hits),
                                          _ptr(n_out), _ptr(total)), ctx._h)
     return hits, n_out, total
+
+
+def _flatten_queries(reader, queries, scorer):
+    flat = [reader.stats(scorer, t) for q in queries for t in q]
+    terms = (N.BM25Term * max(len(flat), 1))()
+    for i, t in enumerate(flat):
+        terms[i] = t
+    off = np.zeros(len(queries) + 1, np.uint32)
+    off[1:] = np.cumsum([len(q) for q in queries])
+    return terms, off
+
+
+class PreparedBatch:
+    """Query descriptors marshalled once (terms + statistics), reusable across steps."""
+
+    def __init__(self, reader, queries, kind, scorer, k, filt=None, threshold=FLT_MIN):
+        self.reader, self.kind, self.scorer, self.k, self.filt, self.threshold = reader, int(kind), scorer, int(k), filt, float(threshold)
+        self.nq = len(queries)
+        self.terms, self.off = _flatten_queries(reader, queries, scorer)
+        self.hits = np.zeros((self.nq, self.k), HIT_DTYPE)
+        self.n_out = np.zeros(self.nq, np.uint32)
+        self.total = np.zeros(self.nq, np.uint64)
+
+    def run_host(self):
+        """Full API call: host descriptors in, host hits out."""
+        r = self.reader
+        fp = C.byref(self.filt) if self.filt is not None else None
+        N.check(N.lib().sdbg_bm25_topk_batch(_seg_array(r.segments), len(r.segments), self.kind, self.terms,
+                                             _ptr(self.off), self.nq, self.scorer.k, fp, self.k, self.threshold,
+                                             _ptr(self.hits), _ptr(self.n_out), _ptr(self.total)), r.segments[0].ctx._h)
+        return self.hits, self.n_out, self.total
+
+    def run_device(self, rank, d_keys_ptr, d_totals_ptr=None):
+        """Results stay in HBM as sortable keys (for the multi-GPU gather + merge)."""
+        r = self.reader
+        fp = C.byref(self.filt) if self.filt is not None else None
+        N.check(N.lib().sdbg_bm25_topk_batch_device(_seg_array(r.segments), len(r.segments), self.kind, self.terms,
+                                                    _ptr(self.off), self.nq, self.scorer.k, fp, self.k, self.threshold,
+                                                    int(rank), C.c_void_p(int(d_keys_ptr)),
+                                                    C.c_void_p(int(d_totals_ptr)) if d_totals_ptr else None),
+                r.segments[0].ctx._h)
+
+
+def merge_gathered(ctx, d_keys_all_ptr, n_ranks, nq, k):
+    """Global top-k from the keys every rank contributed ([rank][query][k] u64 in HBM)."""
+    hits = np.zeros((nq, k), HIT_DTYPE)
+    n_out = np.zeros(nq, np.uint32)
+    N.check(N.lib().sdbg_topk_merge_gathered(ctx._h, C.c_void_p(int(d_keys_all_ptr)), int(n_ranks), int(nq), int(k),
+                                             _ptr(hits), _ptr(n_out)), ctx._h)
+    return hits, n_out
 
 
 def ExecuteTopK(reader, query_terms, kind, scorer, k, filt=None, threshold=FLT_MIN):

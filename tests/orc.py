@@ -122,6 +122,10 @@ def lib():
     L.orc_segment_add_column.argtypes = [vp, C.c_uint64, C.c_int, vp, vp, C.c_uint64]
     L.orc_bm25_topk.argtypes = [vp, C.c_size_t, C.c_int, vp, C.c_size_t, C.c_float, vp, C.c_uint32,
                                 C.c_float, C.c_int, vp, u32p, u64p, u64p]
+    L.orc_bm25_topk_batch.argtypes = [vp, C.c_size_t, C.c_int, vp, vp, C.c_size_t, C.c_float, vp, C.c_uint32,
+                                      C.c_float, C.c_int, C.c_int, vp, vp, vp, u64p]
+    L.orc_synth_segment.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, vp, u64p]
+    L.orc_synth_segment.restype = vp
     L.orc_filter_bitmap.argtypes = [vp, vp, C.c_size_t, vp]
     L.orc_filter_count_sum.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.c_uint64, C.c_int, u64p, vp,
                                        C.POINTER(C.c_double)]
@@ -341,6 +345,37 @@ def bm25_topk(segs, kind, terms, k, k1=1.2, filt=None, threshold_in=np.finfo(np.
                              C.byref(total), C.byref(scored))
     assert rc == 0
     return hits[:n_out.value].copy(), total.value, scored.value
+
+
+def bm25_topk_batch(segs, kind, queries_terms, k, k1=1.2, filt=None, threshold_in=np.finfo(np.float32).tiny,
+                    mode=2, threads=1):
+    """queries_terms: list of lists of BM25Term. Returns (hits [Q,k], n_out, total, postings_scored)."""
+    nq = len(queries_terms)
+    flat = [t for q in queries_terms for t in q]
+    off = np.zeros(nq + 1, np.uint32)
+    off[1:] = np.cumsum([len(q) for q in queries_terms])
+    hits = np.zeros((nq, k), dtype=HIT_DTYPE)
+    n_out = np.zeros(nq, np.uint32)
+    total = np.zeros(nq, np.uint64)
+    scored = C.c_uint64()
+    fp = C.byref(filt) if filt is not None else None
+    rc = lib().orc_bm25_topk_batch(_seg_array(segs), len(segs), 1 if kind in (1, "AND") else 0, term_array(flat),
+                                   ptr(off), nq, k1, fp, k, threshold_in, mode, threads, ptr(hits), ptr(n_out),
+                                   ptr(total), C.byref(scored))
+    assert rc == 0
+    return hits, n_out, total, scored.value
+
+
+def synth_segment_mt(n_docs, t0, nt, doc0=0, threads=8):
+    """Multi-threaded oracle builder for a synthetic shard: returns (Segment, docs_count[nt], sum_dl)."""
+    dc = np.zeros(nt, np.uint32)
+    sdl = C.c_uint64()
+    seg = Segment.__new__(Segment)
+    seg.n_docs = int(n_docs)
+    seg.h = lib().orc_synth_segment(doc0, n_docs, t0, nt, threads, ptr(dc), C.byref(sdl))
+    seg.has_wand = True
+    seg.has_norms = True
+    return seg, dc, sdl.value
 
 
 def filter_bitmap(seg, preds, rows):
