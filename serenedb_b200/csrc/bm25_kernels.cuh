@@ -232,8 +232,32 @@ decode_score_kernel(PostingsDev seg, uint32_t blk_begin, uint32_t nblk, float c0
 
 // ------------------------------------------------------------------------------------------
 // Fused scan + score + top-k kernel.
-// grid = (chains G, queries Q); CTA (g, q) handles windows g, g+G, ... of query q.
-// Shared memory (dynamic): acc[W] f32 | cnt[W] u8 (AND only) | mask[W/32] u32 | cand[cap] u64.
+//
+// grid = (chains G, queries Q). CTA (g, q) owns the doc range [1 + g*chunk, min(N, (g+1)*chunk)] of
+// query q and walks it in WINDOWS DEFINED BY A BLOCK BUDGET, not by a doc count: every window holds
+// at most kBudget posting blocks in total (kBudget / T per term), so the fixed per-window costs are
+// amortised over up to kBudget*128 postings whether the lists are dense (p = 0.5: a window spans a
+// few hundred docs) or sparse (p = 0.002: hundreds of thousands). The reference gets the same effect
+// from ComputeOuterWindow, which aligns windows with the essential lists' block boundaries
+// (search/max_score_iterator.hpp:510-539).
+//
+// Planning is one round of parallel loads: lane (t, j) of warp 0 reads the descriptor of block
+// cursor_t + j; the window ends at the earliest "m-th block end" over the terms that still have m
+// blocks (so no term can overlap the window with more than m blocks); a ballot yields the item list
+// and popcounts advance the cursors. The plan for window i+1 is computed while window i is processed.
+//
+// Window body (no shared-memory atomics, every loop is dense over lanes):
+//   1. decode: one warp per block; docs + BM25 scores land in shared memory as per-term arrays that
+//      are sorted by doc id (blocks of a term are consecutive, padding = 0xFFFFFFFF).
+//   2. fold: for t = 0 .. T-2 every live entry of terms <= t binary-searches term t+1; on a hit its
+//      score is added into the hit slot and the entry dies. A doc has at most one live entry at any
+//      step, so each slot has a unique writer and the sum is formed in ascending-cost order
+//      ((s0+s1)+s2..., ConjunctionScore's order, search/conjunction.hpp:185-195) -- bit-reproducible.
+//      For conjunctions an entry that misses dies too, so only the shortest list keeps searching.
+//   3. emit: live in-window entries -> column filter -> threshold -> ballot-compacted append to the
+//      per-CTA candidate buffer (bitonic select when full = nth_element at 2k, iterators.hpp:216-228).
+//
+// Shared memory (dynamic): docs[E] u32 | score[E] f32 | cnt[E] u8 (AND only) | cand[cap] u64, E = kBudget*128.
 // ------------------------------------------------------------------------------------------
 struct TopkParams {
   PostingsDev seg;
@@ -246,74 +270,110 @@ struct TopkParams {
   uint32_t* cand_n;            // [Q][lists]
   uint32_t lists;              // candidate lists per query = segments * chains
   uint32_t list_base;          // this segment's first list
-  uint32_t W;                  // window size in docs, multiple of 64
-  uint32_t n_windows;
+  uint32_t chunk;              // docs per chain
   uint32_t k;
   uint32_t cap;                // candidate buffer capacity, power of two, > k
   int32_t conjunction;         // 0 OR, 1 AND
 };
 
-// acc index swizzle: at emission a thread owns one mask word => 32 consecutive slots; XOR-ing the
-// low five bits with the word index spreads a warp's reads over all banks.
-__device__ __forceinline__ uint32_t swz(uint32_t i) { return i ^ ((i >> 5) & 31u); }
+constexpr uint32_t kPadDoc = 0xFFFFFFFFu;
 
+// First index in sorted a[0..n) with a[i] >= d (n > 0 is a multiple of 128).
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* a, uint32_t n, uint32_t d) {
+  uint32_t pos = 0;
+  for (uint32_t step = 1u << (31 - __clz(n)); step; step >>= 1) {
+    const uint32_t nxt = pos + step;
+    if (nxt <= n && a[nxt - 1u] < d) pos = nxt;
+  }
+  return pos;
+}
+
+template <uint32_t kBudget>
 __global__ void __launch_bounds__(kTopkThreads)
 bm25_topk_kernel(const TopkParams P) {
+  constexpr uint32_t kEntries = kBudget * 128u;
+  static_assert(kBudget <= 32, "one planner lane per block");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* acc = reinterpret_cast<float*>(smem_raw);
-  uint8_t* cnt = reinterpret_cast<uint8_t*>(acc + P.W);
-  uint32_t* mask = reinterpret_cast<uint32_t*>(cnt + (P.conjunction ? P.W : 0u));
-  unsigned long long* cand = reinterpret_cast<unsigned long long*>(mask + P.W / 32u);
+  uint32_t* e_doc = reinterpret_cast<uint32_t*>(smem_raw);
+  float* e_score = reinterpret_cast<float*>(e_doc + kEntries);
+  uint8_t* e_cnt = reinterpret_cast<uint8_t*>(e_score + kEntries);
+  unsigned long long* cand = reinterpret_cast<unsigned long long*>(e_cnt + (P.conjunction ? kEntries : 0u));
 
   __shared__ __align__(16) uint32_t stage[kTopkWarps][128];
-  __shared__ uint32_t s_first[2][kMaxQueryTerms];   // first overlapping block per term (double buffered)
-  __shared__ uint32_t s_prefix[2][kMaxQueryTerms + 1];
+  __shared__ __align__(16) uint4 s_item[2][32];        // descriptors of the window's blocks, term-major
+  __shared__ uint32_t s_item_term[2][32];
+  __shared__ uint32_t s_phase[2][kMaxQueryTerms + 1];  // first item of each term
+  __shared__ uint32_t s_lo[2], s_hi[2], s_valid[2];
   __shared__ uint32_t s_cursor[kMaxQueryTerms];
+  __shared__ QTermDev s_qt[kMaxQueryTerms];
   __shared__ uint32_t s_ncand, s_matched;
   __shared__ unsigned long long s_theta;
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  const uint32_t q = blockIdx.y, g = blockIdx.x, G = gridDim.x;
+  const uint32_t q = blockIdx.y, g = blockIdx.x;
   const uint32_t t0 = P.qterm_off[q];
   const uint32_t T = min(P.qterm_off[q + 1] - t0, kMaxQueryTerms);
-  const QTermDev* qt = P.qterms + t0;
-  const uint32_t words = P.W / 32u;
+  const uint32_t m = max(1u, kBudget / T);                       // block budget per term
+  const unsigned long long first64 = 1ull + static_cast<unsigned long long>(g) * P.chunk;
+  const bool chain_empty = first64 > P.seg.n_docs;
+  const uint32_t chain_lo = chain_empty ? 1u : uint32_t(first64);
+  const uint32_t chain_hi = chain_empty ? 0u : uint32_t(min(static_cast<unsigned long long>(P.seg.n_docs), first64 + P.chunk - 1ull));
 
-  for (uint32_t i = tid; i < P.W; i += blockDim.x) acc[i] = 0.f;
-  if (P.conjunction) for (uint32_t i = tid; i < P.W / 4u; i += blockDim.x) reinterpret_cast<uint32_t*>(cnt)[i] = 0u;
-  for (uint32_t i = tid; i < words; i += blockDim.x) mask[i] = 0u;
   for (uint32_t i = tid; i < P.cap; i += blockDim.x) cand[i] = 0ull;
-  if (tid < kMaxQueryTerms) s_cursor[tid] = 0u;
+  if (tid < T) s_qt[tid] = P.qterms[t0 + tid];
   if (tid == 0) { s_ncand = 0u; s_matched = 0u; s_theta = 0ull; }
   __syncthreads();
 
-  // Block range of term `lane` for window w: blocks whose [prev_last+1, last_doc] meets [lo, hi).
-  // Galloping search from the term's cursor (the windows of a chain only move forward).
-  auto plan_window = [&](uint32_t w, uint32_t buf) {
-    if (warp != 0) return;
-    uint32_t n = 0;
-    if (lane < T && w < P.n_windows) {
-      const uint32_t lo = 1u + w * P.W;
-      const unsigned long long hi_last64 = static_cast<unsigned long long>(lo) + P.W - 1ull;
-      const uint32_t hi_last = hi_last64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : uint32_t(hi_last64);  // last doc of the window
-      const uint4* B = P.seg.blocks + qt[lane].blk_begin;
-      const uint32_t nblk = qt[lane].nblk;
-      uint32_t a = s_cursor[lane], step = 1u;  // first block with last_doc >= lo
-      while (a + step <= nblk && __ldg(&B[a + step - 1u].y) < lo) { a += step; step <<= 1; }
-      uint32_t l = a, r = min(a + step - 1u, nblk);
-      while (l < r) { const uint32_t m = (l + r) >> 1; if (__ldg(&B[m].y) < lo) l = m + 1u; else r = m; }
-      const uint32_t first = l;
-      s_cursor[lane] = first;
-      uint32_t e = first; step = 1u;           // first block that starts after the window
-      while (e + step <= nblk && __ldg(&B[e + step - 1u].z) < hi_last) { e += step; step <<= 1; }
-      l = e; r = min(e + step - 1u, nblk);
-      while (l < r) { const uint32_t m = (l + r) >> 1; if (__ldg(&B[m].z) < hi_last) l = m + 1u; else r = m; }
-      n = l - first;
-      s_first[buf][lane] = first;
+  // Warp 0, lane t: first block of term t whose last doc reaches the chain (binary search, once).
+  if (warp == 0 && lane < T) {
+    const uint4* B = P.seg.blocks + s_qt[lane].blk_begin;
+    uint32_t l = 0, r = s_qt[lane].nblk;
+    while (l < r) { const uint32_t mid = (l + r) >> 1; if (__ldg(&B[mid].y) < chain_lo) l = mid + 1u; else r = mid; }
+    s_cursor[lane] = l;
+  }
+  __syncwarp();
+
+  // Plans the window starting at doc `lo` into buffer `buf` (warp 0 only); returns the next lo.
+  auto plan = [&](uint32_t lo, uint32_t buf) -> uint32_t {
+    if (lo > chain_hi || lo == 0u) {  // lo == 0: wrapped past 2^32-1
+      if (lane == 0) s_valid[buf] = 0u;
+      return 0u;
     }
-    const uint32_t incl = warp_incl_scan(n, lane);
-    if (lane < kMaxQueryTerms) s_prefix[buf][lane + 1] = incl;
-    if (lane == 0) s_prefix[buf][0] = 0u;
+    const uint32_t t = lane / m, j = lane - t * m;
+    const bool mine = t < T && lane < T * m;
+    uint4 d = make_uint4(0, 0, 0, 0);
+    bool exists = false;
+    if (mine) {
+      const uint32_t b = s_cursor[t] + j;
+      exists = b < s_qt[t].nblk;
+      if (exists) d = ld_ro_v4(P.seg.blocks + s_qt[t].blk_begin + b);
+    }
+    // a term that still has m blocks bounds the window at the end of its m-th block
+    uint32_t hi = (exists && j == m - 1u) ? d.y : 0xFFFFFFFFu;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) hi = min(hi, __shfl_xor_sync(kFull, hi, o));
+    hi = min(hi, chain_hi);
+    const bool overlap = exists && d.z < hi;           // first doc of the block (prev_last + 1) <= hi
+    const bool consumed = exists && d.y <= hi;          // block ends inside the window
+    const uint32_t ov = __ballot_sync(kFull, overlap);
+    const uint32_t co = __ballot_sync(kFull, consumed);
+    if (overlap) {
+      const uint32_t idx = __popc(ov & ((1u << lane) - 1u));
+      s_item[buf][idx] = d;
+      s_item_term[buf][idx] = t;
+    }
+    if (lane <= T) {  // first item of term `lane` = overlapping lanes below the term's first lane
+      const uint32_t first_lane = min(lane * m, 32u);
+      s_phase[buf][lane] = first_lane >= 32u ? __popc(ov) : __popc(ov & ((1u << first_lane) - 1u));
+    }
+    if (lane < T) {
+      const uint32_t lo_l = lane * m, n = min(m, 32u - lo_l);
+      const uint32_t bits = n >= 32u ? 0xFFFFFFFFu : (((1u << n) - 1u) << lo_l);
+      s_cursor[lane] += __popc(co & bits);
+    }
+    if (lane == 0) { s_lo[buf] = lo; s_hi[buf] = hi; s_valid[buf] = 1u; }
+    __syncwarp();
+    return hi + 1u;  // wraps to 0 at 2^32-1: treated as "past the end"
   };
 
   // Sort the candidate buffer, keep the best k, raise the thresholds. All threads call it.
@@ -335,93 +395,107 @@ bm25_topk_kernel(const TopkParams P) {
     __syncthreads();
   };
 
-  plan_window(g, 0);
+  uint32_t next_lo = 0;  // meaningful in warp 0 only
+  if (warp == 0) next_lo = plan(chain_lo, 0);
   __syncthreads();
 
-  uint32_t buf = 0;
-  for (uint32_t w = g; w < P.n_windows; w += G, buf ^= 1u) {
-    const uint32_t lo = 1u + w * P.W;
-    const uint32_t span = min(P.W, P.seg.n_docs - (lo - 1u));  // docs lo .. lo+span-1
+  for (uint32_t buf = 0; s_valid[buf]; buf ^= 1u) {
+    const uint32_t lo = s_lo[buf], hi = s_hi[buf];
+    const uint32_t n_items = s_phase[buf][T];
     if (tid == 0) {  // pick up thresholds published by other chains / earlier segments
       const unsigned long long gt = *reinterpret_cast<volatile unsigned long long*>(P.theta + q);
       if (gt > s_theta) s_theta = gt;
     }
-    plan_window(w + G, buf ^ 1u);  // warp 0 plans the next window, then joins the work below
+    if (warp == 0) next_lo = plan(next_lo, buf ^ 1u);  // next window's plan overlaps this window's work
 
-    // ---- accumulate: one 128-posting block per warp iteration ----
-    // fp32 addition commutes, so two terms may add into a slot in any order; with three or more
-    // the sum order matters, so terms are processed in phases of ascending cost (the order
-    // ConjunctionScore uses, conjunction.hpp:185-195) to keep scores bit-reproducible.
-    const uint32_t phases = T > 2u ? T : 1u;
-    for (uint32_t ph = 0; ph < phases; ++ph) {
-    const uint32_t it_begin = phases > 1u ? s_prefix[buf][ph] : 0u;
-    const uint32_t it_end = phases > 1u ? s_prefix[buf][ph + 1u] : s_prefix[buf][T];
-    for (uint32_t it = it_begin + warp; it < it_end; it += kTopkWarps) {
-      uint32_t t = ph;
-      if (phases == 1u) { t = 0; while (t + 1u < T && it >= s_prefix[buf][t + 1u]) ++t; }
-      const uint32_t b = s_first[buf][t] + (it - s_prefix[buf][t]);
-      const uint4 d = ld_ro_v4(P.seg.blocks + qt[t].blk_begin + b);
+    // ---- 1. decode + score: one 128-posting block per warp iteration -> entries [it*128, it*128+128) ----
+    for (uint32_t it = warp; it < n_items; it += kTopkWarps) {
+      const uint4 d = s_item[buf][it];
+      const uint32_t t = s_item_term[buf][it];
       uint32_t doc[4], f[4];
       decode_docs(P.seg.arena, d, lane, stage[warp], doc);
       decode_freqs(P.seg.arena, d, lane, f);
       const uint32_t len = desc_len(d.w);
-      const float c0 = qt[t].c0, nc = qt[t].norm_const, nl = qt[t].norm_length;
+      const float c0 = s_qt[t].c0, nc = s_qt[t].norm_const, nl = s_qt[t].norm_length;
       uint32_t nrm[4]; bool in[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint32_t off = doc[j] - lo;
-        in[j] = (4u * lane + j < len) && off < span;
-        nrm[j] = in[j] ? load_norm(P.seg.norms, P.seg.norm_width, doc[j]) : 1u;
+        if (4u * lane + j >= len) doc[j] = kPadDoc;       // short (last) block of a list: pad sorts last
+        in[j] = doc[j] >= lo && doc[j] <= hi;               // docs of a straddling block outside the window stay
+        nrm[j] = in[j] ? load_norm(P.seg.norms, P.seg.norm_width, doc[j]) : 1u;   // in the array (sortedness) but are never emitted
       }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (in[j]) {
-          const uint32_t off = doc[j] - lo;
-          atomicAdd(&acc[swz(off)], bm25(f[j], nrm[j], c0, nc, nl));
-          atomicOr(&mask[off >> 5], 1u << (off & 31u));
-          if (P.conjunction) atomicAdd(reinterpret_cast<uint32_t*>(cnt) + (off >> 2), 1u << (8u * (off & 3u)));
-        }
-      }
-    }
-    if (ph + 1u < phases) __syncthreads();
+      uint4 od; float4 os;
+      od.x = doc[0]; od.y = doc[1]; od.z = doc[2]; od.w = doc[3];
+      os.x = in[0] ? bm25(f[0], nrm[0], c0, nc, nl) : 0.f;
+      os.y = in[1] ? bm25(f[1], nrm[1], c0, nc, nl) : 0.f;
+      os.z = in[2] ? bm25(f[2], nrm[2], c0, nc, nl) : 0.f;
+      os.w = in[3] ? bm25(f[3], nrm[3], c0, nc, nl) : 0.f;
+      reinterpret_cast<uint4*>(e_doc + it * 128u)[lane] = od;
+      reinterpret_cast<float4*>(e_score + it * 128u)[lane] = os;
+      if (P.conjunction) reinterpret_cast<uint32_t*>(e_cnt + it * 128u)[lane] = 0u;
     }
     __syncthreads();
 
-    // ---- emit: matched slots -> filter -> threshold -> candidate buffer (optimistic append;
-    //      slots that do not fit stay set and are retried after a compaction) ----
+    // ---- 2. fold term t into term t+1 (sources: live entries of terms 0..t) ----
+    for (uint32_t t = 0; t + 1u < T; ++t) {
+      const uint32_t src_end = s_phase[buf][t + 1u] * 128u;
+      const uint32_t dst_begin = src_end, dst_n = (s_phase[buf][t + 2u] - s_phase[buf][t + 1u]) * 128u;
+      // Conjunction: the only candidates still alive at step t sit in term t's own slots and have
+      // collected every earlier term (cnt == t); anything else can never complete.
+      const uint32_t src_begin = P.conjunction ? s_phase[buf][t] * 128u : 0u;
+      for (uint32_t e = src_begin + tid; e < src_end; e += blockDim.x) {
+        const uint32_t d = e_doc[e];
+        if (d == kPadDoc) continue;
+        if (P.conjunction && e_cnt[e] != t) { e_doc[e] = kPadDoc; continue; }
+        uint32_t pos = dst_n;
+        if (dst_n) pos = lower_bound_u32(e_doc + dst_begin, dst_n, d);
+        if (pos < dst_n && e_doc[dst_begin + pos] == d) {
+          e_score[dst_begin + pos] = __fadd_rn(e_score[e], e_score[dst_begin + pos]);
+          if (P.conjunction) e_cnt[dst_begin + pos] = uint8_t(e_cnt[e] + 1u);
+          e_doc[e] = kPadDoc;                 // folded: the target slot now carries this doc
+        } else if (P.conjunction) {
+          e_doc[e] = kPadDoc;                 // conjunction: a miss kills the candidate
+        }
+      }
+      __syncthreads();
+    }
+
+    // ---- 3. emit live in-window entries ----
+    const uint32_t n_entries = n_items * 128u;
+    const uint32_t emit_begin = P.conjunction ? s_phase[buf][T - 1u] * 128u : 0u;  // AND: only the last term's slots can be complete
     for (;;) {
       const unsigned long long theta = s_theta;
-      uint32_t matched = 0, pending = 0;
-      for (uint32_t wi = tid; wi < words; wi += blockDim.x) {
-        uint32_t m = mask[wi];
-        if (!m) continue;
-        uint32_t keep = 0;
-        while (m) {
-          const uint32_t bit = __ffs(m) - 1u;
-          m &= m - 1u;
-          const uint32_t off = wi * 32u + bit;
-          const uint32_t si = swz(off);
-          const uint32_t doc = lo + off;
-          const bool ok = (!P.conjunction || cnt[off] == T) && filter_pass(P.filt, doc);
-          if (ok) {
-            const unsigned long long key = make_key(acc[si], P.seg.ordinal_base + doc);
-            if (key > theta) {
-              const uint32_t pos = atomicAdd(&s_ncand, 1u);
-              if (pos >= P.cap) { keep |= 1u << bit; continue; }
-              cand[pos] = key;
-            }
-            ++matched;
-          }
-          acc[si] = 0.f;
-          if (P.conjunction) cnt[off] = 0;
+      uint32_t matched = 0;
+      bool pending = false;
+      for (uint32_t e0 = emit_begin; e0 < n_entries; e0 += blockDim.x) {
+        const uint32_t e = e0 + tid;
+        uint32_t d = e < n_entries ? e_doc[e] : kPadDoc;
+        bool live = d != kPadDoc && d >= lo && d <= hi;
+        if (live && P.conjunction) live = e_cnt[e] == T - 1u;
+        if (live) live = filter_pass(P.filt, d);
+        unsigned long long key = 0ull;
+        bool want = false;
+        if (live) {
+          key = make_key(e_score[e], P.seg.ordinal_base + d);
+          want = key > theta;
         }
-        mask[wi] = keep;
-        pending |= keep;
+        // warp-aggregated append: one shared atomic per warp
+        const uint32_t wb = __ballot_sync(kFull, want);
+        uint32_t base = 0;
+        if (lane == 0 && wb) base = atomicAdd(&s_ncand, uint32_t(__popc(wb)));
+        base = __shfl_sync(kFull, base, 0);
+        bool stored = true;
+        if (want) {
+          const uint32_t pos = base + __popc(wb & ((1u << lane) - 1u));
+          if (pos < P.cap) cand[pos] = key; else { stored = false; pending = true; }
+        }
+        if (live && stored) { ++matched; e_doc[e] = kPadDoc; }   // done with this entry (not retried)
+        else if (e < n_entries && !live) e_doc[e] = kPadDoc;
       }
       matched = warp_sum(matched);
       if (lane == 0 && matched) atomicAdd(&s_matched, matched);
-      if (!__syncthreads_or(pending != 0u)) break;
-      compact();  // buffer overflowed: select, raise the threshold, retry what is left
+      if (!__syncthreads_or(int(pending))) break;
+      compact();  // buffer overflowed: select, raise the threshold, retry the entries that did not fit
     }
   }
 

@@ -442,7 +442,7 @@ int filter_view(sdbg_segment* s, const sdbg_col_pred* f, FilterDev* out) {
 }
 
 struct TopkPlan {
-  uint32_t W, n_windows_max, G, lists, cap, k;
+  uint32_t G, lists, cap, k, chunk, budget;
   size_t smem;
 };
 
@@ -462,28 +462,31 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
     if (nt == 0 || nt > kMaxQueryTerms) return fail(c, SDBG_EUNSUPPORTED, "a query needs 1..16 terms");
   }
   uint64_t ord = 0;
+  uint32_t max_docs = 0;
   for (size_t si = 0; si < n_segs; ++si) {
     if (segs[si]->ctx != c) return fail(c, SDBG_EINVAL, "segments of one call must share a context");
     if (!segs[si]->d_blocks) return fail(c, SDBG_EINVAL, "segment has no staged postings");
     ord += segs[si]->n_docs;
+    max_docs = std::max(max_docs, segs[si]->n_docs);
   }
   if (ord >= 0xFFFFFFFFull) return fail(c, SDBG_EUNSUPPORTED, "more than 2^32-1 docs per GPU");
 
   TopkPlan pl;
   pl.k = k;
-  pl.W = uint32_t(env_int("SDBG_TOPK_WINDOW", 8192));
-  if (pl.W < 256 || (pl.W & 63)) return fail(c, SDBG_EINVAL, "SDBG_TOPK_WINDOW must be a multiple of 64, >= 256");
+  pl.budget = uint32_t(env_int("SDBG_TOPK_BUDGET", 16));
+  if (pl.budget != 16 && pl.budget != 32) return fail(c, SDBG_EINVAL, "SDBG_TOPK_BUDGET must be 16 or 32");
+  const uint32_t entries = pl.budget * 128u;
   pl.cap = next_pow2(k + 1024);
-  uint32_t max_docs = 0;
-  for (size_t si = 0; si < n_segs; ++si) max_docs = std::max(max_docs, segs[si]->n_docs);
-  pl.n_windows_max = (max_docs + pl.W - 1) / pl.W;
-  const uint32_t target_ctas = uint32_t(c->sm_count) * 6u;
+  // Enough CTAs to fill the machine a few times over; a query is split into chains (contiguous doc
+  // ranges) only when the batch alone cannot do that.
+  const uint32_t target_ctas = uint32_t(c->sm_count) * 8u;
   pl.G = uint32_t(std::max<size_t>(1, (target_ctas + nq - 1) / nq));
-  pl.G = std::min(pl.G, std::max(1u, pl.n_windows_max));
   pl.G = std::min(pl.G, uint32_t(env_int("SDBG_TOPK_MAX_CHAINS", 296)));
+  pl.G = std::min(pl.G, std::max(1u, max_docs / 4096u));
+  pl.chunk = (max_docs + pl.G - 1) / pl.G;
   pl.lists = pl.G * uint32_t(n_segs);
-  pl.smem = size_t(pl.W) * 4 + (kind == SDBG_QUERY_AND ? pl.W : 0) + pl.W / 8 + size_t(pl.cap) * 8;
-  if (pl.smem > 200 * 1024) return fail(c, SDBG_EUNSUPPORTED, "window + candidate buffer exceed shared memory");
+  pl.smem = size_t(entries) * 8 + (kind == SDBG_QUERY_AND ? entries : 0) + size_t(pl.cap) * 8;
+  if (pl.smem > 200 * 1024) return fail(c, SDBG_EUNSUPPORTED, "hash window + candidate buffer exceed shared memory");
 
   // host-side query descriptors, per segment, sorted by ascending docs_count (conjunction.hpp:520-523)
   const size_t qt_bytes = size_t(total_terms) * sizeof(QTermDev) * n_segs;
@@ -530,7 +533,8 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
   CU(c, cudaMemsetAsync(d_total, 0, nq * 8, c->stream));
 
   if (!c->topk_attr_set) {
-    CU(c, cudaFuncSetAttribute(bm25_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(c, cudaFuncSetAttribute(bm25_topk_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(c, cudaFuncSetAttribute(bm25_topk_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(c, cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     c->topk_attr_set = true;
   }
@@ -546,10 +550,11 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
     P.cand = static_cast<unsigned long long*>(b_cand.p);
     P.cand_n = static_cast<uint32_t*>(b_candn.p);
     P.lists = pl.lists; P.list_base = uint32_t(si) * pl.G;
-    P.W = pl.W; P.n_windows = (s->n_docs + pl.W - 1) / pl.W;
+    P.chunk = pl.chunk;
     P.k = k; P.cap = pl.cap; P.conjunction = kind == SDBG_QUERY_AND ? 1 : 0;
     { ProfScope ps_(c, kProfTopk);
-      bm25_topk_kernel<<<dim3(pl.G, unsigned(nq)), kTopkThreads, pl.smem, c->stream>>>(P); }
+      if (pl.budget == 16) bm25_topk_kernel<16><<<dim3(pl.G, unsigned(nq)), kTopkThreads, pl.smem, c->stream>>>(P);
+      else bm25_topk_kernel<32><<<dim3(pl.G, unsigned(nq)), kTopkThreads, pl.smem, c->stream>>>(P); }
     ++c->launches;
     CU(c, cudaGetLastError());
     base += s->n_docs;
@@ -690,10 +695,9 @@ extern "C" int sdbg_topk_merge_gathered(sdbg_ctx* c, const void* d_keys_all, uin
                             static_cast<const char*>(d_keys_all) + size_t(r) * nq * k * 8, size_t(k) * 8, size_t(k) * 8, nq,
                             cudaMemcpyDeviceToDevice, c->stream));
   const uint32_t cap = next_pow2(k + 1024);
-  if (!c->topk_attr_set) {
-    CU(c, cudaFuncSetAttribute(bm25_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  if (!c->merge_attr_set) {
     CU(c, cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    c->topk_attr_set = true;
+    c->merge_attr_set = true;
   }
   MergeParams M;
   M.cand = static_cast<const unsigned long long*>(b_in.p); M.cand_n = nullptr;
@@ -971,23 +975,34 @@ extern "C" int sdbg_groupby_finalize(sdbg_ctx* c, int64_t key_min, uint64_t span
                                      sdbg_group_row* out, uint64_t cap, uint64_t* n_out) {
   if (!c || !d_i64 || !d_f64 || !out || !n_out || !span) return SDBG_EINVAL;
   CU(c, cudaSetDevice(c->device));
-  static_assert(sizeof(GroupRowDev) == sizeof(sdbg_group_row), "device row mirrors the ABI row");
+  // The dense partials are exactly as large as the answer (40 B per key), so they cross PCIe once
+  // into pinned memory and the ascending-key compaction of non-empty groups is a host loop -- one
+  // stream synchronisation per call instead of a compaction kernel plus three.
   int rc;
-  const uint64_t dev_cap = std::min<uint64_t>(cap, span);
-  if ((rc = ensure(c, c->scratch[9], dev_cap * sizeof(GroupRowDev) + 16))) return rc;
-  auto* d_n = reinterpret_cast<unsigned long long*>(static_cast<char*>(c->scratch[9].p) + dev_cap * sizeof(GroupRowDev));
-  // limbs: a narrow sum has hi == 0 everywhere, and hi*2^32 + lo is then just lo => always finalize "wide".
-  groupby_compact_kernel<<<1, 256, 0, c->stream>>>(static_cast<const long long*>(d_i64), static_cast<const double*>(d_f64), span,
-                                                   key_min, 1, static_cast<GroupRowDev*>(c->scratch[9].p), d_n, dev_cap);
-  ++c->launches;
-  CU(c, cudaGetLastError());
-  unsigned long long n = 0;
-  CU(c, cudaMemcpyAsync(&n, d_n, 8, cudaMemcpyDeviceToHost, c->stream));
+  if ((rc = ensure_pinned(c, span * 40))) return rc;
+  auto* h_i = static_cast<long long*>(c->h_pinned);
+  auto* h_f = reinterpret_cast<double*>(h_i + 4 * span);
+  CU(c, cudaMemcpyAsync(h_i, d_i64, span * 32, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(h_f, d_f64, span * 8, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
+  uint64_t n = 0;
+  for (uint64_t i = 0; i < span; ++i) {
+    if (h_i[i] == 0) continue;
+    if (n < cap) {
+      sdbg_group_row& r = out[n];
+      r.key = key_min + int64_t(i);
+      r.count = uint64_t(h_i[i]);
+      // SUM(int) limbs: total = hi * 2^32 + lo (a narrow sum has hi == 0); exact in 128 bits.
+      const __int128 tot = (static_cast<__int128>(h_i[2 * span + i]) << 32) + static_cast<__int128>(h_i[span + i]);
+      r.sum_i128[0] = int64_t(uint64_t(static_cast<unsigned __int128>(tot)));
+      r.sum_i128[1] = int64_t(uint64_t(static_cast<unsigned __int128>(tot) >> 64));
+      r.sum_f64 = h_f[i];
+      r.cnt_f64 = uint64_t(h_i[3 * span + i]);
+    }
+    ++n;
+  }
   *n_out = n;
   if (n > cap) return fail(c, SDBG_ECAPACITY, "group output buffer too small");
-  CU(c, cudaMemcpyAsync(out, c->scratch[9].p, n * sizeof(GroupRowDev), cudaMemcpyDeviceToHost, c->stream));
-  CU(c, cudaStreamSynchronize(c->stream));
   return SDBG_OK;
 }
 
