@@ -308,6 +308,7 @@ bm25_topk_kernel(const TopkParams P) {
   __shared__ QTermDev s_qt[kMaxQueryTerms];
   __shared__ uint32_t s_ncand, s_matched;
   __shared__ unsigned long long s_theta;
+  __shared__ uint32_t s_hist[258];
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t q = blockIdx.y, g = blockIdx.x;
@@ -376,22 +377,19 @@ bm25_topk_kernel(const TopkParams P) {
     return hi + 1u;  // wraps to 0 at 2^32-1: treated as "past the end"
   };
 
-  // Sort the candidate buffer, keep the best k, raise the thresholds. All threads call it.
+  // Candidate buffer full: exact radix select keeps the best k and raises the thresholds (the GPU
+  // analogue of nth_element at 2k, iterators.hpp:216-228). All threads call it.
   auto compact = [&]() {
-    block_sort_desc(cand, P.cap);
-    if (tid == 0) {
-      const uint32_t have = min(s_ncand, P.cap);
-      if (have > P.k) {
-        const unsigned long long kth = cand[P.k - 1u];
+    if (min(s_ncand, P.cap) > P.k) {       // uniform (shared value, read after a barrier)
+      const unsigned long long kth = block_select_topk(cand, P.cap, P.k, s_hist);
+      if (tid == 0) {
         if (kth > s_theta) s_theta = kth;
         atomicMax(P.theta + q, kth);
         s_ncand = P.k;
-      } else {
-        s_ncand = have;
       }
+    } else if (tid == 0) {
+      s_ncand = min(s_ncand, P.cap);
     }
-    __syncthreads();
-    for (uint32_t i = s_ncand + tid; i < P.cap; i += blockDim.x) cand[i] = 0ull;
     __syncthreads();
   };
 
@@ -499,10 +497,13 @@ bm25_topk_kernel(const TopkParams P) {
     }
   }
 
-  // ---- chain epilogue: sorted candidates + counts to global ----
+  // ---- chain epilogue: best k, sorted descending (only the first pow2(k) slots need the sort) ----
   __syncthreads();
   compact();
   const uint32_t n_out = min(s_ncand, P.k);
+  uint32_t sort_n = 256u;
+  while (sort_n < n_out) sort_n <<= 1;      // compact() left the survivors in [0, n_out) and zeros behind them
+  block_sort_desc(cand, sort_n);
   const size_t list = size_t(q) * P.lists + P.list_base + g;
   unsigned long long* out = P.cand + list * P.cap;
   for (uint32_t i = tid; i < P.cap; i += blockDim.x) out[i] = i < n_out ? cand[i] : 0ull;
@@ -513,13 +514,15 @@ bm25_topk_kernel(const TopkParams P) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Merge the G sorted candidate lists of each query into its final top-k (one CTA per query).
-// keys_out[q][k] sorted descending, zero-padded. Streaming: buffer = [best k so far | next chunk].
+// Merge the candidate lists of each query into its final top-k (one CTA per query).
+// keys_out[q][k] sorted descending, zero-padded. Streaming: buffer = [best so far | next chunk];
+// when the buffer is full an exact radix select keeps the best k; one bitonic sort at the end.
+// Lists are sorted descending, so a list whose head is below the current k-th is skipped outright.
 // ------------------------------------------------------------------------------------------
 struct MergeParams {
   const unsigned long long* cand;  // [Q][G][stride]
   const uint32_t* cand_n;          // [Q][G] (null => every list holds `stride` entries, zeros = empty)
-  uint32_t G, stride, k, cap;      // cap = power of two >= k + chunk
+  uint32_t G, stride, k, cap;      // cap = power of two > k, multiple of the CTA size
   unsigned long long* keys_out;    // [Q][k]
   uint32_t* n_out;                 // [Q]
 };
@@ -529,33 +532,45 @@ topk_merge_kernel(const MergeParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* buf = reinterpret_cast<unsigned long long*>(smem_raw);
   __shared__ uint32_t s_n;
+  __shared__ unsigned long long s_kth;
+  __shared__ uint32_t s_hist[258];
   const uint32_t q = blockIdx.x, tid = threadIdx.x;
   for (uint32_t i = tid; i < P.cap; i += blockDim.x) buf[i] = 0ull;
-  if (tid == 0) s_n = 0u;
+  if (tid == 0) { s_n = 0u; s_kth = 0ull; }
   __syncthreads();
-  const uint32_t room = P.cap - P.k;  // new entries per round
   for (uint32_t g = 0; g < P.G; ++g) {
     const unsigned long long* src = P.cand + (size_t(q) * P.G + g) * P.stride;
     const uint32_t n = P.cand_n ? min(P.cand_n[size_t(q) * P.G + g], P.stride) : P.stride;
-    for (uint32_t base = 0; base < n; base += room) {
-      const uint32_t take = min(room, n - base);
+    uint32_t base = 0;
+    while (base < n) {
       const uint32_t have = s_n;
+      const unsigned long long kth = s_kth;
       __syncthreads();
-      // Lists are sorted descending: once the head of a chunk is below the current k-th, stop.
-      if (have == P.k && src[base] <= buf[P.k - 1u]) break;
+      if (src[base] <= kth) break;                       // sorted list: nothing below can matter
+      const uint32_t take = min(P.cap - have, n - base);
       for (uint32_t i = tid; i < take; i += blockDim.x) buf[have + i] = src[base + i];
       __syncthreads();
-      block_sort_desc(buf, P.cap);
-      if (tid == 0) {
-        uint32_t cntv = min(have + take, P.k);
-        s_n = cntv;
+      base += take;
+      if (have + take == P.cap) {                        // full: keep the best k
+        const unsigned long long nk = block_select_topk(buf, P.cap, P.k, s_hist);
+        if (tid == 0) { s_n = P.k; if (nk > s_kth) s_kth = nk; }
+      } else if (tid == 0) {
+        s_n = have + take;
       }
-      __syncthreads();
-      for (uint32_t i = s_n + tid; i < P.cap; i += blockDim.x) buf[i] = 0ull;
       __syncthreads();
     }
   }
-  // zeros are "empty": count the real ones
+  if (s_n > P.k) {
+    block_select_topk(buf, P.cap, P.k, s_hist);
+    if (tid == 0) s_n = P.k;
+    __syncthreads();
+  }
+  uint32_t sort_n = 256u;
+  while (sort_n < min(s_n, P.k)) sort_n <<= 1;
+  // entries beyond s_n may be stale-free zeros only when a select ran; make sure of it before sorting
+  for (uint32_t i = s_n + tid; i < sort_n; i += blockDim.x) buf[i] = 0ull;
+  __syncthreads();
+  block_sort_desc(buf, sort_n);
   uint32_t real = 0;
   for (uint32_t i = tid; i < P.k; i += blockDim.x) {
     const unsigned long long v = i < s_n ? buf[i] : 0ull;

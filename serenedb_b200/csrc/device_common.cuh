@@ -74,4 +74,81 @@ __device__ __forceinline__ void block_sort_desc(unsigned long long* s, uint32_t 
   }
 }
 
+
+// Exact top-k selection of 64-bit keys in shared memory, O(n): MSB-first radix select finds the k-th
+// largest key (keys are unique: the doc ordinal is part of the key), then the keys >= it are compacted
+// to the front (order not preserved) and the rest of the buffer is zeroed. Zero = empty slot.
+// Requires n_slots % blockDim.x == 0 and n_slots / blockDim.x <= 16; `hist` = 256 + 2 u32 of shared
+// scratch. All threads call it; ends with a barrier. Returns the k-th largest key (0 if fewer than k
+// non-empty keys, in which case nothing is dropped).
+__device__ __forceinline__ unsigned long long block_select_topk(unsigned long long* keys, uint32_t n_slots, uint32_t k,
+                                                                uint32_t* hist) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t per = n_slots / blockDim.x;
+  if (per > 16u) {  // very large k: fall back to a full sort (rare; keeps register use bounded)
+    block_sort_desc(keys, n_slots);
+    const unsigned long long kth_s = keys[k - 1u];
+    __syncthreads();
+    for (uint32_t i = k + tid; i < n_slots; i += blockDim.x) keys[i] = 0ull;
+    __syncthreads();
+    return kth_s;
+  }
+  unsigned long long mine[16];
+#pragma unroll
+  for (uint32_t i = 0; i < 16; ++i) mine[i] = i < per ? keys[i * blockDim.x + tid] : 0ull;
+  unsigned long long prefix = 0ull, mask = 0ull;
+  uint32_t need = k;
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    if (tid < 256) hist[tid] = 0u;
+    __syncthreads();
+#pragma unroll
+    for (uint32_t i = 0; i < 16; ++i)
+      if (i < per && mine[i] != 0ull && (mine[i] & mask) == prefix) atomicAdd(&hist[(mine[i] >> shift) & 255ull], 1u);
+    __syncthreads();
+    if (warp == 0) {
+      // lane l owns digits 255-8l .. 248-8l (descending); find the digit where the running count reaches `need`
+      uint32_t c[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { c[j] = hist[255 - 8 * int(lane) - j]; sum += c[j]; }
+      const uint32_t above = warp_incl_scan(sum, lane) - sum;  // keys in strictly higher digits of higher lanes
+      uint32_t run = above, found = 0xFFFFFFFFu, need_in = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (found == 0xFFFFFFFFu && run < need && run + c[j] >= need) { found = 255u - 8u * lane - uint32_t(j); need_in = need - run; }
+        run += c[j];
+      }
+      const uint32_t who = __ballot_sync(kFull, found != 0xFFFFFFFFu);
+      if (who == 0u) { if (lane == 0) { hist[256] = 0xFFFFFFFFu; hist[257] = 0u; } }   // fewer than `need` keys in total
+      else if (lane == uint32_t(__ffs(who) - 1)) { hist[256] = found; hist[257] = need_in; }
+    }
+    __syncthreads();
+    const uint32_t digit = hist[256];
+    need = hist[257];
+    __syncthreads();
+    if (digit == 0xFFFFFFFFu) return 0ull;   // uniform: fewer than k keys, keep everything
+    prefix |= static_cast<unsigned long long>(digit) << shift;
+    mask |= 0xFFull << shift;
+  }
+  const unsigned long long kth = prefix;
+  // compact survivors (key >= kth) to the front; every thread already holds its keys in registers
+  uint32_t keep = 0;
+#pragma unroll
+  for (uint32_t i = 0; i < 16; ++i) keep += (i < per && mine[i] >= kth && mine[i] != 0ull) ? 1u : 0u;
+  const uint32_t incl = warp_incl_scan(keep, lane);
+  if (lane == 31) hist[warp] = incl;
+  __syncthreads();
+  uint32_t base = incl - keep;
+  for (uint32_t w = 0; w < warp; ++w) base += hist[w];
+  uint32_t total = 0;
+  for (uint32_t w = 0; w < blockDim.x / 32u; ++w) total += hist[w];
+  __syncthreads();
+#pragma unroll
+  for (uint32_t i = 0; i < 16; ++i)
+    if (i < per && mine[i] >= kth && mine[i] != 0ull) keys[base++] = mine[i];
+  __syncthreads();
+  for (uint32_t i = total + tid; i < n_slots; i += blockDim.x) keys[i] = 0ull;
+  __syncthreads();
+  return kth;
+}
+
 }  // namespace sdbg

@@ -476,7 +476,7 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
   pl.budget = uint32_t(env_int("SDBG_TOPK_BUDGET", 16));
   if (pl.budget != 16 && pl.budget != 32) return fail(c, SDBG_EINVAL, "SDBG_TOPK_BUDGET must be 16 or 32");
   const uint32_t entries = pl.budget * 128u;
-  pl.cap = next_pow2(k + 1024);
+  pl.cap = std::max(next_pow2(k + 1024), 4096u);  // O(n) radix select makes a roomy buffer cheap: fewer selections
   // Enough CTAs to fill the machine a few times over; a query is split into chains (contiguous doc
   // ranges) only when the batch alone cannot do that.
   const uint32_t target_ctas = uint32_t(c->sm_count) * 8u;
@@ -694,7 +694,7 @@ extern "C" int sdbg_topk_merge_gathered(sdbg_ctx* c, const void* d_keys_all, uin
     CU(c, cudaMemcpy2DAsync(static_cast<char*>(b_in.p) + size_t(r) * k * 8, size_t(n_ranks) * k * 8,
                             static_cast<const char*>(d_keys_all) + size_t(r) * nq * k * 8, size_t(k) * 8, size_t(k) * 8, nq,
                             cudaMemcpyDeviceToDevice, c->stream));
-  const uint32_t cap = next_pow2(k + 1024);
+  const uint32_t cap = std::max(next_pow2(k + 1024), 4096u);
   if (!c->merge_attr_set) {
     CU(c, cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     c->merge_attr_set = true;
