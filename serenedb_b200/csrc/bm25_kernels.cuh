@@ -118,18 +118,29 @@ __device__ __forceinline__ void decode_docs(const uint4* arena, const uint4& d, 
     unpack4(p, enc - 6u, lane, doc);
     prefix_from_gaps(prev, lane, doc);
   } else if (enc == 4u) {  // de_for_bitset: bit j set => id prev + j
-    const uint32_t words = desc_words(d.w);
-    unsigned long long w0 = 0, w1 = 0;
-    if (2u * lane < words) {
-      const uint4 x = ld_ro_v4(p + lane);
-      w0 = (static_cast<unsigned long long>(x.y) << 32) | x.x;
-      if (2u * lane + 1u < words) w1 = (static_cast<unsigned long long>(x.w) << 32) | x.z;
+    // Position-parallel expansion: in iteration i every lane tests bit 32*i + lane of the bitset (the
+    // 32-bit chunk is broadcast from the lane that loaded it) and a set bit is written to its rank
+    // (= set bits before it). All lanes run the same trip count, unlike a per-lane "next set bit" loop.
+    const uint32_t words = desc_words(d.w);             // 64-bit words, <= 64
+    uint4 x = make_uint4(0, 0, 0, 0);                    // lane l holds 32-bit chunks 4l .. 4l+3
+    if (2u * lane < words) x = ld_ro_v4(p + lane);
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t base = 0;
+    const uint32_t chunks = 2u * words;
+    for (uint32_t i = 0; i < chunks; i += 4u) {
+      const uint32_t src = i >> 2;
+      const uint32_t c0 = __shfl_sync(kFull, x.x, src), c1 = __shfl_sync(kFull, x.y, src);
+      const uint32_t c2 = __shfl_sync(kFull, x.z, src), c3 = __shfl_sync(kFull, x.w, src);
+      const uint32_t id = prev + 32u * i + lane;
+      if ((c0 >> lane) & 1u) stage[base + __popc(c0 & lt)] = id;
+      base += __popc(c0);
+      if ((c1 >> lane) & 1u) stage[base + __popc(c1 & lt)] = id + 32u;
+      base += __popc(c1);
+      if ((c2 >> lane) & 1u) stage[base + __popc(c2 & lt)] = id + 64u;
+      base += __popc(c2);
+      if ((c3 >> lane) & 1u) stage[base + __popc(c3 & lt)] = id + 96u;
+      base += __popc(c3);
     }
-    const uint32_t c = __popcll(w0) + __popcll(w1);
-    uint32_t r = warp_incl_scan(c, lane) - c;
-    const uint32_t id0 = prev + 128u * lane;
-    for (; w0; w0 &= w0 - 1) stage[r++] = id0 + uint32_t(__ffsll(static_cast<long long>(w0)) - 1);
-    for (; w1; w1 &= w1 - 1) stage[r++] = id0 + 64u + uint32_t(__ffsll(static_cast<long long>(w1)) - 1);
     __syncwarp();
     const uint4 o = reinterpret_cast<const uint4*>(stage)[lane];
     doc[0] = o.x; doc[1] = o.y; doc[2] = o.z; doc[3] = o.w;

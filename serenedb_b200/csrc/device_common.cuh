@@ -77,41 +77,29 @@ __device__ __forceinline__ void block_sort_desc(unsigned long long* s, uint32_t 
 
 // Exact top-k selection of 64-bit keys in shared memory, O(n): MSB-first radix select finds the k-th
 // largest key (keys are unique: the doc ordinal is part of the key), then the keys >= it are compacted
-// to the front (order not preserved) and the rest of the buffer is zeroed. Zero = empty slot.
-// Requires n_slots % blockDim.x == 0 and n_slots / blockDim.x <= 16; `hist` = 256 + 2 u32 of shared
-// scratch. All threads call it; ends with a barrier. Returns the k-th largest key (0 if fewer than k
-// non-empty keys, in which case nothing is dropped).
+// to the front in place (order not preserved) and the rest of the buffer is zeroed. Zero = empty slot.
+// `hist` = 258 u32 of shared scratch; n_slots is a multiple of blockDim.x. All threads call it; ends
+// with a barrier. Returns the k-th largest key, or 0 (nothing dropped) when fewer than k keys exist.
 __device__ __forceinline__ unsigned long long block_select_topk(unsigned long long* keys, uint32_t n_slots, uint32_t k,
                                                                 uint32_t* hist) {
-  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  const uint32_t per = n_slots / blockDim.x;
-  if (per > 16u) {  // very large k: fall back to a full sort (rare; keeps register use bounded)
-    block_sort_desc(keys, n_slots);
-    const unsigned long long kth_s = keys[k - 1u];
-    __syncthreads();
-    for (uint32_t i = k + tid; i < n_slots; i += blockDim.x) keys[i] = 0ull;
-    __syncthreads();
-    return kth_s;
-  }
-  unsigned long long mine[16];
-#pragma unroll
-  for (uint32_t i = 0; i < 16; ++i) mine[i] = i < per ? keys[i * blockDim.x + tid] : 0ull;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, nwarps = blockDim.x >> 5;
   unsigned long long prefix = 0ull, mask = 0ull;
   uint32_t need = k;
   for (int shift = 56; shift >= 0; shift -= 8) {
     if (tid < 256) hist[tid] = 0u;
     __syncthreads();
-#pragma unroll
-    for (uint32_t i = 0; i < 16; ++i)
-      if (i < per && mine[i] != 0ull && (mine[i] & mask) == prefix) atomicAdd(&hist[(mine[i] >> shift) & 255ull], 1u);
+    for (uint32_t i = tid; i < n_slots; i += blockDim.x) {
+      const unsigned long long v = keys[i];
+      if (v != 0ull && (v & mask) == prefix) atomicAdd(&hist[(v >> shift) & 255ull], 1u);
+    }
     __syncthreads();
     if (warp == 0) {
       // lane l owns digits 255-8l .. 248-8l (descending); find the digit where the running count reaches `need`
       uint32_t c[8], sum = 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) { c[j] = hist[255 - 8 * int(lane) - j]; sum += c[j]; }
-      const uint32_t above = warp_incl_scan(sum, lane) - sum;  // keys in strictly higher digits of higher lanes
-      uint32_t run = above, found = 0xFFFFFFFFu, need_in = 0;
+      uint32_t run = warp_incl_scan(sum, lane) - sum;  // keys in higher digits (lower lanes)
+      uint32_t found = 0xFFFFFFFFu, need_in = 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         if (found == 0xFFFFFFFFu && run < need && run + c[j] >= need) { found = 255u - 8u * lane - uint32_t(j); need_in = need - run; }
@@ -130,23 +118,29 @@ __device__ __forceinline__ unsigned long long block_select_topk(unsigned long lo
     mask |= 0xFFull << shift;
   }
   const unsigned long long kth = prefix;
-  // compact survivors (key >= kth) to the front; every thread already holds its keys in registers
-  uint32_t keep = 0;
+  // In-place compaction, one tile of blockDim.x*4 slots at a time: survivors of a tile are written to
+  // positions that only cover slots of tiles already read, so no unread key is overwritten.
+  uint32_t written = 0;  // survivors placed so far (uniform)
+  for (uint32_t t0 = 0; t0 < n_slots; t0 += blockDim.x * 4u) {
+    unsigned long long v[4];
+    uint32_t keep = 0;
 #pragma unroll
-  for (uint32_t i = 0; i < 16; ++i) keep += (i < per && mine[i] >= kth && mine[i] != 0ull) ? 1u : 0u;
-  const uint32_t incl = warp_incl_scan(keep, lane);
-  if (lane == 31) hist[warp] = incl;
-  __syncthreads();
-  uint32_t base = incl - keep;
-  for (uint32_t w = 0; w < warp; ++w) base += hist[w];
-  uint32_t total = 0;
-  for (uint32_t w = 0; w < blockDim.x / 32u; ++w) total += hist[w];
-  __syncthreads();
+    for (uint32_t i = 0; i < 4; ++i) {
+      const uint32_t idx = t0 + tid * 4u + i;
+      v[i] = idx < n_slots ? keys[idx] : 0ull;
+      keep += (v[i] != 0ull && v[i] >= kth) ? 1u : 0u;
+    }
+    const uint32_t incl = warp_incl_scan(keep, lane);
+    if (lane == 31) hist[warp] = incl;
+    __syncthreads();   // all reads of this tile are done; warp totals visible
+    uint32_t base = written + incl - keep, total = 0;
+    for (uint32_t w = 0; w < nwarps; ++w) { if (w < warp) base += hist[w]; total += hist[w]; }
 #pragma unroll
-  for (uint32_t i = 0; i < 16; ++i)
-    if (i < per && mine[i] >= kth && mine[i] != 0ull) keys[base++] = mine[i];
-  __syncthreads();
-  for (uint32_t i = total + tid; i < n_slots; i += blockDim.x) keys[i] = 0ull;
+    for (uint32_t i = 0; i < 4; ++i) if (v[i] != 0ull && v[i] >= kth) keys[base++] = v[i];
+    written += total;
+    __syncthreads();
+  }
+  for (uint32_t i = written + tid; i < n_slots; i += blockDim.x) keys[i] = 0ull;
   __syncthreads();
   return kth;
 }
