@@ -233,6 +233,7 @@ def main():
 
     import torch
     import serenedb_b200 as sdb
+    from serenedb_b200 import dist as sd
 
     dist = None
     if world > 1:
@@ -277,8 +278,7 @@ def main():
     def groupby_step():
         scan.groupby_partial(preds, K, key_min, span, V, W_, d_i64.data_ptr(), d_f64.data_ptr())
         if dist is not None:   # one collective per dtype group merges the partial aggregates (NVLink)
-            dist.all_reduce(d_i64)
-            dist.all_reduce(d_f64)
+            sd.merge_groupby_partials(dist, d_i64, d_f64)
             torch.cuda.synchronize()
         return scan.groupby_finalize(key_min, span, d_i64.data_ptr(), d_f64.data_ptr(), span)
 
@@ -325,8 +325,7 @@ def main():
         if dist is None:
             return escan.groupby(preds, K, sum_int_field=V, avg_f64_field=W_, cap=span, n_groups_hint=span)
         escan.groupby_partial(preds, K, key_min, span, V, W_, d_i64.data_ptr(), d_f64.data_ptr())
-        dist.all_reduce(d_i64)
-        dist.all_reduce(d_f64)
+        sd.merge_groupby_partials(dist, d_i64, d_f64)
         torch.cuda.synchronize()
         return escan.groupby_finalize(key_min, span, d_i64.data_ptr(), d_f64.data_ptr(), span)
 
@@ -390,10 +389,10 @@ def main():
         dc, sum_dl = cseg.synth_corpus(rank * n_docs, 0, N_TERMS, threads=min(cores, 64))
         dct = torch.tensor(dc.astype(np.int64), device=dev)
         sdl = torch.tensor([sum_dl], dtype=torch.int64, device=dev)
-        if dist is not None:   # corpus-wide statistics: summed once at index-build time (collectors.cpp:36-52)
-            dist.all_reduce(dct)
-            dist.all_reduce(sdl)
-        reader = sdb.IndexReader([cseg], n_docs * world, int(sdl.item()), dct.cpu().numpy())
+        ndf = torch.tensor([n_docs], dtype=torch.int64, device=dev)
+        # corpus-wide statistics: summed once at index-build time (collectors.cpp:36-52), not per query
+        sd.global_term_stats(dist, dct, sdl, ndf)
+        reader = sdb.IndexReader([cseg], int(ndf.item()), int(sdl.item()), dct.cpu().numpy())
         scorer = sdb.BM25(1.2, 0.75)
         queries = make_queries(args.queries)
         batch = sdb.PreparedBatch(reader, queries, sdb.OR, scorer, TOPK)
@@ -407,7 +406,7 @@ def main():
         def bm25_step():
             batch.run_device(rank, keys.data_ptr())
             if dist is not None:   # one collective: gather every rank's k best keys, then select locally
-                dist.all_gather_into_tensor(keys_all, keys)
+                sd.gather_topk_keys(dist, keys, keys_all)
                 torch.cuda.synchronize()
                 return sdb.merge_gathered(ctx, keys_all.data_ptr(), world, nq, TOPK)
             return None
