@@ -403,12 +403,12 @@ def main():
         keys = torch.zeros(nq * TOPK, dtype=torch.int64, device=dev)
         keys_all = torch.zeros(world * nq * TOPK, dtype=torch.int64, device=dev) if dist is not None else None
 
-        def bm25_step():
+        def bm25_step(to_host=False):
             batch.run_device(rank, keys.data_ptr())
             if dist is not None:   # one collective: gather every rank's k best keys, then select locally
                 sd.gather_topk_keys(dist, keys, keys_all)
                 torch.cuda.synchronize()
-                return sdb.merge_gathered(ctx, keys_all.data_ptr(), world, nq, TOPK)
+                return sdb.merge_gathered(ctx, keys_all.data_ptr(), world, nq, TOPK, to_host=to_host)
             return None
 
         for _ in range(args.warmup):
@@ -440,7 +440,7 @@ def main():
             if dist is None:
                 hits, n_out, total = batch.run_host()
             else:
-                hits, n_out = bm25_step()
+                hits, n_out = bm25_step(to_host=True)
         be_ms = max_over_ranks(ctx.timer_stop()) / e_steps2
         barrier()
         bm = {

@@ -144,6 +144,7 @@ int sdbg_bm25_topk_batch_device(sdbg_segment* const* segs, size_t n_segs, int ki
                                 float k1, const sdbg_col_pred* filt, uint32_t k, float threshold_in,
                                 uint32_t rank, void* d_keys /* n_queries*k u64 */,
                                 void* d_totals /* n_queries u64 */);
+/* out may be NULL: the merged keys then stay in HBM (device-resident pipelines / timing). */
 int sdbg_topk_merge_gathered(sdbg_ctx*, const void* d_keys_all /* n_ranks*n_queries*k u64 */,
                              uint32_t n_ranks, size_t n_queries, uint32_t k, sdbg_hit* out, uint32_t* n_out);
 /* Test probe: decode+score one whole posting list (exhaustive, no top-k). Buffers sized docs_count. */

@@ -51,5 +51,28 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+HOST_DIR = os.path.join(HERE, "host")
+SELFTEST = os.path.join(LIB_DIR, "adapter_selftest")
+
+
+def build_adapters(force=False):
+    """Compile the C++ adapters (GpuTopKIterator : irs::DocIterator, GpuAggScan) against the mock
+    reference headers and link them with libsdbg.so into a self-test binary."""
+    srcs = [os.path.join(HOST_DIR, f) for f in ("adapter_selftest.cpp", "gpu_adapters.cpp")]
+    deps = srcs + [os.path.join(HOST_DIR, f) for f in ("gpu_adapters.hpp", "irs_mock.hpp")] + [LIB_PATH]
+    if not force and os.path.exists(SELFTEST) and all(os.path.getmtime(d) <= os.path.getmtime(SELFTEST) for d in deps):
+        return SELFTEST
+    gxx = shutil.which("g++")
+    if gxx is None:
+        if os.path.exists(SELFTEST):
+            return SELFTEST
+        raise RuntimeError("g++ not found")
+    cmd = [gxx, "-std=c++20", "-O2", "-Wall", "-Wextra", "-o", SELFTEST] + srcs + ["-L" + LIB_DIR, "-lsdbg", "-Wl,-rpath,$ORIGIN"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    return SELFTEST
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))

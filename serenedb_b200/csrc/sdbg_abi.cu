@@ -473,7 +473,7 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
 
   TopkPlan pl;
   pl.k = k;
-  pl.budget = uint32_t(env_int("SDBG_TOPK_BUDGET", 16));
+  pl.budget = uint32_t(env_int("SDBG_TOPK_BUDGET", 32));
   if (pl.budget != 16 && pl.budget != 32) return fail(c, SDBG_EINVAL, "SDBG_TOPK_BUDGET must be 16 or 32");
   const uint32_t entries = pl.budget * 128u;
   pl.cap = std::max(next_pow2(k + 1024), 4096u);  // O(n) radix select makes a roomy buffer cheap: fewer selections
@@ -680,7 +680,7 @@ extern "C" int sdbg_bm25_topk_batch_device(sdbg_segment* const* segs, size_t n_s
 
 extern "C" int sdbg_topk_merge_gathered(sdbg_ctx* c, const void* d_keys_all, uint32_t n_ranks, size_t nq, uint32_t k,
                                         sdbg_hit* out, uint32_t* n_out) {
-  if (!c || !d_keys_all || !out || !n_out || !n_ranks || !nq || !k) return SDBG_EINVAL;
+  if (!c || !d_keys_all || !n_ranks || !nq || !k || (out && !n_out)) return SDBG_EINVAL;
   CU(c, cudaSetDevice(c->device));
   // gathered layout [rank][query][k]; the merge kernel wants [query][list][stride] -> stride trick:
   // treat each rank's block as a list with a rank-major base pointer. Re-pack with a tiny kernel-free
@@ -706,6 +706,7 @@ extern "C" int sdbg_topk_merge_gathered(sdbg_ctx* c, const void* d_keys_all, uin
   topk_merge_kernel<<<unsigned(nq), kTopkThreads, size_t(cap) * 8, c->stream>>>(M);
   ++c->launches;
   CU(c, cudaGetLastError());
+  if (!out) { CU(c, cudaStreamSynchronize(c->stream)); return SDBG_OK; }   // results stay in HBM (scratch of this context)
   const size_t kb = nq * size_t(k) * 8, nb = nq * 4;
   if ((rc = ensure_pinned(c, kb + nb))) return rc;
   char* h = static_cast<char*>(c->h_pinned);

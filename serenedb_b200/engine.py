@@ -361,8 +361,12 @@ class PreparedBatch:
                 r.segments[0].ctx._h)
 
 
-def merge_gathered(ctx, d_keys_all_ptr, n_ranks, nq, k):
+def merge_gathered(ctx, d_keys_all_ptr, n_ranks, nq, k, to_host=True):
     """Global top-k from the keys every rank contributed ([rank][query][k] u64 in HBM)."""
+    if not to_host:
+        N.check(N.lib().sdbg_topk_merge_gathered(ctx._h, C.c_void_p(int(d_keys_all_ptr)), int(n_ranks), int(nq), int(k),
+                                                 None, None), ctx._h)
+        return None, None
     hits = np.zeros((nq, k), HIT_DTYPE)
     n_out = np.zeros(nq, np.uint32)
     N.check(N.lib().sdbg_topk_merge_gathered(ctx._h, C.c_void_p(int(d_keys_all_ptr)), int(n_ranks), int(nq), int(k),

@@ -1,0 +1,43 @@
+"""The C++ adapters (serenedb_b200/host) driven like the reference's callers, checked against the oracle."""
+import json
+import subprocess
+
+import numpy as np
+import pytest
+
+import orc
+
+pytestmark = pytest.mark.gpu
+
+
+def test_adapters_match_oracle():
+    from serenedb_b200 import build as b
+    exe = b.build_adapters()
+    n = 200_000
+    res = subprocess.run([exe, str(n)], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    topk, agg = [json.loads(l) for l in res.stdout.strip().splitlines()]
+    # ---- GpuTopKIterator::Collect vs oracle (2-term OR + INCLUDE-column range filter, k = 100) ----
+    oseg, dc, sum_dl = orc.synth_segment_mt(n, 0, 8, threads=4)
+    nn = orc.synth_column(2, 1, 1, n).astype(np.int32)
+    oseg.add_column(9, nn)
+    terms = []
+    for t in (2, 5):
+        st = orc.bm25_stats(n, sum_dl, int(dc[t]))
+        x = orc.BM25Term()
+        x.idf, x.norm_const, x.norm_length, x.boost, x.term = st.idf, st.norm_const, st.norm_length, 1.0, t
+        terms.append(x)
+    oh, ototal, _ = orc.bm25_topk([oseg], "OR", terms, 100, filt=orc.make_pred(9, "BETWEEN", 250000, 749999), mode=1)
+    assert [d for d, _ in topk["topk"]] == oh["doc"].tolist()
+    assert np.array_equal(np.array([s for _, s in topk["topk"]], np.float32), oh["score"])
+    assert topk["total"] == ototal
+    assert np.float32(topk["threshold"]) == oh["score"][-1]      # threshold raised to the k-th score
+    # ---- GpuAggScan chunks vs oracle GROUP BY ----
+    cols = {10: (10, 0), 11: (11, 1), 12: (12, 2), 13: (13, 3), 14: (14, 4)}
+    for f, (stream, kind) in cols.items():
+        oseg.add_column(f, orc.synth_column(stream, kind, 0, n))
+    exp = orc.filter_groupby([oseg], [orc.make_pred(11, "LT", 500000), orc.make_pred(12, "GE", 0.25, is_float=True)], 10, 13, 14, cap=100001)
+    assert agg["groups"] == len(exp) and agg["rows"] == int(exp["count"].sum())
+    assert agg["chunks"] == (len(exp) + 2047) // 2048           # <= STANDARD_VECTOR_SIZE rows per call
+    assert agg["sum_v"] == int(exp["sum_lo"].astype(object).sum())
+    assert agg["avg_sum"] == pytest.approx(float((exp["sum_f64"] / exp["cnt_f64"]).sum()), rel=1e-9)

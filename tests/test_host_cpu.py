@@ -128,3 +128,16 @@ def test_bm25_collect_matches_oracle():
         o = orc.bm25_stats(dwf, ttf, dwt)
         assert (t.idf, t.norm_const, t.norm_length) == (o.idf, o.norm_const, o.norm_length)
         assert float(s.num(t)) == orc.lib().orc_bm25_num(1.2, 1.0, o.idf)
+
+
+def test_cpp_adapters_build_and_fail_loudly_without_gpu():
+    """GpuTopKIterator / GpuAggScan compile against the mock reference headers and link with the C ABI;
+    without a device the self-test reports SDBG_ENODEVICE instead of computing anything on the CPU."""
+    import subprocess
+    import torch
+    from serenedb_b200 import build as b
+    exe = b.build_adapters()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by tests/test_gpu_adapters.py")
+    res = subprocess.run([exe, "1000"], capture_output=True, text=True)
+    assert res.returncode == 3 and '"error": -2' in res.stdout
