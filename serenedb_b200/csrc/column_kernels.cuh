@@ -297,6 +297,153 @@ filter_groupby_kernel(const GroupByParams P) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// TMA-pipelined variant of the fused filter -> GROUP BY kernel (NOT NULL columns).
+//
+// The register-staged kernel above is latency-bound: bytes in flight are tied to resident warps, and a
+// warp that is busy issuing its RED atomics is not loading. Here a single producer thread streams
+// column tiles into a kStages-deep shared-memory ring with 1-D bulk async copies
+// (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes -> SASS UBLKCP) signalled through
+// mbarriers, and the consumer warps evaluate predicates from shared memory and issue the REDs. In-flight
+// bytes per SM = CTAs/SM * kStages * tile bytes (2 * 4 * 20 KB = 160 KB), independent of how far the
+// consumers have got. Persistent CTAs, tiles handed out round-robin.
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxStreams = 7;   // up to 4 predicate columns + key + sum_int + sum_f64 (deduplicated)
+
+struct TmaGroupByParams {
+  const void* src[kMaxStreams];   // distinct referenced columns
+  int32_t elem[kMaxStreams];      // 8 (int64 / float64) or 4 (int32)
+  int32_t type[kMaxStreams];      // 0 i64, 1 f64, 2 i32
+  int32_t n_streams;
+  int32_t n_preds;
+  int32_t pred_stream[kMaxPreds];
+  int32_t pred_op[kMaxPreds];
+  int64_t pred_lo_i[kMaxPreds], pred_hi_i[kMaxPreds];
+  double pred_lo_f[kMaxPreds], pred_hi_f[kMaxPreds];
+  int32_t key_stream, sum_i_stream, sum_f_stream;   // -1 when absent
+  int32_t wide_int;
+  int64_t key_min;
+  uint64_t key_span;
+  uint64_t rows;
+  GroupSlot* table;
+  unsigned long long* out_of_range;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int kStages, int kTileRows, int kConsumerWarps>
+__global__ void __launch_bounds__((kConsumerWarps + 1) * 32)
+filter_groupby_tma_kernel(const TmaGroupByParams P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages];
+  __shared__ uint32_t s_off[kMaxStreams + 1];   // byte offset of each stream inside a stage
+
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  if (tid == 0) {
+    uint32_t o = 0;
+    for (int s = 0; s < P.n_streams; ++s) { s_off[s] = o; o += uint32_t(P.elem[s]) * kTileRows; }
+    s_off[P.n_streams] = o;
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1u); mbar_init(&empty_bar[s], kConsumerWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const uint32_t stage_bytes = s_off[P.n_streams];
+  const uint64_t n_tiles = (P.rows + kTileRows - 1) / kTileRows;
+
+  if (warp == kConsumerWarps) {
+    // ===== producer: one thread keeps the ring full =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t st = it % kStages, use = it / kStages;
+        mbar_wait(&empty_bar[st], (use & 1u) ^ 1u);           // consumers released the previous use of this stage
+        const uint64_t row0 = tile * kTileRows;
+        const uint32_t nrows = uint32_t(min(static_cast<unsigned long long>(kTileRows), static_cast<unsigned long long>(P.rows - row0)));
+        uint32_t total = 0;
+        for (int s = 0; s < P.n_streams; ++s) total += (nrows * uint32_t(P.elem[s]) + 15u) & ~15u;
+        mbar_arrive_expect_tx(&full_bar[st], total);
+        unsigned char* dst = smem + size_t(st) * stage_bytes;
+        for (int s = 0; s < P.n_streams; ++s) {
+          const uint32_t bytes = (nrows * uint32_t(P.elem[s]) + 15u) & ~15u;   // columns carry >= 64 B of slack
+          bulk_g2s(dst + s_off[s], static_cast<const char*>(P.src[s]) + row0 * uint64_t(P.elem[s]), bytes, &full_bar[st]);
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== consumers =====
+  uint32_t it = 0;
+  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const uint32_t st = it % kStages, use = it / kStages;
+    mbar_wait(&full_bar[st], use & 1u);
+    const unsigned char* base = smem + size_t(st) * stage_bytes;
+    const uint64_t row0 = tile * kTileRows;
+    const uint32_t nrows = uint32_t(min(static_cast<unsigned long long>(kTileRows), static_cast<unsigned long long>(P.rows - row0)));
+#pragma unroll 2
+    for (uint32_t r = tid; r < nrows; r += kConsumerWarps * 32u) {
+      bool pass = true;
+#pragma unroll
+      for (int i = 0; i < kMaxPreds; ++i) {
+        if (i < P.n_preds) {
+          const int s = P.pred_stream[i];
+          const unsigned char* col = base + s_off[s];
+          if (P.type[s] == 1) {
+            pass &= cmp_f64(P.pred_op[i], reinterpret_cast<const double*>(col)[r], P.pred_lo_f[i], P.pred_hi_f[i]);
+          } else {
+            const long long v = P.type[s] == 2 ? static_cast<long long>(reinterpret_cast<const int*>(col)[r])
+                                               : reinterpret_cast<const long long*>(col)[r];
+            pass &= cmp_i64(P.pred_op[i], v, P.pred_lo_i[i], P.pred_hi_i[i]);
+          }
+        }
+      }
+      if (!pass) continue;
+      const unsigned char* kc = base + s_off[P.key_stream];
+      const long long key = P.type[P.key_stream] == 2 ? static_cast<long long>(reinterpret_cast<const int*>(kc)[r])
+                                                      : reinterpret_cast<const long long*>(kc)[r];
+      const unsigned long long idx = static_cast<unsigned long long>(key - P.key_min);
+      if (idx >= P.key_span) { atomicAdd(P.out_of_range, 1ull); continue; }
+      GroupSlot* g = P.table + idx;
+      atomicAdd(&g->count, 1ull);
+      if (P.sum_i_stream >= 0) {
+        const unsigned char* vc = base + s_off[P.sum_i_stream];
+        const long long v = P.type[P.sum_i_stream] == 2 ? static_cast<long long>(reinterpret_cast<const int*>(vc)[r])
+                                                        : reinterpret_cast<const long long*>(vc)[r];
+        if (P.wide_int) {
+          atomicAdd(reinterpret_cast<unsigned long long*>(&g->sum_lo), static_cast<unsigned long long>(v) & 0xFFFFFFFFull);
+          atomicAdd(reinterpret_cast<unsigned long long*>(&g->sum_hi), static_cast<unsigned long long>(v >> 32));
+        } else {
+          atomicAdd(reinterpret_cast<unsigned long long*>(&g->sum_lo), static_cast<unsigned long long>(v));
+        }
+      }
+      if (P.sum_f_stream >= 0) atomicAdd(&g->sum_f, reinterpret_cast<const double*>(base + s_off[P.sum_f_stream])[r]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[st]);   // this warp is done reading the stage
+  }
+}
+
 // Dense table -> flat partial buffers for a SUM all-reduce:
 // d_i64 = [count | sum_lo | sum_hi | cnt_f64] (4*span int64), d_f64 = [sum_f] (span float64).
 __global__ void __launch_bounds__(256)

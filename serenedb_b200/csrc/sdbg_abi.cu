@@ -940,9 +940,40 @@ int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred
     P.wide_int = plan.wide_int; P.count_f = plan.count_f;
     P.key_min = key_min; P.key_span = span; P.rows = rows;
     P.table = table; P.cnt_f = cnt_f; P.out_of_range = oor;
-    const unsigned grid = unsigned(c->sm_count) * unsigned(env_int("SDBG_GROUPBY_CTAS_PER_SM", 8));
-    { ProfScope ps_(c, kProfGroupBy);
-      filter_groupby_kernel<2><<<grid, 256, 0, c->stream>>>(P); }
+    // NOT NULL columns (the common analytic case) go through the TMA-pipelined kernel; nullable
+    // columns need their validity words next to the values and keep the register-staged kernel.
+    bool any_nullable = P.key.validity || (P.has_sum_i && P.sum_i.validity) || (P.has_sum_f && P.sum_f.validity);
+    for (int i = 0; i < P.ps.n; ++i) any_nullable |= P.ps.p[i].col.validity != nullptr || P.ps.p[i].op >= 7;
+    if (!any_nullable && env_int("SDBG_GROUPBY_TMA", 1)) {
+      TmaGroupByParams T;
+      std::memset(&T, 0, sizeof T);
+      auto stream_of = [&](const ColDev& col) {
+        for (int i = 0; i < T.n_streams; ++i) if (T.src[i] == col.values) return i;
+        T.src[T.n_streams] = col.values; T.type[T.n_streams] = col.type; T.elem[T.n_streams] = col.type == SDBG_I32 ? 4 : 8;
+        return T.n_streams++;
+      };
+      T.n_preds = P.ps.n;
+      for (int i = 0; i < P.ps.n; ++i) {
+        T.pred_stream[i] = stream_of(P.ps.p[i].col); T.pred_op[i] = P.ps.p[i].op;
+        T.pred_lo_i[i] = P.ps.p[i].lo_i; T.pred_hi_i[i] = P.ps.p[i].hi_i; T.pred_lo_f[i] = P.ps.p[i].lo_f; T.pred_hi_f[i] = P.ps.p[i].hi_f;
+      }
+      T.key_stream = stream_of(P.key);
+      T.sum_i_stream = P.has_sum_i ? stream_of(P.sum_i) : -1;
+      T.sum_f_stream = P.has_sum_f ? stream_of(P.sum_f) : -1;
+      T.wide_int = plan.wide_int; T.key_min = key_min; T.key_span = span; T.rows = rows; T.table = table; T.out_of_range = oor;
+      constexpr int kStages = 4, kTileRows = 512, kConsumerWarps = 8;
+      const size_t smem = size_t(kStages) * kTileRows * 8 * size_t(T.n_streams);
+      auto kern = filter_groupby_tma_kernel<kStages, kTileRows, kConsumerWarps>;
+      CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      const unsigned per_sm = unsigned(std::max<size_t>(1, std::min<size_t>(size_t(env_int("SDBG_GROUPBY_TMA_CTAS", 2)), (220 * 1024) / (smem + 1024))));
+      const unsigned grid = unsigned(c->sm_count) * per_sm;
+      { ProfScope ps_(c, kProfGroupBy);
+        kern<<<grid, (kConsumerWarps + 1) * 32, smem, c->stream>>>(T); }
+    } else {
+      const unsigned grid = unsigned(c->sm_count) * unsigned(env_int("SDBG_GROUPBY_CTAS_PER_SM", 8));
+      ProfScope ps_(c, kProfGroupBy);
+      filter_groupby_kernel<2><<<grid, 256, 0, c->stream>>>(P);
+    }
     ++c->launches;
     CU(c, cudaGetLastError());
   }

@@ -416,8 +416,9 @@ class IResearchScan:
                                                     NO_FIELD if avg_f64_field is None else int(avg_f64_field),
                                                     C.c_void_p(int(d_i64_ptr)), C.c_void_p(int(d_f64_ptr))), self.ctx._h)
 
-    def groupby_finalize(self, key_min, key_span, d_i64_ptr, d_f64_ptr, cap):
-        out = np.zeros(int(cap), GROUP_DTYPE)
+    def groupby_finalize(self, key_min, key_span, d_i64_ptr, d_f64_ptr, cap, out=None):
+        if out is None:
+            out = np.empty(int(cap), GROUP_DTYPE)
         n = C.c_uint64()
         N.check(N.lib().sdbg_groupby_finalize(self.ctx._h, int(key_min), int(key_span), C.c_void_p(int(d_i64_ptr)),
                                               C.c_void_p(int(d_f64_ptr)), _ptr(out), int(cap), C.byref(n)), self.ctx._h)
