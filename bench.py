@@ -218,6 +218,7 @@ def main():
     ap.add_argument("--queries", type=int, default=4096)
     ap.add_argument("--skip-bm25", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="kernel probes only (no host round trip)")
     ap.add_argument("--cpu-rows", type=int, default=100_000_000)
     ap.add_argument("--cpu-queries", type=int, default=256)
     ap.add_argument("--cpu-threads", type=int, default=0)
@@ -311,48 +312,50 @@ def main():
     n_groups = len(res)
     n_pass = int(res["count"].sum())
 
-    # ------------------------------------------------------------------ e2e: host columns -> host groups
-    host = {}
-    for f, (_, _, dt) in COLS.items():
-        h = torch.empty(rows, dtype=torch.int64 if dt == np.int64 else torch.float64, pin_memory=True)
-        seg.column_to_host(f, h.data_ptr(), rows)
-        host[f] = h
-    torch.cuda.synchronize()
-    eseg = sdb.Segment(ctx, rows)
-    escan = sdb.IResearchScan([eseg])
-    h2d = rows * 40
-    d2h = None
-
-    def e2e_step():
+    gb_e2e, e_ms, e_steps, h2d, d2h, host = None, None, 0, rows * 40, 0, {}
+    if not args.skip_e2e:
+        # ------------------------------------------------------------------ e2e: host columns -> host groups
+        host = {}
         for f, (_, _, dt) in COLS.items():
-            eseg.stage_column(f, (host[f].data_ptr(), dt, rows))
-        if dist is None:
-            return escan.groupby(preds, K, sum_int_field=V, avg_f64_field=W_, cap=span, n_groups_hint=span)
-        escan.groupby_partial(preds, K, key_min, span, V, W_, d_i64.data_ptr(), d_f64.data_ptr())
-        sd.merge_groupby_partials(dist, d_i64, d_f64)
+            h = torch.empty(rows, dtype=torch.int64 if dt == np.int64 else torch.float64, pin_memory=True)
+            seg.column_to_host(f, h.data_ptr(), rows)
+            host[f] = h
         torch.cuda.synchronize()
-        return escan.groupby_finalize(key_min, span, d_i64.data_ptr(), d_f64.data_ptr(), span)
+        eseg = sdb.Segment(ctx, rows)
+        escan = sdb.IResearchScan([eseg])
+        h2d = rows * 40
+        d2h = None
 
-    e_steps = max(1, min(args.steps, 5))
-    eres = e2e_step()
-    eres = e2e_step()
-    barrier()
-    ctx.timer_start()
-    for _ in range(e_steps):
+        def e2e_step():
+            for f, (_, _, dt) in COLS.items():
+                eseg.stage_column(f, (host[f].data_ptr(), dt, rows))
+            if dist is None:
+                return escan.groupby(preds, K, sum_int_field=V, avg_f64_field=W_, cap=span, n_groups_hint=span)
+            escan.groupby_partial(preds, K, key_min, span, V, W_, d_i64.data_ptr(), d_f64.data_ptr())
+            sd.merge_groupby_partials(dist, d_i64, d_f64)
+            torch.cuda.synchronize()
+            return escan.groupby_finalize(key_min, span, d_i64.data_ptr(), d_f64.data_ptr(), span)
+
+        e_steps = max(1, min(args.steps, 5))
         eres = e2e_step()
-    torch.cuda.synchronize()
-    e_ms = max_over_ranks(ctx.timer_stop()) / e_steps
-    barrier()
-    d2h = int(len(eres)) * 48 + 16
-    assert np.array_equal(eres["count"], res["count"]) and np.array_equal(eres["sum_lo"], res["sum_lo"])
-    gb_e2e = world * rows / (e_ms * 1e-3) / 1e6
-    eseg.close()
+        eres = e2e_step()
+        barrier()
+        ctx.timer_start()
+        for _ in range(e_steps):
+            eres = e2e_step()
+        torch.cuda.synchronize()
+        e_ms = max_over_ranks(ctx.timer_stop()) / e_steps
+        barrier()
+        d2h = int(len(eres)) * 48 + 16
+        assert np.array_equal(eres["count"], res["count"]) and np.array_equal(eres["sum_lo"], res["sum_lo"])
+        gb_e2e = world * rows / (e_ms * 1e-3) / 1e6
+        eseg.close()
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)
     cpu_gb = None
     cores = host_cores()
     threads = min(cores, args.cpu_threads or cores)
-    if rank == 0 and world == 1 and not args.skip_cpu:
+    if rank == 0 and world == 1 and not args.skip_cpu and not args.skip_e2e:
         crow = min(args.cpu_rows, rows)
         cols = {f: host[f].numpy() for f in COLS}
         cres, ctimes = cpu_groupby(cols, crow, threads, 3)
@@ -376,8 +379,8 @@ def main():
                    "l2": "inputs (%.1f GB/GPU) larger than L2; no flush needed" % (rows * 40 / 1e9),
                    "merge": "none" if world == 1 else "2 NCCL all-reduces (int64 limbs+counts, float64 sums) per step"},
         "clocks": clocks,
-        "e2e": {"value": round(gb_e2e, 1), "unit": "Mrows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": round(e_ms, 3), "steps": e_steps},
+        "e2e": None if gb_e2e is None else {"value": round(gb_e2e, 1), "unit": "Mrows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                                               "ms_per_step": round(e_ms, 3), "steps": e_steps},
         "gpu_launches": int(gb_launches),
         "roofline": {"bound": "hbm", "achieved": round(gb_ach, 1), "peak": hbm_peak, "unit": "GB/s",
                      "frac": round(gb_ach / hbm_peak, 4), "traffic": None, "kernel": "filter_groupby_kernel",

@@ -222,10 +222,10 @@ filter_count_sum_kernel(const PredSet ps, const ColDev sum_col, int has_sum, uin
 // 32 bytes per group = one L2 sector, updated with fire-and-forget RED atomics; at 1e5 groups it is
 // 3.2 MB and stays L2-resident while the 40 B/row column stream goes by.
 // ------------------------------------------------------------------------------------------
-struct GroupSlot {            // 32 bytes, one sector
+struct GroupSlot {            // 32 bytes = one L2 sector per group
   unsigned long long count;   // COUNT(*)
   long long sum_lo;           // SUM(int): low limb  (narrow mode: the whole sum)
-  long long sum_hi;           // SUM(int): high limb (wide mode: sum of v >> 32); cnt_f64 when avg col is nullable
+  long long sum_hi;           // SUM(int): high limb (wide mode: sum of v >> 32)
   double sum_f;               // SUM(double)
 };
 static_assert(sizeof(GroupSlot) == 32, "one L2 sector per group");
@@ -317,11 +317,13 @@ struct TmaGroupByParams {
   int32_t n_streams;
   int32_t n_preds;
   int32_t pred_stream[kMaxPreds];
-  int32_t pred_op[kMaxPreds];
+  int32_t pred_negate[kMaxPreds];   // 1: pass = !(lo <= v <= hi)   (SQL <>)
+  // every comparison is normalised on the host to a closed range lo <= v <= hi (empty when lo > hi)
   int64_t pred_lo_i[kMaxPreds], pred_hi_i[kMaxPreds];
   double pred_lo_f[kMaxPreds], pred_hi_f[kMaxPreds];
   int32_t key_stream, sum_i_stream, sum_f_stream;   // -1 when absent
   int32_t wide_int;
+  int32_t debug_skip;   // timing experiments only (SDBG_GROUPBY_DEBUG): bits 1/2/4 drop the count / sum_int / sum_f64 RED
   int64_t key_min;
   uint64_t key_span;
   uint64_t rows;
@@ -401,6 +403,8 @@ filter_groupby_tma_kernel(const TmaGroupByParams P) {
     const unsigned char* base = smem + size_t(st) * stage_bytes;
     const uint64_t row0 = tile * kTileRows;
     const uint32_t nrows = uint32_t(min(static_cast<unsigned long long>(kTileRows), static_cast<unsigned long long>(P.rows - row0)));
+    // One row per lane; predicates are branch-free closed-range tests on the staged tile; a passing row
+    // issues its REDs (fire-and-forget) into the L2-resident group table.
 #pragma unroll 2
     for (uint32_t r = tid; r < nrows; r += kConsumerWarps * 32u) {
       bool pass = true;
@@ -409,13 +413,16 @@ filter_groupby_tma_kernel(const TmaGroupByParams P) {
         if (i < P.n_preds) {
           const int s = P.pred_stream[i];
           const unsigned char* col = base + s_off[s];
+          bool in;
           if (P.type[s] == 1) {
-            pass &= cmp_f64(P.pred_op[i], reinterpret_cast<const double*>(col)[r], P.pred_lo_f[i], P.pred_hi_f[i]);
+            const double v = reinterpret_cast<const double*>(col)[r];
+            in = (v >= P.pred_lo_f[i]) & (v <= P.pred_hi_f[i]);
           } else {
             const long long v = P.type[s] == 2 ? static_cast<long long>(reinterpret_cast<const int*>(col)[r])
                                                : reinterpret_cast<const long long*>(col)[r];
-            pass &= cmp_i64(P.pred_op[i], v, P.pred_lo_i[i], P.pred_hi_i[i]);
+            in = (v >= P.pred_lo_i[i]) & (v <= P.pred_hi_i[i]);
           }
+          pass &= in != (P.pred_negate[i] != 0);
         }
       }
       if (!pass) continue;
@@ -425,8 +432,8 @@ filter_groupby_tma_kernel(const TmaGroupByParams P) {
       const unsigned long long idx = static_cast<unsigned long long>(key - P.key_min);
       if (idx >= P.key_span) { atomicAdd(P.out_of_range, 1ull); continue; }
       GroupSlot* g = P.table + idx;
-      atomicAdd(&g->count, 1ull);
-      if (P.sum_i_stream >= 0) {
+      if (!(P.debug_skip & 1)) atomicAdd(&g->count, 1ull);
+      if (P.sum_i_stream >= 0 && !(P.debug_skip & 2)) {
         const unsigned char* vc = base + s_off[P.sum_i_stream];
         const long long v = P.type[P.sum_i_stream] == 2 ? static_cast<long long>(reinterpret_cast<const int*>(vc)[r])
                                                         : reinterpret_cast<const long long*>(vc)[r];
@@ -437,10 +444,93 @@ filter_groupby_tma_kernel(const TmaGroupByParams P) {
           atomicAdd(reinterpret_cast<unsigned long long*>(&g->sum_lo), static_cast<unsigned long long>(v));
         }
       }
-      if (P.sum_f_stream >= 0) atomicAdd(&g->sum_f, reinterpret_cast<const double*>(base + s_off[P.sum_f_stream])[r]);
+      if (P.sum_f_stream >= 0 && !(P.debug_skip & 4)) atomicAdd(&g->sum_f, reinterpret_cast<const double*>(base + s_off[P.sum_f_stream])[r]);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[st]);   // this warp is done reading the stage
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Hash-table GROUP BY for key ranges too wide for the dense table (DuckDB's regular hash aggregate).
+// Open addressing with linear probing in global memory; a slot is claimed by CAS on its key, the
+// aggregates are then updated with the same RED atomics as the dense path. Capacity is a power of two
+// >= 2x the group-count hint; if the table fills up the kernel raises `overflow` and the host retries
+// with a larger table. The reserved key value INT64_MIN lives in an extra slot at index `capacity`.
+// ------------------------------------------------------------------------------------------
+struct HashSlot {              // 48 bytes
+  long long key;               // kEmptyKey = unclaimed
+  unsigned long long count;
+  long long sum_lo, sum_hi;    // SUM(int) limbs (wide form: v & 0xFFFFFFFF, v >> 32)
+  double sum_f;
+  unsigned long long cnt_f;
+};
+constexpr long long kEmptyKey = static_cast<long long>(0x8000000000000000ull);
+
+struct HashGroupByParams {
+  PredSet ps;
+  ColDev key, sum_i, sum_f;
+  int32_t has_sum_i, has_sum_f;
+  uint64_t rows;
+  HashSlot* table;             // capacity + 1 slots
+  uint64_t capacity;           // power of two
+  unsigned int* overflow;      // set when a probe sequence wraps the whole table
+};
+
+__device__ __forceinline__ uint64_t hash_key(long long k) {
+  unsigned long long z = static_cast<unsigned long long>(k) * 0x9E3779B97F4A7C15ull;
+  z ^= z >> 32;
+  return z;
+}
+
+__device__ __forceinline__ void hash_update(const HashGroupByParams& P, long long key, long long v, bool v_ok, double w, bool w_ok) {
+  HashSlot* g = nullptr;
+  if (key == kEmptyKey) {
+    g = P.table + P.capacity;  // dedicated slot for the reserved value
+    g->key = key;              // benign race: every writer stores the same value
+  } else {
+    uint64_t h = hash_key(key) & (P.capacity - 1);
+    for (uint64_t probes = 0; probes < P.capacity; ++probes) {
+      long long cur = *reinterpret_cast<volatile long long*>(&P.table[h].key);
+      if (cur == kEmptyKey) cur = static_cast<long long>(atomicCAS(reinterpret_cast<unsigned long long*>(&P.table[h].key),
+                                                                   static_cast<unsigned long long>(kEmptyKey), static_cast<unsigned long long>(key)));
+      if (cur == kEmptyKey || cur == key) { g = P.table + h; break; }
+      h = (h + 1) & (P.capacity - 1);
+    }
+    if (!g) { atomicExch(P.overflow, 1u); return; }
+  }
+  atomicAdd(&g->count, 1ull);
+  if (P.has_sum_i && v_ok) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(&g->sum_lo), static_cast<unsigned long long>(v) & 0xFFFFFFFFull);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&g->sum_hi), static_cast<unsigned long long>(v >> 32));
+  }
+  if (P.has_sum_f && w_ok) { atomicAdd(&g->sum_f, w); atomicAdd(&g->cnt_f, 1ull); }
+}
+
+__global__ void __launch_bounds__(256)
+hash_init_kernel(HashSlot* table, uint64_t n) {
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
+    HashSlot s; s.key = kEmptyKey; s.count = 0; s.sum_lo = 0; s.sum_hi = 0; s.sum_f = 0.0; s.cnt_f = 0;
+    table[i] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+filter_groupby_hash_kernel(const HashGroupByParams P) {
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x * 2ull;
+  for (uint64_t r = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 2ull; r < P.rows; r += stride) {
+    const uint32_t m = preds2(P.ps, r, P.rows);
+    if (!m) continue;
+    long long k0, k1, v0 = 0, v1 = 0;
+    double w0 = 0, w1 = 0;
+    load2_i64(P.key, r, k0, k1);
+    if (P.has_sum_i) load2_i64(P.sum_i, r, v0, v1);
+    if (P.has_sum_f) load2_f64(P.sum_f, r, w0, w1);
+    bool vi0 = true, vi1 = true, wf0 = true, wf1 = true;
+    if (P.has_sum_i && P.sum_i.validity) { vi0 = col_valid(P.sum_i, r); vi1 = r + 1 < P.rows && col_valid(P.sum_i, r + 1); }
+    if (P.has_sum_f && P.sum_f.validity) { wf0 = col_valid(P.sum_f, r); wf1 = r + 1 < P.rows && col_valid(P.sum_f, r + 1); }
+    if (m & 1u) hash_update(P, k0, v0, vi0, w0, wf0);
+    if (m & 2u) hash_update(P, k1, v1, vi1, w1, wf1);
   }
 }
 

@@ -954,21 +954,64 @@ int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred
       };
       T.n_preds = P.ps.n;
       for (int i = 0; i < P.ps.n; ++i) {
-        T.pred_stream[i] = stream_of(P.ps.p[i].col); T.pred_op[i] = P.ps.p[i].op;
-        T.pred_lo_i[i] = P.ps.p[i].lo_i; T.pred_hi_i[i] = P.ps.p[i].hi_i; T.pred_lo_f[i] = P.ps.p[i].lo_f; T.pred_hi_f[i] = P.ps.p[i].hi_f;
+        const PredDev& pd = P.ps.p[i];
+        T.pred_stream[i] = stream_of(pd.col);
+        // normalise the comparison to a closed range (exact: integers step by 1, doubles by one ulp)
+        int64_t li = INT64_MIN, hi_ = INT64_MAX; double lf = -HUGE_VAL, hf = HUGE_VAL; int neg = 0; bool empty = false;
+        if (pd.col.type == SDBG_F64) {
+          const double x = pd.lo_f;
+          if (std::isnan(x) || (pd.op == SDBG_OP_BETWEEN && std::isnan(pd.hi_f))) empty = true;   // comparisons with NaN are false
+          switch (pd.op) {
+            case SDBG_OP_LT: if (x == -HUGE_VAL) empty = true; else hf = std::nextafter(x, -HUGE_VAL); break;
+            case SDBG_OP_LE: hf = x; break;
+            case SDBG_OP_GT: if (x == HUGE_VAL) empty = true; else lf = std::nextafter(x, HUGE_VAL); break;
+            case SDBG_OP_GE: lf = x; break;
+            case SDBG_OP_EQ: lf = hf = x; break;
+            case SDBG_OP_NE: lf = hf = x; neg = 1; if (std::isnan(x)) { empty = false; lf = 1; hf = 0; } break;  // v <> NaN is true
+            default: lf = x; hf = pd.hi_f; break;
+          }
+          if (empty) { lf = 1; hf = 0; neg = 0; }
+        } else {
+          const int64_t x = pd.lo_i;
+          switch (pd.op) {
+            case SDBG_OP_LT: if (x == INT64_MIN) empty = true; else hi_ = x - 1; break;
+            case SDBG_OP_LE: hi_ = x; break;
+            case SDBG_OP_GT: if (x == INT64_MAX) empty = true; else li = x + 1; break;
+            case SDBG_OP_GE: li = x; break;
+            case SDBG_OP_EQ: li = hi_ = x; break;
+            case SDBG_OP_NE: li = hi_ = x; neg = 1; break;
+            default: li = x; hi_ = pd.hi_i; break;
+          }
+          if (empty) { li = 1; hi_ = 0; }
+        }
+        T.pred_lo_i[i] = li; T.pred_hi_i[i] = hi_; T.pred_lo_f[i] = lf; T.pred_hi_f[i] = hf; T.pred_negate[i] = neg;
       }
       T.key_stream = stream_of(P.key);
       T.sum_i_stream = P.has_sum_i ? stream_of(P.sum_i) : -1;
       T.sum_f_stream = P.has_sum_f ? stream_of(P.sum_f) : -1;
+      T.debug_skip = env_int("SDBG_GROUPBY_DEBUG", 0);
       T.wide_int = plan.wide_int; T.key_min = key_min; T.key_span = span; T.rows = rows; T.table = table; T.out_of_range = oor;
-      constexpr int kStages = 4, kTileRows = 512, kConsumerWarps = 8;
-      const size_t smem = size_t(kStages) * kTileRows * 8 * size_t(T.n_streams);
-      auto kern = filter_groupby_tma_kernel<kStages, kTileRows, kConsumerWarps>;
-      CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-      const unsigned per_sm = unsigned(std::max<size_t>(1, std::min<size_t>(size_t(env_int("SDBG_GROUPBY_TMA_CTAS", 2)), (220 * 1024) / (smem + 1024))));
-      const unsigned grid = unsigned(c->sm_count) * per_sm;
-      { ProfScope ps_(c, kProfGroupBy);
-        kern<<<grid, (kConsumerWarps + 1) * 32, smem, c->stream>>>(T); }
+      const int shape = env_int("SDBG_GROUPBY_TMA_SHAPE", 0);
+      auto launch = [&](auto kern, int stages, int tile_rows, int consumer_warps) -> int {
+        const size_t smem = size_t(stages) * size_t(tile_rows) * 8 * size_t(T.n_streams);
+        CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        const size_t fit = std::max<size_t>(1, (220 * 1024) / (smem + 2048));
+        const size_t by_threads = std::max<size_t>(1, 2048 / (size_t(consumer_warps + 1) * 32));
+        const unsigned per_sm = unsigned(std::min<size_t>(std::min(fit, by_threads), size_t(env_int("SDBG_GROUPBY_TMA_CTAS", 8))));
+        const unsigned grid = unsigned(c->sm_count) * per_sm;
+        ProfScope ps_(c, kProfGroupBy);
+        kern<<<grid, (consumer_warps + 1) * 32, smem, c->stream>>>(T);
+        return SDBG_OK;
+      };
+      int lrc;
+      switch (shape) {
+        case 1: lrc = launch(filter_groupby_tma_kernel<4, 256, 8>, 4, 256, 8); break;
+        case 2: lrc = launch(filter_groupby_tma_kernel<4, 512, 16>, 4, 512, 16); break;
+        case 3: lrc = launch(filter_groupby_tma_kernel<3, 256, 8>, 3, 256, 8); break;
+        case 4: lrc = launch(filter_groupby_tma_kernel<4, 1024, 16>, 4, 1024, 16); break;
+        default: lrc = launch(filter_groupby_tma_kernel<4, 512, 8>, 4, 512, 8); break;
+      }
+      if (lrc) return lrc;
     } else {
       const unsigned grid = unsigned(c->sm_count) * unsigned(env_int("SDBG_GROUPBY_CTAS_PER_SM", 8));
       ProfScope ps_(c, kProfGroupBy);
@@ -987,6 +1030,75 @@ int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred
   if (h_oor) return fail(c, SDBG_EINVAL, "GROUP BY key outside [key_min, key_min + span)");
   if (plan_out) *plan_out = plan;
   return SDBG_OK;
+}
+
+}  // namespace
+
+namespace {
+
+int groupby_hash(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred* preds, size_t n_preds, uint64_t key_field,
+                 uint32_t n_groups_hint, uint64_t sum_int_field, uint64_t avg_f64_field, sdbg_group_row* out, uint64_t cap,
+                 uint64_t* n_out) {
+  sdbg_ctx* c = segs[0]->ctx;
+  uint64_t capacity = 1 << 16;
+  while (capacity < 2ull * std::max<uint64_t>(n_groups_hint, cap)) capacity <<= 1;
+  int rc;
+  for (int attempt = 0; attempt < 8; ++attempt, capacity <<= 2) {
+    const size_t bytes = (capacity + 1) * sizeof(HashSlot);
+    if (bytes > (size_t(8) << 30)) return fail(c, SDBG_ECAPACITY, "hash aggregate table would exceed 8 GiB");
+    if ((rc = ensure(c, c->scratch[11], bytes + 64))) return rc;
+    auto* table = static_cast<HashSlot*>(c->scratch[11].p);
+    auto* overflow = reinterpret_cast<unsigned int*>(static_cast<char*>(c->scratch[11].p) + bytes);
+    hash_init_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(table, capacity + 1);
+    ++c->launches;
+    CU(c, cudaMemsetAsync(overflow, 0, 64, c->stream));
+    for (size_t si = 0; si < n_segs; ++si) {
+      sdbg_segment* s = segs[si];
+      HashGroupByParams P;
+      std::memset(&P, 0, sizeof P);
+      uint64_t rows = 0, r = 0;
+      if ((rc = pred_set(s, preds, n_preds, &P.ps, &rows))) return rc;
+      if ((rc = col_view(s, key_field, &P.key, &r))) return rc;
+      if (P.key.validity) return fail(c, SDBG_EUNSUPPORTED, "nullable GROUP BY key");
+      if (P.key.type == SDBG_F64) return fail(c, SDBG_EUNSUPPORTED, "float GROUP BY key");
+      if (!rows) rows = r;
+      if (sum_int_field != UINT64_MAX) { if ((rc = col_view(s, sum_int_field, &P.sum_i, &r))) return rc; P.has_sum_i = 1; }
+      if (avg_f64_field != UINT64_MAX) {
+        if ((rc = col_view(s, avg_f64_field, &P.sum_f, &r))) return rc;
+        if (P.sum_f.type != SDBG_F64) return fail(c, SDBG_EINVAL, "avg_f64_field is not a float column");
+        P.has_sum_f = 1;
+      }
+      P.rows = rows; P.table = table; P.capacity = capacity; P.overflow = overflow;
+      { ProfScope ps_(c, kProfGroupBy);
+        filter_groupby_hash_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(P); }
+      ++c->launches;
+      CU(c, cudaGetLastError());
+    }
+    unsigned int h_over = 0;
+    CU(c, cudaMemcpyAsync(&h_over, overflow, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (h_over) continue;  // table filled up: retry with 4x the capacity
+    std::vector<HashSlot> h(capacity + 1);
+    CU(c, cudaMemcpyAsync(h.data(), table, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    std::vector<const HashSlot*> live;
+    for (const HashSlot& sl : h) if (sl.count) live.push_back(&sl);
+    std::sort(live.begin(), live.end(), [](const HashSlot* a, const HashSlot* b) { return a->key < b->key; });
+    *n_out = live.size();
+    if (live.size() > cap) return fail(c, SDBG_ECAPACITY, "group output buffer too small");
+    for (size_t i = 0; i < live.size(); ++i) {
+      const HashSlot& sl = *live[i];
+      sdbg_group_row& g = out[i];
+      g.key = sl.key; g.count = sl.count;
+      const __int128 tot = (static_cast<__int128>(sl.sum_hi) << 32) + static_cast<__int128>(sl.sum_lo);
+      g.sum_i128[0] = int64_t(uint64_t(static_cast<unsigned __int128>(tot)));
+      g.sum_i128[1] = int64_t(uint64_t(static_cast<unsigned __int128>(tot) >> 64));
+      g.sum_f64 = sl.sum_f;
+      g.cnt_f64 = avg_f64_field != UINT64_MAX ? sl.cnt_f : sl.count;
+    }
+    return SDBG_OK;
+  }
+  return fail(c, SDBG_ECAPACITY, "hash aggregate: too many groups");
 }
 
 }  // namespace
@@ -1041,7 +1153,6 @@ extern "C" int sdbg_groupby_finalize(sdbg_ctx* c, int64_t key_min, uint64_t span
 extern "C" int sdbg_filter_groupby(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred* preds, size_t n_preds,
                                    uint64_t key_field, uint32_t n_groups_hint, uint64_t sum_int_field, uint64_t avg_f64_field,
                                    sdbg_group_row* out, uint64_t cap, uint64_t* n_out) {
-  (void)n_groups_hint;
   if (!segs || !n_segs || !out || !n_out || (!preds && n_preds)) return SDBG_EINVAL;
   sdbg_ctx* c = segs[0]->ctx;
   CU(c, cudaSetDevice(c->device));
@@ -1054,8 +1165,12 @@ extern "C" int sdbg_filter_groupby(sdbg_segment* const* segs, size_t n_segs, con
   }
   if (kmin > kmax) { *n_out = 0; return SDBG_OK; }
   const unsigned __int128 span128 = static_cast<unsigned __int128>(static_cast<__int128>(kmax) - kmin) + 1;
-  if (span128 > (static_cast<unsigned __int128>(1) << 26))
-    return fail(c, SDBG_EUNSUPPORTED, "GROUP BY key range > 2^26: the hash-table path is not built yet (dense path only)");
+  // Dense ("perfect hash") table when statistics bound the key range to something table-sized,
+  // otherwise a real hash table sized from the group-count hint.
+  const unsigned __int128 dense_limit = std::max<unsigned __int128>(static_cast<unsigned __int128>(1) << 20,
+                                                                    static_cast<unsigned __int128>(n_groups_hint) * 8);
+  if (span128 > (static_cast<unsigned __int128>(1) << 26) || span128 > dense_limit || env_int("SDBG_GROUPBY_FORCE_HASH", 0))
+    return groupby_hash(segs, n_segs, preds, n_preds, key_field, n_groups_hint, sum_int_field, avg_f64_field, out, cap, n_out);
   const uint64_t span = uint64_t(span128);
   int rc;
   if ((rc = ensure(c, c->scratch[8], span * 40 + 64))) return rc;

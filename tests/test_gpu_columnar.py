@@ -149,3 +149,30 @@ def test_groupby_nulls_and_multisegment():
     for f in ("key", "count", "sum_lo", "sum_hi", "cnt_f64"):
         assert np.array_equal(got[f], exp[f]), f
     assert np.allclose(got["sum_f64"], exp["sum_f64"], rtol=1e-9)
+
+
+def test_groupby_hash_path_wide_keys():
+    """Keys spread over the whole int64 range (incl. INT64_MIN, the table's reserved value) take the
+    hash-table path; results equal the oracle's hash aggregate."""
+    rows = 300_001
+    rng = np.random.default_rng(21)
+    pool = rng.integers(np.iinfo(np.int64).min, np.iinfo(np.int64).max, size=5000, dtype=np.int64)
+    pool[0] = np.iinfo(np.int64).min
+    pool[1] = np.iinfo(np.int64).max
+    key = pool[rng.integers(0, len(pool), size=rows)]
+    v = rng.integers(-2**45, 2**45, size=rows).astype(np.int64)
+    w = rng.random(rows)
+    a = rng.integers(0, 100, size=rows).astype(np.int64)
+    oseg = orc.Segment(rows, has_wand=False)
+    gseg = sdb.Segment(ctx(), rows)
+    for f, vals in {1: key, 2: v, 3: w, 4: a}.items():
+        oseg.add_column(f, vals)
+        gseg.stage_column(f, vals)
+    got = sdb.IResearchScan([gseg]).groupby([sdb.pred(4, "LT", 60)], 1, sum_int_field=2, avg_f64_field=3, cap=6000, n_groups_hint=5000)
+    exp = orc.filter_groupby([oseg], [orc.make_pred(4, "LT", 60)], 1, 2, 3, cap=6000)
+    for f in ("key", "count", "sum_lo", "sum_hi", "cnt_f64"):
+        assert np.array_equal(got[f], exp[f]), f
+    assert np.allclose(got["sum_f64"], exp["sum_f64"], rtol=1e-9)
+    # a too-small hint still works (the table grows and the scan is retried)
+    got2 = sdb.IResearchScan([gseg]).groupby([sdb.pred(4, "LT", 60)], 1, sum_int_field=2, avg_f64_field=3, cap=6000, n_groups_hint=1)
+    assert np.array_equal(got2["key"], exp["key"]) and np.array_equal(got2["count"], exp["count"])
