@@ -454,7 +454,7 @@ bm25_topk_kernel(const TopkParams P) {
       const uint32_t src_begin = P.conjunction ? s_phase[buf][t] * 128u : 0u;
       for (uint32_t e = src_begin + tid; e < src_end; e += blockDim.x) {
         const uint32_t d = e_doc[e];
-        if (d == kPadDoc) continue;
+        if (d - lo > hi - lo) continue;     // padding (0xFFFFFFFF), folded entries, docs of straddling blocks outside the window
         if (P.conjunction && e_cnt[e] != t) { e_doc[e] = kPadDoc; continue; }
         uint32_t pos = dst_n;
         if (dst_n) pos = lower_bound_u32(e_doc + dst_begin, dst_n, d);
@@ -472,39 +472,41 @@ bm25_topk_kernel(const TopkParams P) {
     // ---- 3. emit live in-window entries ----
     const uint32_t n_entries = n_items * 128u;
     const uint32_t emit_begin = P.conjunction ? s_phase[buf][T - 1u] * 128u : 0u;  // AND: only the last term's slots can be complete
+    bool first_pass = true;
     for (;;) {
       const unsigned long long theta = s_theta;
+      const uint32_t theta_hi = uint32_t(theta >> 32);
       uint32_t matched = 0;
       bool pending = false;
       for (uint32_t e0 = emit_begin; e0 < n_entries; e0 += blockDim.x) {
         const uint32_t e = e0 + tid;
-        uint32_t d = e < n_entries ? e_doc[e] : kPadDoc;
-        bool live = d != kPadDoc && d >= lo && d <= hi;
+        const uint32_t d = e < n_entries ? e_doc[e] : kPadDoc;
+        bool live = d - lo <= hi - lo;                       // in window, not padding / folded / already stored
         if (live && P.conjunction) live = e_cnt[e] == T - 1u;
-        if (live) live = filter_pass(P.filt, d);
+        if (live && P.filt.values != nullptr) live = filter_pass(P.filt, d);
+        matched += (live && first_pass) ? 1u : 0u;
+        // cheap pre-test on the score bits alone; the full 64-bit key only for the few that may qualify
+        const uint32_t sbits = live ? __float_as_uint(e_score[e]) : 0u;
+        bool want = live && sbits >= theta_hi;
         unsigned long long key = 0ull;
-        bool want = false;
-        if (live) {
-          key = make_key(e_score[e], P.seg.ordinal_base + d);
-          want = key > theta;
-        }
-        // warp-aggregated append: one shared atomic per warp
+        if (want) { key = make_key(__uint_as_float(sbits), P.seg.ordinal_base + d); want = key > theta; }
         const uint32_t wb = __ballot_sync(kFull, want);
-        uint32_t base = 0;
-        if (lane == 0 && wb) base = atomicAdd(&s_ncand, uint32_t(__popc(wb)));
-        base = __shfl_sync(kFull, base, 0);
-        bool stored = true;
-        if (want) {
-          const uint32_t pos = base + __popc(wb & ((1u << lane) - 1u));
-          if (pos < P.cap) cand[pos] = key; else { stored = false; pending = true; }
+        if (wb) {                                            // uniform: most iterations append nothing once the threshold is up
+          uint32_t base = 0;
+          if (lane == 0) base = atomicAdd(&s_ncand, uint32_t(__popc(wb)));
+          base = __shfl_sync(kFull, base, 0);
+          if (want) {
+            const uint32_t pos = base + __popc(wb & ((1u << lane) - 1u));
+            if (pos < P.cap) { cand[pos] = key; e_doc[e] = kPadDoc; }   // stored: tombstone so that a retry skips it
+            else pending = true;
+          }
         }
-        if (live && stored) { ++matched; e_doc[e] = kPadDoc; }   // done with this entry (not retried)
-        else if (e < n_entries && !live) e_doc[e] = kPadDoc;
       }
       matched = warp_sum(matched);
       if (lane == 0 && matched) atomicAdd(&s_matched, matched);
       if (!__syncthreads_or(int(pending))) break;
       compact();  // buffer overflowed: select, raise the threshold, retry the entries that did not fit
+      first_pass = false;
     }
   }
 

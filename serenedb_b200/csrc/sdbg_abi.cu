@@ -476,7 +476,7 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
   pl.budget = uint32_t(env_int("SDBG_TOPK_BUDGET", 32));
   if (pl.budget != 16 && pl.budget != 32) return fail(c, SDBG_EINVAL, "SDBG_TOPK_BUDGET must be 16 or 32");
   const uint32_t entries = pl.budget * 128u;
-  pl.cap = std::max(next_pow2(k + 1024), 4096u);  // O(n) radix select makes a roomy buffer cheap: fewer selections
+  pl.cap = std::max(next_pow2(k + 1024), uint32_t(env_int("SDBG_TOPK_CAP", 2048)));  // selection is O(n): buffer size trades shared memory (occupancy) against selection count
   // Enough CTAs to fill the machine a few times over; a query is split into chains (contiguous doc
   // ranges) only when the batch alone cannot do that.
   const uint32_t target_ctas = uint32_t(c->sm_count) * 8u;
