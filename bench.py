@@ -181,11 +181,12 @@ def run_reference(args, rank):
     t = times[args.warmup:]
     ms = 1e3 * float(np.mean(t))
     val = rows / np.mean(t) / 1e6
-    line = {"impl": "reference", "metric": "filter->GROUP BY throughput (BASELINE.json configs[1])", "value": round(val, 2),
+    line = {"impl": "reference", "metric": "filter->GROUP BY throughput (BASELINE.json configs[1]; bm25 object = configs[2])", "value": round(val, 2),
             "unit": "Mrows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64", "data": "synthetic",
-            "config": {"workload": "groupby: %d-row x 8-col table, a<500000 AND b>=0.25 -> GROUP BY k(1e5) SUM(v),AVG(w),COUNT" % args.rows,
-                       "sample_rows": rows},
+            "config": {"workload": "groupby: %d rows/GPU x 8 int64/float64 columns (5 referenced, 40 B/row), a<500000 AND b>=0.25 -> "
+                                   "GROUP BY k (1e5 keys) SUM(v), AVG(w), COUNT(*)" % args.rows,
+                       "rows_per_gpu": args.rows, "sample_rows": rows},
             "cpu_baseline": {"value": round(val, 2), "unit": "Mrows/s", "cores": threads, "kind": "port",
                              "sample": "%d-row prefix of the same synthetic table per step (oracle restatement; the reference "
                                        "binary needs clang-21+DuckDB+Abseil and cannot be built here)" % rows},
@@ -199,7 +200,7 @@ def run_reference(args, rank):
             dt, _, _, _ = cpu_bm25(seg, dc, sum_dl, args.docs, qs, threads)
             ts.append(dt)
         t = ts[args.warmup:]
-        line["bm25"] = {"metric": "BM25 top-1000 postings scanned (BASELINE.json configs[2])", "value": round(postings / np.mean(t) / 1e6, 2),
+        line["bm25"] = {"metric": "BM25 top-1000, 2-term OR batch: postings scanned per second (BASELINE.json configs[2])", "value": round(postings / np.mean(t) / 1e6, 2),
                         "unit": "Mdocs/s", "ms_per_step": round(1e3 * float(np.mean(t)), 3),
                         "cpu_baseline": {"value": round(postings / np.mean(t) / 1e6, 2), "unit": "Mdocs/s", "cores": threads, "kind": "port",
                                          "sample": "%d of the %d two-term OR queries per step, block-max pruned oracle, simdcomp unpack from oracle/_ref"
@@ -454,7 +455,7 @@ def main():
             "metric": "BM25 top-1000, 2-term OR batch: postings scanned per second (BASELINE.json configs[2])",
             "value": round(world * postings / (bm_ms * 1e-3) / 1e6, 1), "unit": "Mdocs/s", "ms_per_step": round(bm_ms, 3),
             "corpus_docs_per_s_M": round(world * n_docs * nq / (bm_ms * 1e-3) / 1e6, 1),
-            "config": {"workload": "bm25: %d docs/GPU synthetic Zipf corpus, %d two-term OR queries/step over %d terms, top-%d, exhaustive scan (no block-max skipping yet)"
+            "config": {"workload": "bm25: %d docs/GPU synthetic Zipf corpus, %d two-term OR queries/step over %d terms, top-%d, exhaustive scan of both lists (block-max pruning level 1 acts on single-term queries only)"
                                    % (n_docs, nq, N_TERMS, TOPK), "postings_per_step": postings,
                        "l2": "256 MB write between timed steps (index ~L2-sized)"},
             "e2e": {"value": round(world * postings / (be_ms * 1e-3) / 1e6, 1), "unit": "Mdocs/s",

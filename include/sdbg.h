@@ -60,6 +60,12 @@ int sdbg_timer_stop(sdbg_ctx*, float* ms);
 int sdbg_sync(sdbg_ctx*);
 /* Number of kernels this context has launched since creation (bench's gpu_launches claim). */
 uint64_t sdbg_launch_count(const sdbg_ctx*);
+/* Block-max (WAND / MaxScore) pruning, the `WandContext` of irs::ExecuteTopK (doc_collector.hpp:88). On by
+ * default when the segment carries block-max data; results (hits) are identical either way, but with
+ * pruning total_matches is a lower bound (wand_scoring_test.cpp:382-384). Level 1 (default): blocks / windows
+ * whose block-max bound cannot beat the threshold are dropped while planning; level 2 additionally tests the
+ * largest term's blocks against the exact partial scores of the smaller terms (MaxScore-style). 0 = off. */
+int sdbg_set_wand(sdbg_ctx*, int level);
 /* Per-kernel device timing for roofline reports: when enabled, a CUDA event pair is recorded on the
  * context's stream around each hot kernel launch. kernel_id: 0 filter_groupby, 1 bm25_topk,
  * 2 topk_merge, 3 filter_count_sum. read() synchronises and returns the summed duration and the

@@ -54,6 +54,7 @@ SIGNATURES = {
     "sdbg_sync": (C.c_int, [_vp]),
     "sdbg_launch_count": (C.c_uint64, [_vp]),
     "sdbg_flush_l2": (C.c_int, [_vp]),
+    "sdbg_set_wand": (C.c_int, [_vp, C.c_int]),
     "sdbg_profile_enable": (C.c_int, [_vp, C.c_int]),
     "sdbg_profile_read": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), _u64p]),
     "sdbg_segment_create": (C.c_int, [_vp, C.c_uint32, C.POINTER(_vp)]),

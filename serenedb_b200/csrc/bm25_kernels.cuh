@@ -285,6 +285,7 @@ struct TopkParams {
   uint32_t k;
   uint32_t cap;                // candidate buffer capacity, power of two, > k
   int32_t conjunction;         // 0 OR, 1 AND
+  int32_t wand;                // 1: block-max pruning on (total_matches becomes a lower bound, like the reference with WAND)
 };
 
 constexpr uint32_t kPadDoc = 0xFFFFFFFFu;
@@ -315,6 +316,8 @@ bm25_topk_kernel(const TopkParams P) {
   __shared__ uint32_t s_item_term[2][32];
   __shared__ uint32_t s_phase[2][kMaxQueryTerms + 1];  // first item of each term
   __shared__ uint32_t s_lo[2], s_hi[2], s_valid[2];
+  __shared__ float s_item_bound[2][32];                // block-max upper bound of each item (+inf when unknown)
+  __shared__ float s_term_ub[2][kMaxQueryTerms];       // max bound over the term's blocks in the window (0 if none)
   __shared__ uint32_t s_cursor[kMaxQueryTerms];
   __shared__ QTermDev s_qt[kMaxQueryTerms];
   __shared__ uint32_t s_ncand, s_matched;
@@ -345,47 +348,91 @@ bm25_topk_kernel(const TopkParams P) {
   }
   __syncwarp();
 
+  // level 1 prunes single-term queries only (planner-level block skip is free there); with several terms the
+  // other terms' window bounds almost always keep every block alive, so the test would be pure overhead.
+  const bool prune = P.wand && !P.conjunction && P.seg.blk_max != nullptr && (T == 1u || P.wand >= 2);
+
   // Plans the window starting at doc `lo` into buffer `buf` (warp 0 only); returns the next lo.
+  // With pruning on, windows whose summed block-max bound cannot beat the current threshold are
+  // consumed without being handed to the decoders (UpdateWindowScores, max_score_iterator.hpp:437).
   auto plan = [&](uint32_t lo, uint32_t buf) -> uint32_t {
-    if (lo > chain_hi || lo == 0u) {  // lo == 0: wrapped past 2^32-1
-      if (lane == 0) s_valid[buf] = 0u;
-      return 0u;
-    }
-    const uint32_t t = lane / m, j = lane - t * m;
-    const bool mine = t < T && lane < T * m;
-    uint4 d = make_uint4(0, 0, 0, 0);
-    bool exists = false;
-    if (mine) {
-      const uint32_t b = s_cursor[t] + j;
-      exists = b < s_qt[t].nblk;
-      if (exists) d = ld_ro_v4(P.seg.blocks + s_qt[t].blk_begin + b);
-    }
-    // a term that still has m blocks bounds the window at the end of its m-th block
-    uint32_t hi = (exists && j == m - 1u) ? d.y : 0xFFFFFFFFu;
+    for (uint32_t tries = 0;; ++tries) {
+      if (lo > chain_hi || lo == 0u) {  // lo == 0: wrapped past 2^32-1
+        if (lane == 0) s_valid[buf] = 0u;
+        return 0u;
+      }
+      const uint32_t t = lane / m, j = lane - t * m;
+      const bool mine = t < T && lane < T * m;
+      uint4 d = make_uint4(0, 0, 0, 0);
+      bool exists = false;
+      uint32_t gblk = 0;
+      if (mine) {
+        const uint32_t b = s_cursor[t] + j;
+        exists = b < s_qt[t].nblk;
+        gblk = s_qt[t].blk_begin + b;
+        if (exists) d = ld_ro_v4(P.seg.blocks + gblk);
+      }
+      // a term that still has m blocks bounds the window at the end of its m-th block
+      uint32_t hi = (exists && j == m - 1u) ? d.y : 0xFFFFFFFFu;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) hi = min(hi, __shfl_xor_sync(kFull, hi, o));
-    hi = min(hi, chain_hi);
-    const bool overlap = exists && d.z < hi;           // first doc of the block (prev_last + 1) <= hi
-    const bool consumed = exists && d.y <= hi;          // block ends inside the window
-    const uint32_t ov = __ballot_sync(kFull, overlap);
-    const uint32_t co = __ballot_sync(kFull, consumed);
-    if (overlap) {
-      const uint32_t idx = __popc(ov & ((1u << lane) - 1u));
-      s_item[buf][idx] = d;
-      s_item_term[buf][idx] = t;
+      for (int o = 16; o > 0; o >>= 1) hi = min(hi, __shfl_xor_sync(kFull, hi, o));
+      hi = min(hi, chain_hi);
+      bool overlap = exists && d.z < hi;                 // first doc of the block (prev_last + 1) <= hi
+      const bool consumed = exists && d.y <= hi;          // block ends inside the window
+      const uint32_t co = __ballot_sync(kFull, consumed);
+      float bound = __int_as_float(0x7f800000);           // +inf: no block-max data => never skipped
+      bool skip_window = false;
+      if (prune) {
+        if (overlap) {
+          const uint2 fn = __ldg(P.seg.blk_max + gblk);
+          if (fn.x != 0u) bound = bm25(fn.x, fn.y, s_qt[t].c0, s_qt[t].norm_const, s_qt[t].norm_length);
+        }
+        // per-term window bound = max over the term's blocks that reach into the window (0 if none)
+        s_item_bound[buf][lane] = overlap ? bound : 0.f;
+        __syncwarp();
+        if (lane < T) {
+          float ub = 0.f;
+          for (uint32_t i = lane * m; i < min(lane * m + m, 32u); ++i) ub = fmaxf(ub, s_item_bound[buf][i]);
+          s_term_ub[buf][lane] = ub;
+        }
+        __syncwarp();
+        // A block is dropped when even its own block-max plus the best the OTHER terms can add inside this
+        // window stays below the threshold (SingleWandIterator's block skip, iterator_score.hpp:218-233, for
+        // one term; the window-level test of MaxScore for several). Strict '<': an equal score could still
+        // win on doc id. Sum in ascending-cost order with this term's contribution replaced by the bound.
+        const float thr = __uint_as_float(uint32_t(s_theta >> 32));
+        float sum = 0.f;
+        for (uint32_t u = 0; u < T; ++u) sum = __fadd_rn(sum, u == t ? bound : s_term_ub[buf][u]);
+        if (overlap && sum < thr) overlap = false;
+        __syncwarp();
+      }
+      const uint32_t ov = __ballot_sync(kFull, overlap);
+      skip_window = prune && ov == 0u && tries < 64u;
+      if (overlap) {
+        const uint32_t idx = __popc(ov & ((1u << lane) - 1u));
+        s_item[buf][idx] = d;
+        s_item_term[buf][idx] = t;
+      }
+      __syncwarp();
+      if (overlap) s_item_bound[buf][__popc(ov & ((1u << lane) - 1u))] = bound;   // re-indexed by item
+      if (lane <= T) {  // first item of term `lane` = overlapping lanes below the term's first lane
+        const uint32_t first_lane = min(lane * m, 32u);
+        s_phase[buf][lane] = first_lane >= 32u ? __popc(ov) : __popc(ov & ((1u << first_lane) - 1u));
+      }
+      if (lane < T) {
+        const uint32_t lo_l = lane * m, n = min(m, 32u - lo_l);
+        const uint32_t bits = n >= 32u ? 0xFFFFFFFFu : (((1u << n) - 1u) << lo_l);
+        s_cursor[lane] += __popc(co & bits);
+      }
+      __syncwarp();
+      if (!skip_window) {
+        if (lane == 0) { s_lo[buf] = lo; s_hi[buf] = hi; s_valid[buf] = 1u; }
+        __syncwarp();
+        return hi + 1u;  // wraps to 0 at 2^32-1: treated as "past the end"
+      }
+      lo = hi + 1u;      // nothing in [lo, hi] can reach the threshold: plan the next window straight away
+      __syncwarp();
     }
-    if (lane <= T) {  // first item of term `lane` = overlapping lanes below the term's first lane
-      const uint32_t first_lane = min(lane * m, 32u);
-      s_phase[buf][lane] = first_lane >= 32u ? __popc(ov) : __popc(ov & ((1u << first_lane) - 1u));
-    }
-    if (lane < T) {
-      const uint32_t lo_l = lane * m, n = min(m, 32u - lo_l);
-      const uint32_t bits = n >= 32u ? 0xFFFFFFFFu : (((1u << n) - 1u) << lo_l);
-      s_cursor[lane] += __popc(co & bits);
-    }
-    if (lane == 0) { s_lo[buf] = lo; s_hi[buf] = hi; s_valid[buf] = 1u; }
-    __syncwarp();
-    return hi + 1u;  // wraps to 0 at 2^32-1: treated as "past the end"
   };
 
   // Candidate buffer full: exact radix select keeps the best k and raises the thresholds (the GPU
@@ -418,30 +465,66 @@ bm25_topk_kernel(const TopkParams P) {
     if (warp == 0) next_lo = plan(next_lo, buf ^ 1u);  // next window's plan overlaps this window's work
 
     // ---- 1. decode + score: one 128-posting block per warp iteration -> entries [it*128, it*128+128) ----
-    for (uint32_t it = warp; it < n_items; it += kTopkWarps) {
-      const uint4 d = s_item[buf][it];
-      const uint32_t t = s_item_term[buf][it];
-      uint32_t doc[4], f[4];
-      decode_docs(P.seg.arena, d, lane, stage[warp], doc);
-      decode_freqs(P.seg.arena, d, lane, f);
-      const uint32_t len = desc_len(d.w);
-      const float c0 = s_qt[t].c0, nc = s_qt[t].norm_const, nl = s_qt[t].norm_length;
-      uint32_t nrm[4]; bool in[4];
+    // With pruning on and more than one term, the largest term (last, it is only ever a fold target)
+    // is decoded in a second phase: a block of it is skipped when its block-max bound plus the EXACT
+    // best partial score the smaller terms reach inside the block's doc range cannot beat the
+    // threshold -- the essential / non-essential split of MaxScoreIterator (max_score_iterator.hpp:450-508)
+    // at block granularity. A skipped block leaves sorted fillers (doc = its last doc, score < 0).
+    const uint32_t last_begin = (prune && P.wand >= 2 && T > 1u) ? s_phase[buf][T - 1u] : n_items;
+    for (uint32_t ph = 0; ph < 2u; ++ph) {
+      const uint32_t it_begin = ph == 0u ? 0u : last_begin;
+      const uint32_t it_end = ph == 0u ? last_begin : n_items;
+      if (ph == 1u && it_begin == it_end) break;
+      if (ph == 1u) __syncthreads();                       // smaller terms' entries are complete
+      const float thr = __uint_as_float(uint32_t(s_theta >> 32));
+      for (uint32_t it = it_begin + warp; it < it_end; it += kTopkWarps) {
+        const uint4 d = s_item[buf][it];
+        const uint32_t t = s_item_term[buf][it];
+        if (ph == 1u) {
+          float ub = 0.f;
+          for (uint32_t u = 0; u + 1u < T; ++u) {
+            const uint32_t ub_begin = s_phase[buf][u] * 128u, un = (s_phase[buf][u + 1u] - s_phase[buf][u]) * 128u;
+            float mx = 0.f;
+            if (un) {
+              const uint32_t p0 = lower_bound_u32(e_doc + ub_begin, un, d.z + 1u);   // first doc of the block
+              const uint32_t p1 = lower_bound_u32(e_doc + ub_begin, un, d.y + 1u);   // one past its last doc
+              for (uint32_t i = p0 + lane; i < p1; i += 32u) mx = fmaxf(mx, e_score[ub_begin + i]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (4u * lane + j >= len) doc[j] = kPadDoc;       // short (last) block of a list: pad sorts last
-        in[j] = doc[j] >= lo && doc[j] <= hi;               // docs of a straddling block outside the window stay
-        nrm[j] = in[j] ? load_norm(P.seg.norms, P.seg.norm_width, doc[j]) : 1u;   // in the array (sortedness) but are never emitted
+              for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
+            }
+            ub = __fadd_rn(ub, mx);
+          }
+          ub = __fadd_rn(ub, s_item_bound[buf][it]);
+          if (ub < thr) {                                  // uniform per warp
+            const uint4 od = make_uint4(d.y, d.y, d.y, d.y);
+            const float4 os = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f);
+            reinterpret_cast<uint4*>(e_doc + it * 128u)[lane] = od;
+            reinterpret_cast<float4*>(e_score + it * 128u)[lane] = os;
+            continue;
+          }
+        }
+        uint32_t doc[4], f[4];
+        decode_docs(P.seg.arena, d, lane, stage[warp], doc);
+        decode_freqs(P.seg.arena, d, lane, f);
+        const uint32_t len = desc_len(d.w);
+        const float c0 = s_qt[t].c0, nc = s_qt[t].norm_const, nl = s_qt[t].norm_length;
+        uint32_t nrm[4]; bool in[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (4u * lane + j >= len) doc[j] = kPadDoc;       // short (last) block of a list: pad sorts last
+          in[j] = doc[j] >= lo && doc[j] <= hi;               // docs of a straddling block outside the window stay
+          nrm[j] = in[j] ? load_norm(P.seg.norms, P.seg.norm_width, doc[j]) : 1u;   // in the array (sortedness) but are never emitted
+        }
+        uint4 od; float4 os;
+        od.x = doc[0]; od.y = doc[1]; od.z = doc[2]; od.w = doc[3];
+        os.x = in[0] ? bm25(f[0], nrm[0], c0, nc, nl) : 0.f;
+        os.y = in[1] ? bm25(f[1], nrm[1], c0, nc, nl) : 0.f;
+        os.z = in[2] ? bm25(f[2], nrm[2], c0, nc, nl) : 0.f;
+        os.w = in[3] ? bm25(f[3], nrm[3], c0, nc, nl) : 0.f;
+        reinterpret_cast<uint4*>(e_doc + it * 128u)[lane] = od;
+        reinterpret_cast<float4*>(e_score + it * 128u)[lane] = os;
+        if (P.conjunction) reinterpret_cast<uint32_t*>(e_cnt + it * 128u)[lane] = 0u;
       }
-      uint4 od; float4 os;
-      od.x = doc[0]; od.y = doc[1]; od.z = doc[2]; od.w = doc[3];
-      os.x = in[0] ? bm25(f[0], nrm[0], c0, nc, nl) : 0.f;
-      os.y = in[1] ? bm25(f[1], nrm[1], c0, nc, nl) : 0.f;
-      os.z = in[2] ? bm25(f[2], nrm[2], c0, nc, nl) : 0.f;
-      os.w = in[3] ? bm25(f[3], nrm[3], c0, nc, nl) : 0.f;
-      reinterpret_cast<uint4*>(e_doc + it * 128u)[lane] = od;
-      reinterpret_cast<float4*>(e_score + it * 128u)[lane] = os;
-      if (P.conjunction) reinterpret_cast<uint32_t*>(e_cnt + it * 128u)[lane] = 0u;
     }
     __syncthreads();
 
@@ -484,9 +567,10 @@ bm25_topk_kernel(const TopkParams P) {
         bool live = d - lo <= hi - lo;                       // in window, not padding / folded / already stored
         if (live && P.conjunction) live = e_cnt[e] == T - 1u;
         if (live && P.filt.values != nullptr) live = filter_pass(P.filt, d);
-        matched += (live && first_pass) ? 1u : 0u;
         // cheap pre-test on the score bits alone; the full 64-bit key only for the few that may qualify
         const uint32_t sbits = live ? __float_as_uint(e_score[e]) : 0u;
+        if (sbits & 0x80000000u) live = false;               // filler of a pruned block (negative score)
+        matched += (live && first_pass) ? 1u : 0u;
         bool want = live && sbits >= theta_hi;
         unsigned long long key = 0ull;
         if (want) { key = make_key(__uint_as_float(sbits), P.seg.ordinal_base + d); want = key > theta; }

@@ -60,6 +60,7 @@ struct sdbg_ctx {
   bool topk_attr_set = false;
   bool merge_attr_set = false;
   // optional per-kernel timing: CUDA events recorded on `stream` around the hot kernels
+  int wand = 1;       // block-max pruning level: 0 off (exact total_matches), 1 planner-level block/window skips, 2 + exact-partial-score skips of the largest term
   bool profiling = false;
   struct ProfSpan { int id; cudaEvent_t a, b; };
   std::vector<ProfSpan> spans;
@@ -169,6 +170,7 @@ extern "C" int sdbg_init(int device, sdbg_ctx** out) {
   auto* c = new sdbg_ctx;
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
+  c->wand = std::max(0, std::min(2, env_int("SDBG_WAND", 1)));
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
     delete c;
@@ -208,6 +210,11 @@ extern "C" int sdbg_flush_l2(sdbg_ctx* c) {
   return SDBG_OK;
 }
 
+extern "C" int sdbg_set_wand(sdbg_ctx* c, int enabled) {
+  if (!c) return SDBG_EINVAL;
+  c->wand = enabled < 0 ? 0 : enabled > 2 ? 2 : enabled;
+  return SDBG_OK;
+}
 extern "C" int sdbg_profile_enable(sdbg_ctx* c, int on) {
   if (!c) return SDBG_EINVAL;
   CU(c, cudaStreamSynchronize(c->stream));
@@ -552,6 +559,7 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
     P.lists = pl.lists; P.list_base = uint32_t(si) * pl.G;
     P.chunk = pl.chunk;
     P.k = k; P.cap = pl.cap; P.conjunction = kind == SDBG_QUERY_AND ? 1 : 0;
+    P.wand = (c->wand && s->has_wand) ? c->wand : 0;
     { ProfScope ps_(c, kProfTopk);
       if (pl.budget == 16) bm25_topk_kernel<16><<<dim3(pl.G, unsigned(nq)), kTopkThreads, pl.smem, c->stream>>>(P);
       else bm25_topk_kernel<32><<<dim3(pl.G, unsigned(nq)), kTopkThreads, pl.smem, c->stream>>>(P); }

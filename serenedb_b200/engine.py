@@ -82,6 +82,10 @@ class Context:
     def flush_l2(self):
         N.check(N.lib().sdbg_flush_l2(self._h), self._h)
 
+    def set_wand(self, enabled=True):
+        """Block-max pruning on/off (WandContext of irs::ExecuteTopK). Off => exact total_matches."""
+        N.check(N.lib().sdbg_set_wand(self._h, int(enabled)), self._h)
+
     def profile(self, on=True):
         N.check(N.lib().sdbg_profile_enable(self._h, 1 if on else 0), self._h)
 

@@ -12,6 +12,7 @@ def ctx():
     global _ctx
     if _ctx is None:
         _ctx = sdb.Context(0)
+        _ctx.set_wand(False)   # exact total_matches (ExecuteTopKWithCount semantics); tests/test_gpu_wand.py turns pruning on
     return _ctx
 
 
