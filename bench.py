@@ -220,6 +220,7 @@ def main():
     ap.add_argument("--skip-bm25", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="kernel probes only (no host round trip)")
+    ap.add_argument("--skip-extra", action="store_true", help="skip BASELINE configs[0] and configs[3]")
     ap.add_argument("--cpu-rows", type=int, default=100_000_000)
     ap.add_argument("--cpu-queries", type=int, default=256)
     ap.add_argument("--cpu-threads", type=int, default=0)
@@ -390,6 +391,7 @@ def main():
     if cpu_gb:
         line["cpu_baseline"] = cpu_gb
 
+    oseg = odc = osdl = None
     # ------------------------------------------------------------------ BM25 (configs[2])
     if not args.skip_bm25:
         n_docs = args.docs
@@ -487,6 +489,70 @@ def main():
                 assert np.array_equal(hits[qi, :n]["score"], ohits[qi, :n]["score"]), "bm25 parity (scores) q%d" % qi
         line["bm25"] = bm
         line["gpu_launches"] = int(gb_launches + bm_launches)
+    # ------------------------------------------------------------------ BASELINE configs[0] and configs[3] (N=1)
+    if world == 1 and not args.skip_extra and not args.skip_bm25:
+        import orc
+        other = {}
+        # configs[0]: 1 Mi rows int64 + float64, single filter + COUNT/SUM; reference CPU path on ONE thread
+        r1 = 1 << 20
+        s1 = sdb.Segment(ctx, r1)
+        s1.synth_column(1, 21, 1, 0, r1)   # x = h % 1e6
+        s1.synth_column(2, 22, 2, 0, r1)   # y in [0,1)
+        sc1 = sdb.IResearchScan([s1])
+        q_int = ([sdb.pred(1, "LT", 250000)], 1)
+        q_flt = ([sdb.pred(2, "LT", 0.25)], 2)
+        for _ in range(5):
+            sc1.count_sum(*q_int); sc1.count_sum(*q_flt)
+        reps = 50
+        ctx.sync(); ctx.timer_start()
+        for _ in range(reps):
+            g_int = sc1.count_sum(*q_int); g_flt = sc1.count_sum(*q_flt)
+        ms1 = ctx.timer_stop() / (2 * reps)
+        o1 = orc.Segment(r1, has_wand=False)
+        o1.add_column(1, orc.synth_column(21, 1, 0, r1)); o1.add_column(2, orc.synth_column(22, 2, 0, r1))
+        t = time.perf_counter()
+        for _ in range(5):
+            c_int = orc.filter_count_sum([o1], [orc.make_pred(1, "LT", 250000)], 1, threads=1)
+            c_flt = orc.filter_count_sum([o1], [orc.make_pred(2, "LT", 0.25, is_float=True)], 2, threads=1)
+        cpu1 = (time.perf_counter() - t) / 10
+        assert g_int[:2] == c_int[:2] and g_flt[0] == c_flt[0] and abs(g_flt[2] - c_flt[2]) <= 1e-9 * abs(c_flt[2])
+        other["configs[0]"] = {"workload": "1 Mi rows, WHERE x<250000 / y<0.25 -> COUNT(*), SUM; host call incl. result D2H (launch-bound: 8 MiB)",
+                               "value": round(r1 / (ms1 * 1e-3) / 1e6, 1), "unit": "Mrows/s", "us_per_query": round(ms1 * 1e3, 1),
+                               "cpu_baseline": {"value": round(r1 / cpu1 / 1e6, 1), "unit": "Mrows/s", "cores": 1, "kind": "port"}}
+        s1.close()
+        # configs[3]: 5-term conjunctive BM25 + range filter on an int32 INCLUDE column, top-1000 (hybrid)
+        cseg.synth_column(9, 2, 6, rank * n_docs + 1, n_docs)   # n = h % 1e6 for docs 1..N
+        filt = sdb.pred(9, "BETWEEN", 250000, 749999)
+        q4 = [0, 1, 2, 3, 4]
+        nq4 = 64
+        b4 = sdb.PreparedBatch(reader, [q4] * nq4, sdb.AND, scorer, TOPK, filt=filt)
+        ctx.set_wand(0)
+        b4.run_host()
+        ctx.flush_l2(); ctx.sync(); ctx.timer_start()
+        h4, n4, t4 = b4.run_host()
+        ms4 = ctx.timer_stop()
+        ctx.set_wand(1)
+        p4 = int(sum(int(dc[t]) for t in q4))
+        oseg4, odc4, osdl4 = cpu_bm25_setup(n_docs, threads) if oseg is None else (oseg, odc, osdl)
+        col = np.zeros(n_docs, np.int32)
+        col[:] = orc.synth_column(2, 1, 1, n_docs).astype(np.int32)
+        oseg4.add_column(9, col)
+        qt4 = []
+        for t_ in q4:
+            st = orc.bm25_stats(n_docs, sum_dl, int(dc[t_]))
+            x = orc.BM25Term(); x.idf, x.norm_const, x.norm_length, x.boost, x.term = st.idf, st.norm_const, st.norm_length, 1.0, t_
+            qt4.append(x)
+        ncpu4 = min(threads, 32)
+        tcpu = time.perf_counter()
+        oh4, on4, ot4, _ = orc.bm25_topk_batch([oseg4], "AND", [qt4] * ncpu4, TOPK, filt=orc.make_pred(9, "BETWEEN", 250000, 749999), mode=1, threads=threads)
+        cpu4 = time.perf_counter() - tcpu
+        assert np.array_equal(h4[0, :n4[0]]["doc"], oh4[0, :on4[0]]["doc"]) and np.array_equal(h4[0, :n4[0]]["score"], oh4[0, :on4[0]]["score"])
+        assert int(t4[0]) == int(ot4[0])
+        other["configs[3]"] = {"workload": "%d docs, 5-term AND (terms 0-4, %d postings) + n BETWEEN 250000 AND 749999, top-1000; batch of %d, host call" % (n_docs, p4, nq4),
+                               "value": round(nq4 * p4 / (ms4 * 1e-3) / 1e6, 1), "unit": "Mdocs/s", "ms_per_query": round(ms4 / nq4, 3), "matches": int(t4[0]),
+                               "cpu_baseline": {"value": round(ncpu4 * p4 / cpu4 / 1e6, 1), "unit": "Mdocs/s", "cores": min(threads, ncpu4), "kind": "port",
+                                                "sample": "%d concurrent copies of the query" % ncpu4}}
+        line["other_configs"] = other
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
