@@ -48,7 +48,7 @@ struct QTermDev {  // one term of one query, 32 bytes
   float norm_const;
   float norm_length;
   uint32_t docs_count;
-  uint32_t pad0, pad1;
+  uint32_t root_freq, root_norm;   // block-max pair of the whole list (0,0 = unknown)
 };
 
 constexpr uint32_t kMaxQueryTerms = 16;
@@ -300,7 +300,8 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* a, uint32_t 
   return pos;
 }
 
-template <uint32_t kBudget>
+// kDrive compiles the driver-mode code (pruning level 2) in; the default kernel stays free of its registers.
+template <uint32_t kBudget, bool kDrive>
 __global__ void __launch_bounds__(kTopkThreads)
 bm25_topk_kernel(const TopkParams P) {
   constexpr uint32_t kEntries = kBudget * 128u;
@@ -310,6 +311,7 @@ bm25_topk_kernel(const TopkParams P) {
   float* e_score = reinterpret_cast<float*>(e_doc + kEntries);
   uint8_t* e_cnt = reinterpret_cast<uint8_t*>(e_score + kEntries);
   unsigned long long* cand = reinterpret_cast<unsigned long long*>(e_cnt + (P.conjunction ? kEntries : 0u));
+  uint16_t* s_probe = reinterpret_cast<uint16_t*>(cand + P.cap);   // kEntries u16, only present at wand level 2
 
   __shared__ __align__(16) uint32_t stage[kTopkWarps][128];
   __shared__ __align__(16) uint4 s_item[2][32];        // descriptors of the window's blocks, term-major
@@ -317,6 +319,10 @@ bm25_topk_kernel(const TopkParams P) {
   __shared__ uint32_t s_phase[2][kMaxQueryTerms + 1];  // first item of each term
   __shared__ uint32_t s_lo[2], s_hi[2], s_valid[2];
   __shared__ float s_item_bound[2][32];                // block-max upper bound of each item (+inf when unknown)
+  __shared__ uint32_t s_driver;                        // 1: the largest list is probed per candidate instead of scanned
+  __shared__ uint32_t s_Lb0[2], s_Lb1[2];              // block range of the largest list that covers the window (driver mode)
+  __shared__ uint32_t s_nprobe;
+  __shared__ float s_ubL;                              // global block-max bound of the largest list
   __shared__ float s_term_ub[2][kMaxQueryTerms];       // max bound over the term's blocks in the window (0 if none)
   __shared__ uint32_t s_cursor[kMaxQueryTerms];
   __shared__ QTermDev s_qt[kMaxQueryTerms];
@@ -350,19 +356,37 @@ bm25_topk_kernel(const TopkParams P) {
 
   // level 1 prunes single-term queries only (planner-level block skip is free there); with several terms the
   // other terms' window bounds almost always keep every block alive, so the test would be pure overhead.
+  // level 2 adds DRIVER MODE for disjunctions: once the threshold exceeds the global block-max bound of the
+  // largest list L, a doc that occurs only in L can no longer qualify (L is "non-essential",
+  // max_score_iterator.hpp:450-508). From then on windows are planned over the other lists only and L is
+  // probed per surviving candidate (ProcessNonEssentialFromCandidates, :406-429) instead of being scanned.
   const bool prune = P.wand && !P.conjunction && P.seg.blk_max != nullptr && (T == 1u || P.wand >= 2);
+  const bool can_drive = kDrive && prune && P.wand >= 2 && T >= 2u;
+  if (tid == 0) {
+    s_driver = 0u;
+    const QTermDev& L = s_qt[T - 1u];
+    s_ubL = (can_drive && L.root_freq != 0u) ? bm25(L.root_freq, L.root_norm, L.c0, L.norm_const, L.norm_length)
+                                              : __int_as_float(0x7f800000);
+  }
+  __syncthreads();
 
   // Plans the window starting at doc `lo` into buffer `buf` (warp 0 only); returns the next lo.
-  // With pruning on, windows whose summed block-max bound cannot beat the current threshold are
-  // consumed without being handed to the decoders (UpdateWindowScores, max_score_iterator.hpp:437).
+  // With pruning on, blocks / windows whose block-max bound cannot beat the current threshold are consumed
+  // without being handed to the decoders (UpdateWindowScores, max_score_iterator.hpp:437).
   auto plan = [&](uint32_t lo, uint32_t buf) -> uint32_t {
+    const float thr = __uint_as_float(uint32_t(s_theta >> 32));
+    if (can_drive && !s_driver && thr > s_ubL) { if (lane == 0) s_driver = 1u; }   // one-way switch (the threshold only rises)
+    __syncwarp();
+    const bool driver = kDrive && s_driver != 0u;
+    const uint32_t Tp = driver ? T - 1u : T;             // lists that get planner lanes
+    const uint32_t mp = max(1u, kBudget / Tp);
     for (uint32_t tries = 0;; ++tries) {
       if (lo > chain_hi || lo == 0u) {  // lo == 0: wrapped past 2^32-1
         if (lane == 0) s_valid[buf] = 0u;
         return 0u;
       }
-      const uint32_t t = lane / m, j = lane - t * m;
-      const bool mine = t < T && lane < T * m;
+      const uint32_t t = lane / mp, j = lane - t * mp;
+      const bool mine = t < Tp && lane < Tp * mp;
       uint4 d = make_uint4(0, 0, 0, 0);
       bool exists = false;
       uint32_t gblk = 0;
@@ -372,8 +396,8 @@ bm25_topk_kernel(const TopkParams P) {
         gblk = s_qt[t].blk_begin + b;
         if (exists) d = ld_ro_v4(P.seg.blocks + gblk);
       }
-      // a term that still has m blocks bounds the window at the end of its m-th block
-      uint32_t hi = (exists && j == m - 1u) ? d.y : 0xFFFFFFFFu;
+      // a term that still has mp blocks bounds the window at the end of its mp-th block
+      uint32_t hi = (exists && j == mp - 1u) ? d.y : 0xFFFFFFFFu;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) hi = min(hi, __shfl_xor_sync(kFull, hi, o));
       hi = min(hi, chain_hi);
@@ -381,7 +405,6 @@ bm25_topk_kernel(const TopkParams P) {
       const bool consumed = exists && d.y <= hi;          // block ends inside the window
       const uint32_t co = __ballot_sync(kFull, consumed);
       float bound = __int_as_float(0x7f800000);           // +inf: no block-max data => never skipped
-      bool skip_window = false;
       if (prune) {
         if (overlap) {
           const uint2 fn = __ldg(P.seg.blk_max + gblk);
@@ -390,24 +413,24 @@ bm25_topk_kernel(const TopkParams P) {
         // per-term window bound = max over the term's blocks that reach into the window (0 if none)
         s_item_bound[buf][lane] = overlap ? bound : 0.f;
         __syncwarp();
-        if (lane < T) {
+        if (lane < Tp) {
           float ub = 0.f;
-          for (uint32_t i = lane * m; i < min(lane * m + m, 32u); ++i) ub = fmaxf(ub, s_item_bound[buf][i]);
+          for (uint32_t i = lane * mp; i < min(lane * mp + mp, 32u); ++i) ub = fmaxf(ub, s_item_bound[buf][i]);
           s_term_ub[buf][lane] = ub;
         }
         __syncwarp();
-        // A block is dropped when even its own block-max plus the best the OTHER terms can add inside this
+        // A block is dropped when even its own block-max plus the best the OTHER lists can add inside this
         // window stays below the threshold (SingleWandIterator's block skip, iterator_score.hpp:218-233, for
         // one term; the window-level test of MaxScore for several). Strict '<': an equal score could still
         // win on doc id. Sum in ascending-cost order with this term's contribution replaced by the bound.
-        const float thr = __uint_as_float(uint32_t(s_theta >> 32));
         float sum = 0.f;
-        for (uint32_t u = 0; u < T; ++u) sum = __fadd_rn(sum, u == t ? bound : s_term_ub[buf][u]);
+        for (uint32_t u = 0; u < Tp; ++u) sum = __fadd_rn(sum, u == t ? bound : s_term_ub[buf][u]);
+        if (driver) sum = __fadd_rn(sum, s_ubL);
         if (overlap && sum < thr) overlap = false;
         __syncwarp();
       }
       const uint32_t ov = __ballot_sync(kFull, overlap);
-      skip_window = prune && ov == 0u && tries < 64u;
+      const bool skip_window = prune && ov == 0u && tries < 64u;
       if (overlap) {
         const uint32_t idx = __popc(ov & ((1u << lane) - 1u));
         s_item[buf][idx] = d;
@@ -415,18 +438,35 @@ bm25_topk_kernel(const TopkParams P) {
       }
       __syncwarp();
       if (overlap) s_item_bound[buf][__popc(ov & ((1u << lane) - 1u))] = bound;   // re-indexed by item
-      if (lane <= T) {  // first item of term `lane` = overlapping lanes below the term's first lane
-        const uint32_t first_lane = min(lane * m, 32u);
+      if (lane <= Tp) {  // first item of term `lane` = overlapping lanes below the term's first lane
+        const uint32_t first_lane = min(lane * mp, 32u);
         s_phase[buf][lane] = first_lane >= 32u ? __popc(ov) : __popc(ov & ((1u << first_lane) - 1u));
       }
-      if (lane < T) {
-        const uint32_t lo_l = lane * m, n = min(m, 32u - lo_l);
+      if (lane > Tp && lane <= T) s_phase[buf][lane] = __popc(ov);     // driver mode: the probed list owns no items
+      if (lane < Tp) {
+        const uint32_t lo_l = lane * mp, n = min(mp, 32u - lo_l);
         const uint32_t bits = n >= 32u ? 0xFFFFFFFFu : (((1u << n) - 1u) << lo_l);
         s_cursor[lane] += __popc(co & bits);
       }
+      if (kDrive && driver && lane == 31u) {
+        // block range of L covering [lo, hi]: gallop from its cursor (windows only move forward)
+        const uint4* B = P.seg.blocks + s_qt[T - 1u].blk_begin;
+        const uint32_t nblk = s_qt[T - 1u].nblk;
+        uint32_t a = s_cursor[T - 1u], step = 1u;          // first block with last_doc >= lo
+        while (a + step <= nblk && __ldg(&B[a + step - 1u].y) < lo) { a += step; step <<= 1; }
+        uint32_t l = a, r = min(a + step - 1u, nblk);
+        while (l < r) { const uint32_t mid = (l + r) >> 1; if (__ldg(&B[mid].y) < lo) l = mid + 1u; else r = mid; }
+        const uint32_t b0 = l;
+        uint32_t e = b0; step = 1u;                         // first block that starts after hi
+        while (e + step <= nblk && __ldg(&B[e + step - 1u].z) < hi) { e += step; step <<= 1; }
+        l = e; r = min(e + step - 1u, nblk);
+        while (l < r) { const uint32_t mid = (l + r) >> 1; if (__ldg(&B[mid].z) < hi) l = mid + 1u; else r = mid; }
+        s_cursor[T - 1u] = b0;
+        s_Lb0[buf] = b0; s_Lb1[buf] = l;
+      }
       __syncwarp();
       if (!skip_window) {
-        if (lane == 0) { s_lo[buf] = lo; s_hi[buf] = hi; s_valid[buf] = 1u; }
+        if (lane == 0) { s_lo[buf] = lo; s_hi[buf] = hi; s_valid[buf] = driver ? 2u : 1u; }
         __syncwarp();
         return hi + 1u;  // wraps to 0 at 2^32-1: treated as "past the end"
       }
@@ -457,79 +497,46 @@ bm25_topk_kernel(const TopkParams P) {
 
   for (uint32_t buf = 0; s_valid[buf]; buf ^= 1u) {
     const uint32_t lo = s_lo[buf], hi = s_hi[buf];
-    const uint32_t n_items = s_phase[buf][T];
+    const bool driver = kDrive && s_valid[buf] == 2u;               // this window was planned without the largest list
+    const uint32_t Tw = driver ? T - 1u : T;              // lists decoded into entry arrays in this window
+    const uint32_t n_items = s_phase[buf][Tw];
     if (tid == 0) {  // pick up thresholds published by other chains / earlier segments
       const unsigned long long gt = *reinterpret_cast<volatile unsigned long long*>(P.theta + q);
       if (gt > s_theta) s_theta = gt;
+      s_nprobe = 0u;
     }
     if (warp == 0) next_lo = plan(next_lo, buf ^ 1u);  // next window's plan overlaps this window's work
 
     // ---- 1. decode + score: one 128-posting block per warp iteration -> entries [it*128, it*128+128) ----
-    // With pruning on and more than one term, the largest term (last, it is only ever a fold target)
-    // is decoded in a second phase: a block of it is skipped when its block-max bound plus the EXACT
-    // best partial score the smaller terms reach inside the block's doc range cannot beat the
-    // threshold -- the essential / non-essential split of MaxScoreIterator (max_score_iterator.hpp:450-508)
-    // at block granularity. A skipped block leaves sorted fillers (doc = its last doc, score < 0).
-    const uint32_t last_begin = (prune && P.wand >= 2 && T > 1u) ? s_phase[buf][T - 1u] : n_items;
-    for (uint32_t ph = 0; ph < 2u; ++ph) {
-      const uint32_t it_begin = ph == 0u ? 0u : last_begin;
-      const uint32_t it_end = ph == 0u ? last_begin : n_items;
-      if (ph == 1u && it_begin == it_end) break;
-      if (ph == 1u) __syncthreads();                       // smaller terms' entries are complete
-      const float thr = __uint_as_float(uint32_t(s_theta >> 32));
-      for (uint32_t it = it_begin + warp; it < it_end; it += kTopkWarps) {
-        const uint4 d = s_item[buf][it];
-        const uint32_t t = s_item_term[buf][it];
-        if (ph == 1u) {
-          float ub = 0.f;
-          for (uint32_t u = 0; u + 1u < T; ++u) {
-            const uint32_t ub_begin = s_phase[buf][u] * 128u, un = (s_phase[buf][u + 1u] - s_phase[buf][u]) * 128u;
-            float mx = 0.f;
-            if (un) {
-              const uint32_t p0 = lower_bound_u32(e_doc + ub_begin, un, d.z + 1u);   // first doc of the block
-              const uint32_t p1 = lower_bound_u32(e_doc + ub_begin, un, d.y + 1u);   // one past its last doc
-              for (uint32_t i = p0 + lane; i < p1; i += 32u) mx = fmaxf(mx, e_score[ub_begin + i]);
+    for (uint32_t it = warp; it < n_items; it += kTopkWarps) {
+      const uint4 d = s_item[buf][it];
+      const uint32_t t = s_item_term[buf][it];
+      uint32_t doc[4], f[4];
+      decode_docs(P.seg.arena, d, lane, stage[warp], doc);
+      decode_freqs(P.seg.arena, d, lane, f);
+      const uint32_t len = desc_len(d.w);
+      const float c0 = s_qt[t].c0, nc = s_qt[t].norm_const, nl = s_qt[t].norm_length;
+      uint32_t nrm[4]; bool in[4];
 #pragma unroll
-              for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
-            }
-            ub = __fadd_rn(ub, mx);
-          }
-          ub = __fadd_rn(ub, s_item_bound[buf][it]);
-          if (ub < thr) {                                  // uniform per warp
-            const uint4 od = make_uint4(d.y, d.y, d.y, d.y);
-            const float4 os = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f);
-            reinterpret_cast<uint4*>(e_doc + it * 128u)[lane] = od;
-            reinterpret_cast<float4*>(e_score + it * 128u)[lane] = os;
-            continue;
-          }
-        }
-        uint32_t doc[4], f[4];
-        decode_docs(P.seg.arena, d, lane, stage[warp], doc);
-        decode_freqs(P.seg.arena, d, lane, f);
-        const uint32_t len = desc_len(d.w);
-        const float c0 = s_qt[t].c0, nc = s_qt[t].norm_const, nl = s_qt[t].norm_length;
-        uint32_t nrm[4]; bool in[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (4u * lane + j >= len) doc[j] = kPadDoc;       // short (last) block of a list: pad sorts last
-          in[j] = doc[j] >= lo && doc[j] <= hi;               // docs of a straddling block outside the window stay
-          nrm[j] = in[j] ? load_norm(P.seg.norms, P.seg.norm_width, doc[j]) : 1u;   // in the array (sortedness) but are never emitted
-        }
-        uint4 od; float4 os;
-        od.x = doc[0]; od.y = doc[1]; od.z = doc[2]; od.w = doc[3];
-        os.x = in[0] ? bm25(f[0], nrm[0], c0, nc, nl) : 0.f;
-        os.y = in[1] ? bm25(f[1], nrm[1], c0, nc, nl) : 0.f;
-        os.z = in[2] ? bm25(f[2], nrm[2], c0, nc, nl) : 0.f;
-        os.w = in[3] ? bm25(f[3], nrm[3], c0, nc, nl) : 0.f;
-        reinterpret_cast<uint4*>(e_doc + it * 128u)[lane] = od;
-        reinterpret_cast<float4*>(e_score + it * 128u)[lane] = os;
-        if (P.conjunction) reinterpret_cast<uint32_t*>(e_cnt + it * 128u)[lane] = 0u;
+      for (int j = 0; j < 4; ++j) {
+        if (4u * lane + j >= len) doc[j] = kPadDoc;       // short (last) block of a list: pad sorts last
+        in[j] = doc[j] >= lo && doc[j] <= hi;               // docs of a straddling block outside the window stay
+        nrm[j] = in[j] ? load_norm(P.seg.norms, P.seg.norm_width, doc[j]) : 1u;   // in the array (sortedness) but are never emitted
       }
+      uint4 od; float4 os;
+      od.x = doc[0]; od.y = doc[1]; od.z = doc[2]; od.w = doc[3];
+      os.x = in[0] ? bm25(f[0], nrm[0], c0, nc, nl) : 0.f;
+      os.y = in[1] ? bm25(f[1], nrm[1], c0, nc, nl) : 0.f;
+      os.z = in[2] ? bm25(f[2], nrm[2], c0, nc, nl) : 0.f;
+      os.w = in[3] ? bm25(f[3], nrm[3], c0, nc, nl) : 0.f;
+      reinterpret_cast<uint4*>(e_doc + it * 128u)[lane] = od;
+      reinterpret_cast<float4*>(e_score + it * 128u)[lane] = os;
+      if (P.conjunction) reinterpret_cast<uint32_t*>(e_cnt + it * 128u)[lane] = 0u;
     }
     __syncthreads();
 
     // ---- 2. fold term t into term t+1 (sources: live entries of terms 0..t) ----
-    for (uint32_t t = 0; t + 1u < T; ++t) {
+    for (uint32_t t = 0; t + 1u < Tw; ++t) {
       const uint32_t src_end = s_phase[buf][t + 1u] * 128u;
       const uint32_t dst_begin = src_end, dst_n = (s_phase[buf][t + 2u] - s_phase[buf][t + 1u]) * 128u;
       // Conjunction: the only candidates still alive at step t sit in term t's own slots and have
@@ -552,9 +559,85 @@ bm25_topk_kernel(const TopkParams P) {
       __syncthreads();
     }
 
+    // ---- 2b. driver mode: probe the largest list L for the candidates that can still qualify ----
+    if (kDrive && driver) {
+      const uint32_t n_ent = n_items * 128u;
+      const float thr = __uint_as_float(uint32_t(s_theta >> 32));
+      const float ubL = s_ubL;
+      for (uint32_t e0 = 0; e0 < n_ent; e0 += blockDim.x) {
+        const uint32_t e = e0 + tid;
+        const uint32_t d = e < n_ent ? e_doc[e] : kPadDoc;
+        const bool live = d - lo <= hi - lo;
+        // even with L's best possible contribution this doc stays below the threshold: drop it
+        const bool cand = live && !(__fadd_rn(e_score[live ? e : 0u], ubL) < thr);
+        if (live && !cand) e_doc[e] = kPadDoc;
+        const uint32_t cb = __ballot_sync(kFull, cand);
+        if (cb) {
+          uint32_t base = 0;
+          if (lane == 0) base = atomicAdd(&s_nprobe, uint32_t(__popc(cb)));
+          base = __shfl_sync(kFull, base, 0);
+          if (cand) s_probe[base + __popc(cb & ((1u << lane) - 1u))] = uint16_t(e);
+        }
+      }
+      __syncthreads();
+      const QTermDev& L = s_qt[T - 1u];
+      const uint4* LB = P.seg.blocks + L.blk_begin;
+      const uint32_t Lb0 = s_Lb0[buf], Lb1 = s_Lb1[buf];
+      const uint32_t n_probe = s_nprobe;
+      uint32_t have_blk = 0xFFFFFFFFu;
+      uint32_t pdoc[4], pf[4];
+      bool have_f = false;
+      uint4 pd = make_uint4(0, 0, 0, 0);
+      for (uint32_t c = warp; c < n_probe; c += kTopkWarps) {
+        const uint32_t e = s_probe[c];
+        const uint32_t d = e_doc[e];
+        const float partial = e_score[e];
+        // 32-ary search over L's blocks [Lb0, Lb1): first block with last_doc >= d
+        uint32_t bl = Lb0, bn = Lb1 - Lb0;
+        while (bn > 1u) {
+          const uint32_t step = (bn + 31u) >> 5;
+          const uint32_t idx = min((lane + 1u) * step, bn) - 1u;        // lane i looks at the last block of its slice
+          const bool ge = __ldg(&LB[bl + idx].y) >= d;
+          const uint32_t m = __ballot_sync(kFull, ge);
+          if (m == 0u) { bl += bn; bn = 0u; break; }                     // beyond every block of the range
+          const uint32_t fsl = uint32_t(__ffs(m) - 1);
+          const uint32_t nb = min((fsl + 1u) * step, bn) - fsl * step;
+          bl += fsl * step; bn = nb;
+        }
+        if (bn == 0u) continue;
+        if (have_blk != bl) {
+          pd = ld_ro_v4(LB + bl);
+          have_blk = bl; have_f = false;
+          if (!(pd.z < d && d <= pd.y)) { have_blk = 0xFFFFFFFFu; continue; }   // d falls between blocks: not in L
+          const uint2 fn = __ldg(P.seg.blk_max + L.blk_begin + bl);
+          if (fn.x != 0u && __fadd_rn(partial, bm25(fn.x, fn.y, L.c0, L.norm_const, L.norm_length)) < thr) {
+            e_doc[e] = kPadDoc;                                          // cannot qualify even with this block's best
+            have_blk = 0xFFFFFFFFu;
+            continue;
+          }
+          decode_docs(P.seg.arena, pd, lane, stage[warp], pdoc);
+          const uint32_t len = desc_len(pd.w);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (4u * lane + j >= len) pdoc[j] = kPadDoc;
+        } else if (!(pd.z < d && d <= pd.y)) {
+          continue;
+        }
+        const bool h0 = pdoc[0] == d, h1 = pdoc[1] == d, h2 = pdoc[2] == d, h3 = pdoc[3] == d;
+        const uint32_t hit = __ballot_sync(kFull, h0 | h1 | h2 | h3);
+        if (!hit) continue;                                              // doc not in L
+        if (!have_f) { decode_freqs(P.seg.arena, pd, lane, pf); have_f = true; }
+        if (h0 | h1 | h2 | h3) {
+          const uint32_t fr = h0 ? pf[0] : h1 ? pf[1] : h2 ? pf[2] : pf[3];
+          const float sL = bm25(fr, load_norm(P.seg.norms, P.seg.norm_width, d), L.c0, L.norm_const, L.norm_length);
+          e_score[e] = __fadd_rn(partial, sL);                           // L is last in ascending-cost order
+        }
+      }
+      __syncthreads();
+    }
+
     // ---- 3. emit live in-window entries ----
     const uint32_t n_entries = n_items * 128u;
-    const uint32_t emit_begin = P.conjunction ? s_phase[buf][T - 1u] * 128u : 0u;  // AND: only the last term's slots can be complete
+    const uint32_t emit_begin = P.conjunction ? s_phase[buf][T - 1u] * 128u : 0u;  // AND: only the last term's slots can be complete (never in driver mode)
     bool first_pass = true;
     for (;;) {
       const unsigned long long theta = s_theta;

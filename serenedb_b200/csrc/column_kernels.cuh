@@ -324,6 +324,12 @@ struct TmaGroupByParams {
   int32_t key_stream, sum_i_stream, sum_f_stream;   // -1 when absent
   int32_t wide_int;
   int32_t debug_skip;   // timing experiments only (SDBG_GROUPBY_DEBUG): bits 1/2/4 drop the count / sum_int / sum_f64 RED
+  // Packed accumulators (kPacked kernels): COUNT and SUM(int) share one 64-bit word, count << pack_shift |
+  // sum of (v - pack_bias), so a passing row costs one integer RED instead of two. The host proves from the
+  // column's min/max and the row count that neither field can overflow; rows are dealt to pack_tables
+  // (1..3) words of the slot by tile index when one word would not be enough.
+  int32_t pack_shift, pack_tables;
+  int64_t pack_bias;
   int64_t key_min;
   uint64_t key_span;
   uint64_t rows;
@@ -354,7 +360,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <int kStages, int kTileRows, int kConsumerWarps>
+template <int kStages, int kTileRows, int kConsumerWarps, bool kPacked>
 __global__ void __launch_bounds__((kConsumerWarps + 1) * 32)
 filter_groupby_tma_kernel(const TmaGroupByParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -403,6 +409,7 @@ filter_groupby_tma_kernel(const TmaGroupByParams P) {
     const unsigned char* base = smem + size_t(st) * stage_bytes;
     const uint64_t row0 = tile * kTileRows;
     const uint32_t nrows = uint32_t(min(static_cast<unsigned long long>(kTileRows), static_cast<unsigned long long>(P.rows - row0)));
+    const uint32_t pack_word = kPacked ? uint32_t(tile % uint64_t(P.pack_tables)) : 0u;   // words 0..2 of the slot: count / sum_lo / sum_hi
     // One row per lane; predicates are branch-free closed-range tests on the staged tile; a passing row
     // issues its REDs (fire-and-forget) into the L2-resident group table.
 #pragma unroll 2
@@ -432,6 +439,14 @@ filter_groupby_tma_kernel(const TmaGroupByParams P) {
       const unsigned long long idx = static_cast<unsigned long long>(key - P.key_min);
       if (idx >= P.key_span) { atomicAdd(P.out_of_range, 1ull); continue; }
       GroupSlot* g = P.table + idx;
+      if (kPacked) {
+        const unsigned char* vc = base + s_off[P.sum_i_stream];
+        const long long v = P.type[P.sum_i_stream] == 2 ? static_cast<long long>(reinterpret_cast<const int*>(vc)[r])
+                                                        : reinterpret_cast<const long long*>(vc)[r];
+        if (!(P.debug_skip & 3))
+          atomicAdd(reinterpret_cast<unsigned long long*>(g) + pack_word,
+                    (1ull << P.pack_shift) + static_cast<unsigned long long>(v - P.pack_bias));
+      } else {
       if (!(P.debug_skip & 1)) atomicAdd(&g->count, 1ull);
       if (P.sum_i_stream >= 0 && !(P.debug_skip & 2)) {
         const unsigned char* vc = base + s_off[P.sum_i_stream];
@@ -443,6 +458,7 @@ filter_groupby_tma_kernel(const TmaGroupByParams P) {
         } else {
           atomicAdd(reinterpret_cast<unsigned long long*>(&g->sum_lo), static_cast<unsigned long long>(v));
         }
+      }
       }
       if (P.sum_f_stream >= 0 && !(P.debug_skip & 4)) atomicAdd(&g->sum_f, reinterpret_cast<const double*>(base + s_off[P.sum_f_stream])[r]);
     }
@@ -538,9 +554,19 @@ filter_groupby_hash_kernel(const HashGroupByParams P) {
 // d_i64 = [count | sum_lo | sum_hi | cnt_f64] (4*span int64), d_f64 = [sum_f] (span float64).
 __global__ void __launch_bounds__(256)
 groupby_pack_kernel(const GroupSlot* __restrict__ table, const unsigned long long* __restrict__ cnt_f,
-                    uint64_t span, long long* __restrict__ d_i64, double* __restrict__ d_f64) {
+                    uint64_t span, long long* __restrict__ d_i64, double* __restrict__ d_f64,
+                    int pack_shift, int pack_tables, long long pack_bias) {
   for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < span; i += uint64_t(gridDim.x) * blockDim.x) {
-    const GroupSlot g = table[i];
+    GroupSlot g = table[i];
+    if (pack_tables) {  // packed accumulators: split count << shift | sum(v - bias) back into the plain fields
+      const unsigned long long w[3] = {g.count, static_cast<unsigned long long>(g.sum_lo), static_cast<unsigned long long>(g.sum_hi)};
+      const unsigned long long mask = (1ull << pack_shift) - 1ull;
+      unsigned long long cnt = 0, sum = 0;
+      for (int t = 0; t < pack_tables; ++t) { cnt += w[t] >> pack_shift; sum += w[t] & mask; }
+      g.count = cnt;
+      g.sum_lo = static_cast<long long>(sum + static_cast<unsigned long long>(pack_bias) * cnt);   // two's complement: exact, |SUM| < 2^62 here
+      g.sum_hi = 0;
+    }
     d_i64[i] = static_cast<long long>(g.count);
     d_i64[span + i] = g.sum_lo;
     d_i64[2 * span + i] = g.sum_hi;

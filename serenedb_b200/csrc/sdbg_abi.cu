@@ -492,7 +492,7 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
   pl.G = std::min(pl.G, std::max(1u, max_docs / 4096u));
   pl.chunk = (max_docs + pl.G - 1) / pl.G;
   pl.lists = pl.G * uint32_t(n_segs);
-  pl.smem = size_t(entries) * 8 + (kind == SDBG_QUERY_AND ? entries : 0) + size_t(pl.cap) * 8;
+  pl.smem = size_t(entries) * 8 + (kind == SDBG_QUERY_AND ? entries : 0) + size_t(pl.cap) * 8 + (c->wand >= 2 ? size_t(entries) * 2 : 0);
   if (pl.smem > 200 * 1024) return fail(c, SDBG_EUNSUPPORTED, "hash window + candidate buffer exceed shared memory");
 
   // host-side query descriptors, per segment, sorted by ascending docs_count (conjunction.hpp:520-523)
@@ -517,7 +517,7 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
         d.c0 = t.boost * (k1 + 1) * t.idf;  // bm25.cpp:224
         d.norm_const = t.norm_const; d.norm_length = t.norm_length;
         d.docs_count = s->term_docs[t.term];
-        d.pad0 = d.pad1 = 0;
+        d.root_freq = s->term_max[t.term].freq; d.root_norm = s->term_max[t.term].norm;
       }
       std::stable_sort(dst + b, dst + e, [](const QTermDev& x, const QTermDev& y) { return x.docs_count < y.docs_count; });
     }
@@ -540,8 +540,10 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
   CU(c, cudaMemsetAsync(d_total, 0, nq * 8, c->stream));
 
   if (!c->topk_attr_set) {
-    CU(c, cudaFuncSetAttribute(bm25_topk_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CU(c, cudaFuncSetAttribute(bm25_topk_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(c, cudaFuncSetAttribute(bm25_topk_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(c, cudaFuncSetAttribute(bm25_topk_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(c, cudaFuncSetAttribute(bm25_topk_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(c, cudaFuncSetAttribute(bm25_topk_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(c, cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     c->topk_attr_set = true;
   }
@@ -561,8 +563,12 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
     P.k = k; P.cap = pl.cap; P.conjunction = kind == SDBG_QUERY_AND ? 1 : 0;
     P.wand = (c->wand && s->has_wand) ? c->wand : 0;
     { ProfScope ps_(c, kProfTopk);
-      if (pl.budget == 16) bm25_topk_kernel<16><<<dim3(pl.G, unsigned(nq)), kTopkThreads, pl.smem, c->stream>>>(P);
-      else bm25_topk_kernel<32><<<dim3(pl.G, unsigned(nq)), kTopkThreads, pl.smem, c->stream>>>(P); }
+      const dim3 grid(pl.G, unsigned(nq));
+      const bool drive = c->wand >= 2 && kind != SDBG_QUERY_AND;
+      if (pl.budget == 16) { if (drive) bm25_topk_kernel<16, true><<<grid, kTopkThreads, pl.smem, c->stream>>>(P);
+                             else bm25_topk_kernel<16, false><<<grid, kTopkThreads, pl.smem, c->stream>>>(P); }
+      else { if (drive) bm25_topk_kernel<32, true><<<grid, kTopkThreads, pl.smem, c->stream>>>(P);
+             else bm25_topk_kernel<32, false><<<grid, kTopkThreads, pl.smem, c->stream>>>(P); } }
     ++c->launches;
     CU(c, cudaGetLastError());
     base += s->n_docs;
@@ -890,7 +896,8 @@ extern "C" int sdbg_filter_count_sum(sdbg_segment* const* segs, size_t n_segs, c
 
 namespace {
 
-struct GroupPlan { int wide_int = 0; int count_f = 0; };
+struct GroupPlan { int wide_int = 0; int count_f = 0; int pack_shift = 0; int pack_tables = 0; int64_t pack_bias = 0; };
+constexpr int kGroupByTileRows = 512;   // tile of the default TMA shape; packed accumulators are only planned for it
 
 int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred* preds, size_t n_preds, uint64_t key_field,
                    int64_t key_min, uint64_t span, uint64_t sum_int_field, uint64_t avg_f64_field, void* d_i64, void* d_f64,
@@ -906,17 +913,26 @@ int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred
   CU(c, cudaMemsetAsync(c->scratch[11].p, 0, table_bytes + span * 8 + 64, c->stream));
   GroupPlan plan;
   uint64_t total_rows = 0;
+  int64_t sum_mn = INT64_MAX, sum_mx = INT64_MIN;
+  bool all_tma = env_int("SDBG_GROUPBY_TMA", 1) != 0 && env_int("SDBG_GROUPBY_TMA_SHAPE", 0) == 0;
   for (size_t si = 0; si < n_segs; ++si) {  // statistics decide the accumulator shape
     sdbg_segment* s = segs[si];
     if (sum_int_field != UINT64_MAX) {
       int64_t mn, mx;
       if ((rc = column_minmax(s, sum_int_field, &mn, &mx))) return rc;
       if (mn < INT32_MIN || mx > INT32_MAX) plan.wide_int = 1;
+      sum_mn = std::min(sum_mn, mn); sum_mx = std::max(sum_mx, mx);
+      auto sit = s->cols.find(sum_int_field);
+      if (sit != s->cols.end() && sit->second.d_validity) all_tma = false;
+    }
+    for (size_t i = 0; i < n_preds; ++i) {
+      auto pit = s->cols.find(preds[i].field);
+      if (preds[i].op >= 7 || (pit != s->cols.end() && pit->second.d_validity)) all_tma = false;
     }
     if (avg_f64_field != UINT64_MAX) {
       auto it = s->cols.find(avg_f64_field);
       if (it == s->cols.end()) return fail(c, SDBG_ENOTFOUND, "avg column not staged");
-      if (it->second.d_validity) plan.count_f = 1;
+      if (it->second.d_validity) { plan.count_f = 1; all_tma = false; }
     }
     auto kit = s->cols.find(key_field);
     if (kit == s->cols.end()) return fail(c, SDBG_ENOTFOUND, "key column not staged");
@@ -925,6 +941,23 @@ int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred
     total_rows += kit->second.rows;
   }
   if (total_rows >= (1ull << 31)) return fail(c, SDBG_EUNSUPPORTED, ">= 2^31 rows per GPU in one GROUP BY (limb overflow guard)");
+  // Packed accumulators: one RED carries COUNT and SUM(int) when the column statistics prove that
+  // count << shift | sum(v - min) cannot overflow either field (the RED issue rate, not HBM, is what the
+  // consumer warps run into). Rows are dealt to 1..3 words of the slot by tile index.
+  if (sum_int_field != UINT64_MAX && !plan.wide_int && all_tma && total_rows && sum_mx >= sum_mn && env_int("SDBG_GROUPBY_PACKED", 1)) {
+    const unsigned __int128 range = static_cast<unsigned __int128>(static_cast<uint64_t>(sum_mx) - static_cast<uint64_t>(sum_mn));
+    for (int nt = std::max(1, env_int("SDBG_GROUPBY_PACK_TABLES_MIN", 1)); nt <= 3 && !plan.pack_tables; ++nt) {   // env: test hook
+      uint64_t cap_rows = 0;   // most rows any one word can receive: its share of every segment's tiles
+      for (size_t si = 0; si < n_segs; ++si) {
+        const uint64_t tiles = (segs[si]->cols.find(key_field)->second.rows + kGroupByTileRows - 1) / kGroupByTileRows;
+        cap_rows += (tiles + nt - 1) / nt * kGroupByTileRows;
+      }
+      const unsigned __int128 max_sum = range * cap_rows;
+      int shift = 1;
+      while (shift < 63 && (static_cast<unsigned __int128>(1) << shift) <= max_sum) ++shift;
+      if (shift < 63 && cap_rows < (1ull << (64 - shift))) { plan.pack_tables = nt; plan.pack_shift = shift; plan.pack_bias = sum_mn; }
+    }
+  }
   for (size_t si = 0; si < n_segs; ++si) {
     sdbg_segment* s = segs[si];
     GroupByParams P;
@@ -952,6 +985,7 @@ int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred
     // columns need their validity words next to the values and keep the register-staged kernel.
     bool any_nullable = P.key.validity || (P.has_sum_i && P.sum_i.validity) || (P.has_sum_f && P.sum_f.validity);
     for (int i = 0; i < P.ps.n; ++i) any_nullable |= P.ps.p[i].col.validity != nullptr || P.ps.p[i].op >= 7;
+    if (plan.pack_tables && any_nullable) return fail(c, SDBG_EINVAL, "internal: packed accumulators planned for a nullable segment");
     if (!any_nullable && env_int("SDBG_GROUPBY_TMA", 1)) {
       TmaGroupByParams T;
       std::memset(&T, 0, sizeof T);
@@ -999,6 +1033,7 @@ int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred
       T.sum_f_stream = P.has_sum_f ? stream_of(P.sum_f) : -1;
       T.debug_skip = env_int("SDBG_GROUPBY_DEBUG", 0);
       T.wide_int = plan.wide_int; T.key_min = key_min; T.key_span = span; T.rows = rows; T.table = table; T.out_of_range = oor;
+      T.pack_shift = plan.pack_shift; T.pack_tables = plan.pack_tables; T.pack_bias = plan.pack_bias;
       const int shape = env_int("SDBG_GROUPBY_TMA_SHAPE", 0);
       auto launch = [&](auto kern, int stages, int tile_rows, int consumer_warps) -> int {
         const size_t smem = size_t(stages) * size_t(tile_rows) * 8 * size_t(T.n_streams);
@@ -1013,11 +1048,12 @@ int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred
       };
       int lrc;
       switch (shape) {
-        case 1: lrc = launch(filter_groupby_tma_kernel<4, 256, 8>, 4, 256, 8); break;
-        case 2: lrc = launch(filter_groupby_tma_kernel<4, 512, 16>, 4, 512, 16); break;
-        case 3: lrc = launch(filter_groupby_tma_kernel<3, 256, 8>, 3, 256, 8); break;
-        case 4: lrc = launch(filter_groupby_tma_kernel<4, 1024, 16>, 4, 1024, 16); break;
-        default: lrc = launch(filter_groupby_tma_kernel<4, 512, 8>, 4, 512, 8); break;
+        case 1: lrc = launch(filter_groupby_tma_kernel<4, 256, 8, false>, 4, 256, 8); break;
+        case 2: lrc = launch(filter_groupby_tma_kernel<4, 512, 16, false>, 4, 512, 16); break;
+        case 3: lrc = launch(filter_groupby_tma_kernel<3, 256, 8, false>, 3, 256, 8); break;
+        case 4: lrc = launch(filter_groupby_tma_kernel<4, 1024, 16, false>, 4, 1024, 16); break;
+        default: lrc = plan.pack_tables ? launch(filter_groupby_tma_kernel<4, kGroupByTileRows, 8, true>, 4, kGroupByTileRows, 8)
+                                        : launch(filter_groupby_tma_kernel<4, kGroupByTileRows, 8, false>, 4, kGroupByTileRows, 8); break;
       }
       if (lrc) return lrc;
     } else {
@@ -1029,7 +1065,8 @@ int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred
     CU(c, cudaGetLastError());
   }
   groupby_pack_kernel<<<c->sm_count * 2, 256, 0, c->stream>>>(table, plan.count_f ? cnt_f : nullptr, span,
-                                                               static_cast<long long*>(d_i64), static_cast<double*>(d_f64));
+                                                               static_cast<long long*>(d_i64), static_cast<double*>(d_f64),
+                                                               plan.pack_shift, plan.pack_tables, plan.pack_bias);
   ++c->launches;
   CU(c, cudaGetLastError());
   unsigned long long h_oor = 0;

@@ -127,6 +127,49 @@ def test_groupby_matches_oracle(rows):
     assert int(got["count"].sum()) == int(sel.sum())
 
 
+@pytest.mark.parametrize("env", [{"SDBG_GROUPBY_PACKED": "0"}, {}, {"SDBG_GROUPBY_PACK_TABLES_MIN": "2"},
+                                 {"SDBG_GROUPBY_PACK_TABLES_MIN": "3"}])
+@pytest.mark.parametrize("sum_dtype", [np.int64, np.int32])
+def test_groupby_packed_accumulators(env, sum_dtype, monkeypatch):
+    """COUNT and SUM(int) sharing one RED word (stats-gated) must give the same result as separate
+    accumulators: negative values, several segments of ragged size, 1..3 words per slot."""
+    for k_, v_ in env.items():
+        monkeypatch.setenv(k_, v_)
+    rng = np.random.default_rng(17)
+    segs_o, segs_g = [], []
+    for rows in (70_001, 513, 1):
+        key = rng.integers(-7, 300, size=rows).astype(np.int64)
+        v = rng.integers(-1000, 1001, size=rows).astype(sum_dtype)
+        a = rng.integers(0, 100, size=rows).astype(np.int32)
+        w = rng.random(rows) * 1000.0
+        o = orc.Segment(rows, has_wand=False)
+        g = sdb.Segment(ctx(), rows)
+        for f, vals in {1: key, 2: v, 3: a, 4: w}.items():
+            o.add_column(f, vals)
+            g.stage_column(f, vals)
+        segs_o.append(o)
+        segs_g.append(g)
+    got = sdb.IResearchScan(segs_g).groupby([sdb.pred(3, "LT", 60)], 1, sum_int_field=2, avg_f64_field=4)
+    exp = orc.filter_groupby(segs_o, [orc.make_pred(3, "LT", 60)], 1, 2, 4, cap=1000)
+    for f in ("key", "count", "sum_lo", "sum_hi", "cnt_f64"):
+        assert np.array_equal(got[f], exp[f]), f
+    assert np.allclose(got["sum_f64"], exp["sum_f64"], rtol=1e-9)
+    # a constant column (range 0) and a column at the int32 extremes (range 2^32: too wide to pack at scale)
+    for lo, hi in ((5, 6), (-2**31, 2**31)):
+        rows = 4097
+        key = rng.integers(0, 50, size=rows).astype(np.int64)
+        v = rng.integers(lo, hi, size=rows).astype(np.int64)
+        o = orc.Segment(rows, has_wand=False)
+        g = sdb.Segment(ctx(), rows)
+        for f, vals in {1: key, 2: v}.items():
+            o.add_column(f, vals)
+            g.stage_column(f, vals)
+        got = sdb.IResearchScan([g]).groupby([], 1, sum_int_field=2)
+        exp = orc.filter_groupby([o], [], 1, 2, 999, cap=100)   # 999: no such column = no AVG
+        for f in ("key", "count", "sum_lo", "sum_hi"):
+            assert np.array_equal(got[f], exp[f]), (f, lo, hi)
+
+
 def test_groupby_nulls_and_multisegment():
     rows = 50_000
     rng = np.random.default_rng(9)
