@@ -310,18 +310,26 @@ filter_groupby_kernel(const GroupByParams P) {
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxStreams = 7;   // up to 4 predicate columns + key + sum_int + sum_f64 (deduplicated)
 
+// Everything the row loop needs is resolved on the host into plain scalars (direct constant-bank operands):
+// no stream indirection, no per-row type switch over parameter arrays.
 struct TmaGroupByParams {
   const void* src[kMaxStreams];   // distinct referenced columns
   int32_t elem[kMaxStreams];      // 8 (int64 / float64) or 4 (int32)
-  int32_t type[kMaxStreams];      // 0 i64, 1 f64, 2 i32
+  uint32_t off[kMaxStreams + 1];  // byte offset of each stream inside a stage; off[n_streams] = stage bytes
   int32_t n_streams;
   int32_t n_preds;
-  int32_t pred_stream[kMaxPreds];
-  int32_t pred_negate[kMaxPreds];   // 1: pass = !(lo <= v <= hi)   (SQL <>)
-  // every comparison is normalised on the host to a closed range lo <= v <= hi (empty when lo > hi)
-  int64_t pred_lo_i[kMaxPreds], pred_hi_i[kMaxPreds];
-  double pred_lo_f[kMaxPreds], pred_hi_f[kMaxPreds];
-  int32_t key_stream, sum_i_stream, sum_f_stream;   // -1 when absent
+  // Predicate i: pass = ((key(v) - pred_lo) <=u pred_span) != pred_negate, where key() maps the column type
+  // onto int64 order: integers as they are, doubles through fkey() below. The host normalises every
+  // comparison to a closed range in that key space and removes predicates that are always true / aborts
+  // on ones that are always false, so lo <= lo + span always holds here.
+  uint32_t pred_off[kMaxPreds];
+  int32_t pred_type[kMaxPreds];     // 0 i64, 1 f64, 2 i32
+  int32_t pred_negate[kMaxPreds];   // 1: SQL <>
+  int64_t pred_lo[kMaxPreds];
+  uint64_t pred_span[kMaxPreds];
+  uint32_t key_off, sum_i_off, sum_f_off;
+  int32_t key_type, sum_i_type;     // 0 i64, 2 i32
+  int32_t has_sum_i, has_sum_f;
   int32_t wide_int;
   int32_t debug_skip;   // timing experiments only (SDBG_GROUPBY_DEBUG): bits 1/2/4 drop the count / sum_int / sum_f64 RED
   // Packed accumulators (kPacked kernels): COUNT and SUM(int) share one 64-bit word, count << pack_shift |
@@ -330,12 +338,23 @@ struct TmaGroupByParams {
   // (1..3) words of the slot by tile index when one word would not be enough.
   int32_t pack_shift, pack_tables;
   int64_t pack_bias;
+  // Fixed-point SUM(double) (kFix kernels): a 64-bit floating-point RED costs several integer ones in L2,
+  // so |w| / 2^fix_eunit is truncated to a 2*fix_limb-bit integer and its two limbs are added with integer
+  // REDs into words 2 and 3 of the slot. The host picks fix_eunit from the column's largest magnitude so
+  // that nothing overflows; the sum is exact to 2^-(2*fix_limb) of that magnitude and independent of the
+  // order of the updates. Columns with NaN / infinities keep the floating-point RED.
+  int32_t fix_limb, fix_eunit;
   int64_t key_min;
   uint64_t key_span;
   uint64_t rows;
   GroupSlot* table;
   unsigned long long* out_of_range;
 };
+
+// Order-preserving map from the bits of a double to int64 (negative doubles reversed). -0.0 maps just
+// below +0.0 (the host widens range ends that are zeros accordingly); NaNs land beyond +-inf, outside
+// every closed range, which is the SQL comparison result.
+__host__ __device__ __forceinline__ long long fkey(long long bits) { return bits ^ ((bits >> 63) & 0x7FFFFFFFFFFFFFFFll); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -360,23 +379,68 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <int kStages, int kTileRows, int kConsumerWarps, bool kPacked>
+// |w| / 2^eunit truncated to an integer below 2^(2*limb), split into two limbs carrying w's sign.
+// Requires |w| < 2^(eunit + 2*limb) and w finite (the host checks both against the column statistics).
+__device__ __forceinline__ void fix_limbs(double w, int limb, int eunit, long long& l0, long long& l1) {
+  const long long bits = __double_as_longlong(w);
+  const int ex = int((bits >> 52) & 0x7FF);
+  unsigned long long mant = static_cast<unsigned long long>(bits) & 0xFFFFFFFFFFFFFull;
+  if (ex) mant |= 1ull << 52;
+  const int s = (ex ? ex : 1) - 1075 - eunit;          // |w| = mant * 2^(s + eunit); s <= 2*limb - 53 <= 21
+  unsigned long long lo, hi = 0ull;
+  if (s >= 0) { lo = mant << s; if (s) hi = mant >> (64 - s); }
+  else lo = s > -64 ? mant >> (-s) : 0ull;
+  l0 = static_cast<long long>(lo & ((1ull << limb) - 1ull));
+  l1 = static_cast<long long>((lo >> limb) | (hi << (64 - limb)));
+  if (bits < 0) { l0 = -l0; l1 = -l1; }
+}
+// (s1 * 2^limb + s0) * 2^eunit as a double; the 128-bit integer is formed exactly, then rounded.
+__host__ __device__ __forceinline__ double fix_total(long long s0, long long s1, int limb, int eunit) {
+  long long hi = s1 >> (64 - limb);
+  unsigned long long lo = static_cast<unsigned long long>(s1) << limb;
+  const unsigned long long lo2 = lo + static_cast<unsigned long long>(s0);
+  hi += (s0 >> 63) + (lo2 < lo ? 1 : 0);
+  lo = lo2;
+  const bool neg = hi < 0;
+  if (neg) { lo = ~lo + 1ull; hi = ~hi + (lo == 0ull ? 1 : 0); }
+  const double mag = static_cast<double>(static_cast<unsigned long long>(hi)) * 18446744073709551616.0 + static_cast<double>(lo);
+  return scalbn(neg ? -mag : mag, eunit);
+}
+
+// Rows r, r+1 (r even) of a staged column as int64 values: one 16-byte (int32: 8-byte) shared load.
+// kType: 0 i64, 1 f64 (raw bits), 2 i32 (sign-extended).
+template <int kType>
+__device__ __forceinline__ void load2(const unsigned char* col, uint32_t r, long long (&v)[2]) {
+  if (kType == 2) {
+    const int2 x = *reinterpret_cast<const int2*>(col + size_t(r) * 4u);
+    v[0] = x.x; v[1] = x.y;
+  } else {
+    const longlong2 x = *reinterpret_cast<const longlong2*>(col + size_t(r) * 8u);
+    v[0] = x.x; v[1] = x.y;
+  }
+}
+// Bit j: row r + j lies in the closed key-space range [lo, lo + span].
+template <int kType>
+__device__ __forceinline__ uint32_t range2(const unsigned char* col, uint32_t r, long long lo, unsigned long long span) {
+  long long v[2];
+  load2<kType>(col, r, v);
+  if (kType == 1) { v[0] = fkey(v[0]); v[1] = fkey(v[1]); }
+  return (static_cast<unsigned long long>(v[0] - lo) <= span ? 1u : 0u) | (static_cast<unsigned long long>(v[1] - lo) <= span ? 2u : 0u);
+}
+
+template <int kStages, int kTileRows, int kConsumerWarps, bool kPacked, bool kFix>
 __global__ void __launch_bounds__((kConsumerWarps + 1) * 32)
 filter_groupby_tma_kernel(const TmaGroupByParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages];
-  __shared__ uint32_t s_off[kMaxStreams + 1];   // byte offset of each stream inside a stage
 
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
   if (tid == 0) {
-    uint32_t o = 0;
-    for (int s = 0; s < P.n_streams; ++s) { s_off[s] = o; o += uint32_t(P.elem[s]) * kTileRows; }
-    s_off[P.n_streams] = o;
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1u); mbar_init(&empty_bar[s], kConsumerWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const uint32_t stage_bytes = s_off[P.n_streams];
+  const uint32_t stage_bytes = P.off[P.n_streams];
   const uint64_t n_tiles = (P.rows + kTileRows - 1) / kTileRows;
 
   if (warp == kConsumerWarps) {
@@ -394,7 +458,7 @@ filter_groupby_tma_kernel(const TmaGroupByParams P) {
         unsigned char* dst = smem + size_t(st) * stage_bytes;
         for (int s = 0; s < P.n_streams; ++s) {
           const uint32_t bytes = (nrows * uint32_t(P.elem[s]) + 15u) & ~15u;   // columns carry >= 64 B of slack
-          bulk_g2s(dst + s_off[s], static_cast<const char*>(P.src[s]) + row0 * uint64_t(P.elem[s]), bytes, &full_bar[st]);
+          bulk_g2s(dst + P.off[s], static_cast<const char*>(P.src[s]) + row0 * uint64_t(P.elem[s]), bytes, &full_bar[st]);
         }
       }
     }
@@ -402,6 +466,9 @@ filter_groupby_tma_kernel(const TmaGroupByParams P) {
   }
 
   // ===== consumers =====
+  // Each lane owns two consecutive rows of a 64-row strip, so every staged column is read with one
+  // 16-byte (8-byte for int32) shared load per lane and the column type is a warp-uniform switch
+  // outside the per-row work.
   uint32_t it = 0;
   for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
     const uint32_t st = it % kStages, use = it / kStages;
@@ -409,58 +476,64 @@ filter_groupby_tma_kernel(const TmaGroupByParams P) {
     const unsigned char* base = smem + size_t(st) * stage_bytes;
     const uint64_t row0 = tile * kTileRows;
     const uint32_t nrows = uint32_t(min(static_cast<unsigned long long>(kTileRows), static_cast<unsigned long long>(P.rows - row0)));
-    const uint32_t pack_word = kPacked ? uint32_t(tile % uint64_t(P.pack_tables)) : 0u;   // words 0..2 of the slot: count / sum_lo / sum_hi
-    // One row per lane; predicates are branch-free closed-range tests on the staged tile; a passing row
-    // issues its REDs (fire-and-forget) into the L2-resident group table.
-#pragma unroll 2
-    for (uint32_t r = tid; r < nrows; r += kConsumerWarps * 32u) {
-      bool pass = true;
+    const uint32_t pack_word = kPacked ? uint32_t(tile % uint64_t(P.pack_tables)) : 0u;   // words 0..2 of a slot: count / sum_lo / sum_hi
+    for (uint32_t r = warp * 64u + 2u * lane; r < nrows; r += kConsumerWarps * 64u) {
+      uint32_t m = r + 1u < nrows ? 3u : 1u;   // bit j: row r + j exists and still passes
 #pragma unroll
       for (int i = 0; i < kMaxPreds; ++i) {
         if (i < P.n_preds) {
-          const int s = P.pred_stream[i];
-          const unsigned char* col = base + s_off[s];
-          bool in;
-          if (P.type[s] == 1) {
-            const double v = reinterpret_cast<const double*>(col)[r];
-            in = (v >= P.pred_lo_f[i]) & (v <= P.pred_hi_f[i]);
-          } else {
-            const long long v = P.type[s] == 2 ? static_cast<long long>(reinterpret_cast<const int*>(col)[r])
-                                               : reinterpret_cast<const long long*>(col)[r];
-            in = (v >= P.pred_lo_i[i]) & (v <= P.pred_hi_i[i]);
+          const unsigned char* col = base + P.pred_off[i];
+          uint32_t in;
+          switch (P.pred_type[i]) {
+            case 0: in = range2<0>(col, r, P.pred_lo[i], P.pred_span[i]); break;
+            case 1: in = range2<1>(col, r, P.pred_lo[i], P.pred_span[i]); break;
+            default: in = range2<2>(col, r, P.pred_lo[i], P.pred_span[i]); break;
           }
-          pass &= in != (P.pred_negate[i] != 0);
+          m &= P.pred_negate[i] ? ~in : in;
         }
       }
-      if (!pass) continue;
-      const unsigned char* kc = base + s_off[P.key_stream];
-      const long long key = P.type[P.key_stream] == 2 ? static_cast<long long>(reinterpret_cast<const int*>(kc)[r])
-                                                      : reinterpret_cast<const long long*>(kc)[r];
-      const unsigned long long idx = static_cast<unsigned long long>(key - P.key_min);
-      if (idx >= P.key_span) { atomicAdd(P.out_of_range, 1ull); continue; }
-      GroupSlot* g = P.table + idx;
-      if (kPacked) {
-        const unsigned char* vc = base + s_off[P.sum_i_stream];
-        const long long v = P.type[P.sum_i_stream] == 2 ? static_cast<long long>(reinterpret_cast<const int*>(vc)[r])
-                                                        : reinterpret_cast<const long long*>(vc)[r];
-        if (!(P.debug_skip & 3))
-          atomicAdd(reinterpret_cast<unsigned long long*>(g) + pack_word,
-                    (1ull << P.pack_shift) + static_cast<unsigned long long>(v - P.pack_bias));
-      } else {
-      if (!(P.debug_skip & 1)) atomicAdd(&g->count, 1ull);
-      if (P.sum_i_stream >= 0 && !(P.debug_skip & 2)) {
-        const unsigned char* vc = base + s_off[P.sum_i_stream];
-        const long long v = P.type[P.sum_i_stream] == 2 ? static_cast<long long>(reinterpret_cast<const int*>(vc)[r])
-                                                        : reinterpret_cast<const long long*>(vc)[r];
-        if (P.wide_int) {
-          atomicAdd(reinterpret_cast<unsigned long long*>(&g->sum_lo), static_cast<unsigned long long>(v) & 0xFFFFFFFFull);
-          atomicAdd(reinterpret_cast<unsigned long long*>(&g->sum_hi), static_cast<unsigned long long>(v >> 32));
+      if (m == 0u) continue;
+      long long key[2], v[2] = {0, 0};
+      double w[2] = {0.0, 0.0};
+      if (P.key_type == 2) load2<2>(base + P.key_off, r, key); else load2<0>(base + P.key_off, r, key);
+      if (kPacked || P.has_sum_i) {
+        if (P.sum_i_type == 2) load2<2>(base + P.sum_i_off, r, v); else load2<0>(base + P.sum_i_off, r, v);
+      }
+      if (kFix || P.has_sum_f) {
+        const double2 x = *reinterpret_cast<const double2*>(base + P.sum_f_off + size_t(r) * 8u);
+        w[0] = x.x; w[1] = x.y;
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (!(m & (1u << j))) continue;
+        // a passing row issues its REDs (fire-and-forget) into the L2-resident group table
+        const unsigned long long idx = static_cast<unsigned long long>(key[j] - P.key_min);
+        if (idx >= P.key_span) { atomicAdd(P.out_of_range, 1ull); continue; }
+        unsigned long long* g = reinterpret_cast<unsigned long long*>(P.table + idx);   // words: count, sum_lo, sum_hi, sum_f
+        if (kPacked) {
+          if (!(P.debug_skip & 3)) atomicAdd(g + pack_word, (1ull << P.pack_shift) + static_cast<unsigned long long>(v[j] - P.pack_bias));
         } else {
-          atomicAdd(reinterpret_cast<unsigned long long*>(&g->sum_lo), static_cast<unsigned long long>(v));
+          if (!(P.debug_skip & 1)) atomicAdd(g, 1ull);
+          if (P.has_sum_i && !(P.debug_skip & 2)) {
+            if (P.wide_int) {
+              atomicAdd(g + 1, static_cast<unsigned long long>(v[j]) & 0xFFFFFFFFull);
+              atomicAdd(g + 2, static_cast<unsigned long long>(v[j] >> 32));
+            } else {
+              atomicAdd(g + 1, static_cast<unsigned long long>(v[j]));
+            }
+          }
+        }
+        if (kFix) {
+          long long l0, l1;
+          fix_limbs(w[j], P.fix_limb, P.fix_eunit, l0, l1);
+          if (!(P.debug_skip & 4)) {
+            atomicAdd(g + 2, static_cast<unsigned long long>(l0));
+            atomicAdd(g + 3, static_cast<unsigned long long>(l1));
+          }
+        } else if (P.has_sum_f && !(P.debug_skip & 4)) {
+          atomicAdd(reinterpret_cast<double*>(g + 3), w[j]);
         }
       }
-      }
-      if (P.sum_f_stream >= 0 && !(P.debug_skip & 4)) atomicAdd(&g->sum_f, reinterpret_cast<const double*>(base + s_off[P.sum_f_stream])[r]);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[st]);   // this warp is done reading the stage
@@ -555,11 +628,17 @@ filter_groupby_hash_kernel(const HashGroupByParams P) {
 __global__ void __launch_bounds__(256)
 groupby_pack_kernel(const GroupSlot* __restrict__ table, const unsigned long long* __restrict__ cnt_f,
                     uint64_t span, long long* __restrict__ d_i64, double* __restrict__ d_f64,
-                    int pack_shift, int pack_tables, long long pack_bias) {
+                    int pack_shift, int pack_tables, long long pack_bias, int fix_limb, int fix_eunit) {
   for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < span; i += uint64_t(gridDim.x) * blockDim.x) {
     GroupSlot g = table[i];
+    if (fix_limb) {     // fixed-point SUM(double): words 2, 3 hold the two limb sums (so at most two packed words)
+      const long long s0 = g.sum_hi;
+      long long s1; memcpy(&s1, &g.sum_f, 8);
+      g.sum_f = fix_total(s0, s1, fix_limb, fix_eunit);
+      g.sum_hi = 0;
+    }
     if (pack_tables) {  // packed accumulators: split count << shift | sum(v - bias) back into the plain fields
-      const unsigned long long w[3] = {g.count, static_cast<unsigned long long>(g.sum_lo), static_cast<unsigned long long>(g.sum_hi)};
+      const unsigned long long w[3] = {g.count, static_cast<unsigned long long>(g.sum_lo), static_cast<unsigned long long>(g.sum_hi)};   // sum_hi is 0 in fix mode
       const unsigned long long mask = (1ull << pack_shift) - 1ull;
       unsigned long long cnt = 0, sum = 0;
       for (int t = 0; t < pack_tables; ++t) { cnt += w[t] >> pack_shift; sum += w[t] & mask; }
@@ -639,6 +718,20 @@ minmax_i64_kernel(const ColDev col, uint64_t rows, long long* __restrict__ out /
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(kFull, mn, o)); mx = max(mx, __shfl_xor_sync(kFull, mx, o)); }
   if ((threadIdx.x & 31u) == 0) { atomicMin(out, mn); atomicMax(out + 1, mx); }
+}
+
+// Largest |w| of a double column as raw bits (non-negative doubles order like their bit patterns; any
+// NaN or infinity yields a value >= 0x7FF0000000000000).
+__global__ void __launch_bounds__(256)
+absmax_f64_kernel(const ColDev col, uint64_t rows, unsigned long long* __restrict__ out) {
+  unsigned long long mx = 0ull;
+  for (uint64_t r = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < rows; r += uint64_t(gridDim.x) * blockDim.x) {
+    if (!col_valid(col, r)) continue;
+    mx = max(mx, static_cast<const unsigned long long*>(col.values)[r] & 0x7FFFFFFFFFFFFFFFull);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(kFull, mx, o));
+  if ((threadIdx.x & 31u) == 0) atomicMax(out, mx);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -41,6 +41,8 @@ struct ColumnObj {
   bool owned = true;
   bool has_minmax = false;
   int64_t mn = 0, mx = 0;
+  bool has_absmax = false;      // double columns: bits of the largest |value| (>= 0x7FF0... when NaN / inf occur)
+  uint64_t absmax_bits = 0;
 };
 
 }  // namespace
@@ -361,7 +363,7 @@ extern "C" int sdbg_stage_column(sdbg_segment* s, uint64_t field, sdbg_type t, c
     CU(c, cudaMalloc(&col.d_values, bytes + 64));  // slack: row pairs are loaded as one 16-byte vector
     CU(c, cudaMemsetAsync(static_cast<char*>(col.d_values) + bytes, 0, 64, c->stream));
   }
-  col.type = t; col.rows = rows; col.owned = true; col.has_minmax = false;
+  col.type = t; col.rows = rows; col.owned = true; col.has_minmax = false; col.has_absmax = false;
   CU(c, cudaMemcpyAsync(col.d_values, values, bytes, cudaMemcpyHostToDevice, c->stream));
   if (validity) {
     const size_t vb = ((rows + 63) / 64) * 8;
@@ -824,6 +826,30 @@ int column_minmax(sdbg_segment* s, uint64_t field, int64_t* mn, int64_t* mx) {
   return SDBG_OK;
 }
 
+// Largest magnitude of a double column (raw bits), computed once per column like the integer min/max.
+int column_absmax(sdbg_segment* s, uint64_t field, uint64_t* bits) {
+  sdbg_ctx* c = s->ctx;
+  auto it = s->cols.find(field);
+  if (it == s->cols.end()) return fail(c, SDBG_ENOTFOUND, "column not staged");
+  ColumnObj& col = it->second;
+  if (col.type != SDBG_F64) return fail(c, SDBG_EINVAL, "absmax statistics are kept for double columns");
+  if (!col.has_absmax) {
+    int rc;
+    if ((rc = ensure(c, c->scratch[10], 16))) return rc;
+    CU(c, cudaMemsetAsync(c->scratch[10].p, 0, 16, c->stream));
+    ColDev cd; cd.values = col.d_values; cd.validity = col.d_validity; cd.type = col.type; cd.pad = 0;
+    absmax_f64_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(cd, col.rows, static_cast<unsigned long long*>(c->scratch[10].p));
+    ++c->launches;
+    CU(c, cudaGetLastError());
+    unsigned long long res = 0;
+    CU(c, cudaMemcpyAsync(&res, c->scratch[10].p, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    col.absmax_bits = res; col.has_absmax = true;
+  }
+  *bits = col.absmax_bits;
+  return SDBG_OK;
+}
+
 }  // namespace
 
 extern "C" int sdbg_column_minmax_i64(sdbg_segment* s, uint64_t field, int64_t* mn, int64_t* mx) {
@@ -896,7 +922,7 @@ extern "C" int sdbg_filter_count_sum(sdbg_segment* const* segs, size_t n_segs, c
 
 namespace {
 
-struct GroupPlan { int wide_int = 0; int count_f = 0; int pack_shift = 0; int pack_tables = 0; int64_t pack_bias = 0; };
+struct GroupPlan { int wide_int = 0; int count_f = 0; int pack_shift = 0; int pack_tables = 0; int64_t pack_bias = 0; int fix_limb = 0; int fix_eunit = 0; };
 constexpr int kGroupByTileRows = 512;   // tile of the default TMA shape; packed accumulators are only planned for it
 
 int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred* preds, size_t n_preds, uint64_t key_field,
@@ -914,6 +940,7 @@ int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred
   GroupPlan plan;
   uint64_t total_rows = 0;
   int64_t sum_mn = INT64_MAX, sum_mx = INT64_MIN;
+  uint64_t absmax_bits = 0;
   bool all_tma = env_int("SDBG_GROUPBY_TMA", 1) != 0 && env_int("SDBG_GROUPBY_TMA_SHAPE", 0) == 0;
   for (size_t si = 0; si < n_segs; ++si) {  // statistics decide the accumulator shape
     sdbg_segment* s = segs[si];
@@ -933,6 +960,9 @@ int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred
       auto it = s->cols.find(avg_f64_field);
       if (it == s->cols.end()) return fail(c, SDBG_ENOTFOUND, "avg column not staged");
       if (it->second.d_validity) { plan.count_f = 1; all_tma = false; }
+      uint64_t ab = 0;
+      if (it->second.type == SDBG_F64 && all_tma) { if ((rc = column_absmax(s, avg_f64_field, &ab))) return rc; }
+      absmax_bits = std::max(absmax_bits, ab);
     }
     auto kit = s->cols.find(key_field);
     if (kit == s->cols.end()) return fail(c, SDBG_ENOTFOUND, "key column not staged");
@@ -946,7 +976,8 @@ int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred
   // consumer warps run into). Rows are dealt to 1..3 words of the slot by tile index.
   if (sum_int_field != UINT64_MAX && !plan.wide_int && all_tma && total_rows && sum_mx >= sum_mn && env_int("SDBG_GROUPBY_PACKED", 1)) {
     const unsigned __int128 range = static_cast<unsigned __int128>(static_cast<uint64_t>(sum_mx) - static_cast<uint64_t>(sum_mn));
-    for (int nt = std::max(1, env_int("SDBG_GROUPBY_PACK_TABLES_MIN", 1)); nt <= 3 && !plan.pack_tables; ++nt) {   // env: test hook
+    const int max_tables = avg_f64_field != UINT64_MAX ? 2 : 3;   // words 2, 3 are kept free for the fixed-point SUM(double) limbs
+    for (int nt = std::max(1, env_int("SDBG_GROUPBY_PACK_TABLES_MIN", 1)); nt <= max_tables && !plan.pack_tables; ++nt) {   // env: test hook
       uint64_t cap_rows = 0;   // most rows any one word can receive: its share of every segment's tiles
       for (size_t si = 0; si < n_segs; ++si) {
         const uint64_t tiles = (segs[si]->cols.find(key_field)->second.rows + kGroupByTileRows - 1) / kGroupByTileRows;
@@ -957,6 +988,18 @@ int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred
       while (shift < 63 && (static_cast<unsigned __int128>(1) << shift) <= max_sum) ++shift;
       if (shift < 63 && cap_rows < (1ull << (64 - shift))) { plan.pack_tables = nt; plan.pack_shift = shift; plan.pack_bias = sum_mn; }
     }
+  }
+  // Fixed-point SUM(double): two integer limb REDs instead of one floating-point RED (see TmaGroupByParams).
+  // Needs words 2 and 3 of the slot (no wide integer sum, at most two packed words) and a finite column.
+  if (avg_f64_field != UINT64_MAX && all_tma && !plan.wide_int && total_rows && absmax_bits < 0x7FF0000000000000ull &&
+      env_int("SDBG_GROUPBY_FIXED", 0)) {   // opt-in: bit-reproducible sums, but two integer REDs measure slower than one f64 RED
+    int row_bits = 1;
+    while ((1ull << row_bits) <= total_rows) ++row_bits;
+    plan.fix_limb = std::min(37, 63 - row_bits);                     // |limb sum| <= rows * 2^limb < 2^63
+    double mx; std::memcpy(&mx, &absmax_bits, 8);
+    int e = 0;
+    if (mx > 0) std::frexp(mx, &e);                                  // mx < 2^e
+    plan.fix_eunit = e - 2 * plan.fix_limb;                          // |w| / 2^eunit < 2^(2*limb)
   }
   for (size_t si = 0; si < n_segs; ++si) {
     sdbg_segment* s = segs[si];
@@ -991,16 +1034,20 @@ int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred
       std::memset(&T, 0, sizeof T);
       auto stream_of = [&](const ColDev& col) {
         for (int i = 0; i < T.n_streams; ++i) if (T.src[i] == col.values) return i;
-        T.src[T.n_streams] = col.values; T.type[T.n_streams] = col.type; T.elem[T.n_streams] = col.type == SDBG_I32 ? 4 : 8;
+        T.src[T.n_streams] = col.values; T.elem[T.n_streams] = col.type == SDBG_I32 ? 4 : 8;
         return T.n_streams++;
       };
-      T.n_preds = P.ps.n;
+      // Every comparison becomes a closed range [lo, lo + span] in an int64 key space (integers as they
+      // are, doubles through fkey()): exact, because integers step by 1 and doubles by one ulp. Predicates
+      // that hold for every row are dropped; one that holds for none makes the segment contribute nothing.
+      bool never = false;
+      int stream_idx[kMaxPreds];
+      T.n_preds = 0;
       for (int i = 0; i < P.ps.n; ++i) {
         const PredDev& pd = P.ps.p[i];
-        T.pred_stream[i] = stream_of(pd.col);
-        // normalise the comparison to a closed range (exact: integers step by 1, doubles by one ulp)
-        int64_t li = INT64_MIN, hi_ = INT64_MAX; double lf = -HUGE_VAL, hf = HUGE_VAL; int neg = 0; bool empty = false;
+        int64_t lo, hi; int neg = 0; bool empty = false;
         if (pd.col.type == SDBG_F64) {
+          double lf = -HUGE_VAL, hf = HUGE_VAL;
           const double x = pd.lo_f;
           if (std::isnan(x) || (pd.op == SDBG_OP_BETWEEN && std::isnan(pd.hi_f))) empty = true;   // comparisons with NaN are false
           switch (pd.op) {
@@ -1009,11 +1056,19 @@ int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred
             case SDBG_OP_GT: if (x == HUGE_VAL) empty = true; else lf = std::nextafter(x, HUGE_VAL); break;
             case SDBG_OP_GE: lf = x; break;
             case SDBG_OP_EQ: lf = hf = x; break;
-            case SDBG_OP_NE: lf = hf = x; neg = 1; if (std::isnan(x)) { empty = false; lf = 1; hf = 0; } break;  // v <> NaN is true
+            case SDBG_OP_NE: lf = hf = x; neg = 1; break;
             default: lf = x; hf = pd.hi_f; break;
           }
-          if (empty) { lf = 1; hf = 0; neg = 0; }
+          if (pd.op == SDBG_OP_NE && std::isnan(x)) continue;      // v <> NaN holds for every row
+          if (!empty && lf > hf) empty = true;
+          if (!empty) {
+            if (lf == 0.0) lf = -0.0;                               // -0.0 == +0.0: the range must cover both keys
+            if (hf == 0.0) hf = 0.0;
+            int64_t bl, bh; std::memcpy(&bl, &lf, 8); std::memcpy(&bh, &hf, 8);
+            lo = fkey(bl); hi = fkey(bh);
+          }
         } else {
+          int64_t li = INT64_MIN, hi_ = INT64_MAX;
           const int64_t x = pd.lo_i;
           switch (pd.op) {
             case SDBG_OP_LT: if (x == INT64_MIN) empty = true; else hi_ = x - 1; break;
@@ -1024,19 +1079,38 @@ int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred
             case SDBG_OP_NE: li = hi_ = x; neg = 1; break;
             default: li = x; hi_ = pd.hi_i; break;
           }
-          if (empty) { li = 1; hi_ = 0; }
+          if (li > hi_) empty = true;
+          lo = li; hi = hi_;
         }
-        T.pred_lo_i[i] = li; T.pred_hi_i[i] = hi_; T.pred_lo_f[i] = lf; T.pred_hi_f[i] = hf; T.pred_negate[i] = neg;
+        if (empty) { if (neg) continue; never = true; break; }
+        const int k = T.n_preds++;
+        stream_idx[k] = stream_of(pd.col);
+        T.pred_type[k] = pd.col.type; T.pred_negate[k] = neg;
+        T.pred_lo[k] = lo; T.pred_span[k] = static_cast<uint64_t>(hi) - static_cast<uint64_t>(lo);
       }
-      T.key_stream = stream_of(P.key);
-      T.sum_i_stream = P.has_sum_i ? stream_of(P.sum_i) : -1;
-      T.sum_f_stream = P.has_sum_f ? stream_of(P.sum_f) : -1;
+      if (never) continue;   // WHERE is false for every row of this segment
+      const int key_s = stream_of(P.key);
+      const int sum_i_s = P.has_sum_i ? stream_of(P.sum_i) : -1;
+      const int sum_f_s = P.has_sum_f ? stream_of(P.sum_f) : -1;
+      T.key_type = P.key.type; T.sum_i_type = P.has_sum_i ? P.sum_i.type : 0;
+      T.has_sum_i = P.has_sum_i; T.has_sum_f = P.has_sum_f;
       T.debug_skip = env_int("SDBG_GROUPBY_DEBUG", 0);
       T.wide_int = plan.wide_int; T.key_min = key_min; T.key_span = span; T.rows = rows; T.table = table; T.out_of_range = oor;
       T.pack_shift = plan.pack_shift; T.pack_tables = plan.pack_tables; T.pack_bias = plan.pack_bias;
+      T.fix_limb = plan.fix_limb; T.fix_eunit = plan.fix_eunit;
+      auto set_offsets = [&](int tile_rows) {   // stream offsets inside a stage depend on the tile shape
+        uint32_t o = 0;
+        for (int i = 0; i < T.n_streams; ++i) { T.off[i] = o; o += uint32_t(T.elem[i]) * uint32_t(tile_rows); }
+        T.off[T.n_streams] = o;
+        for (int i = 0; i < T.n_preds; ++i) T.pred_off[i] = T.off[stream_idx[i]];
+        T.key_off = T.off[key_s];
+        T.sum_i_off = sum_i_s >= 0 ? T.off[sum_i_s] : 0;
+        T.sum_f_off = sum_f_s >= 0 ? T.off[sum_f_s] : 0;
+      };
       const int shape = env_int("SDBG_GROUPBY_TMA_SHAPE", 0);
       auto launch = [&](auto kern, int stages, int tile_rows, int consumer_warps) -> int {
-        const size_t smem = size_t(stages) * size_t(tile_rows) * 8 * size_t(T.n_streams);
+        set_offsets(tile_rows);
+        const size_t smem = size_t(stages) * size_t(T.off[T.n_streams]);
         CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         const size_t fit = std::max<size_t>(1, (220 * 1024) / (smem + 2048));
         const size_t by_threads = std::max<size_t>(1, 2048 / (size_t(consumer_warps + 1) * 32));
@@ -1048,12 +1122,16 @@ int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred
       };
       int lrc;
       switch (shape) {
-        case 1: lrc = launch(filter_groupby_tma_kernel<4, 256, 8, false>, 4, 256, 8); break;
-        case 2: lrc = launch(filter_groupby_tma_kernel<4, 512, 16, false>, 4, 512, 16); break;
-        case 3: lrc = launch(filter_groupby_tma_kernel<3, 256, 8, false>, 3, 256, 8); break;
-        case 4: lrc = launch(filter_groupby_tma_kernel<4, 1024, 16, false>, 4, 1024, 16); break;
-        default: lrc = plan.pack_tables ? launch(filter_groupby_tma_kernel<4, kGroupByTileRows, 8, true>, 4, kGroupByTileRows, 8)
-                                        : launch(filter_groupby_tma_kernel<4, kGroupByTileRows, 8, false>, 4, kGroupByTileRows, 8); break;
+        case 1: lrc = launch(filter_groupby_tma_kernel<4, 256, 8, false, false>, 4, 256, 8); break;
+        case 2: lrc = launch(filter_groupby_tma_kernel<4, 512, 16, false, false>, 4, 512, 16); break;
+        case 3: lrc = launch(filter_groupby_tma_kernel<3, 256, 8, false, false>, 3, 256, 8); break;
+        case 4: lrc = launch(filter_groupby_tma_kernel<4, 1024, 16, false, false>, 4, 1024, 16); break;
+        default:
+          if (plan.pack_tables) lrc = plan.fix_limb ? launch(filter_groupby_tma_kernel<4, kGroupByTileRows, 8, true, true>, 4, kGroupByTileRows, 8)
+                                                    : launch(filter_groupby_tma_kernel<4, kGroupByTileRows, 8, true, false>, 4, kGroupByTileRows, 8);
+          else lrc = plan.fix_limb ? launch(filter_groupby_tma_kernel<4, kGroupByTileRows, 8, false, true>, 4, kGroupByTileRows, 8)
+                                   : launch(filter_groupby_tma_kernel<4, kGroupByTileRows, 8, false, false>, 4, kGroupByTileRows, 8);
+          break;
       }
       if (lrc) return lrc;
     } else {
@@ -1066,7 +1144,7 @@ int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred
   }
   groupby_pack_kernel<<<c->sm_count * 2, 256, 0, c->stream>>>(table, plan.count_f ? cnt_f : nullptr, span,
                                                                static_cast<long long*>(d_i64), static_cast<double*>(d_f64),
-                                                               plan.pack_shift, plan.pack_tables, plan.pack_bias);
+                                                               plan.pack_shift, plan.pack_tables, plan.pack_bias, plan.fix_limb, plan.fix_eunit);
   ++c->launches;
   CU(c, cudaGetLastError());
   unsigned long long h_oor = 0;

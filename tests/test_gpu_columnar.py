@@ -170,6 +170,53 @@ def test_groupby_packed_accumulators(env, sum_dtype, monkeypatch):
             assert np.array_equal(got[f], exp[f]), (f, lo, hi)
 
 
+@pytest.mark.parametrize("case", ["mixed", "tiny", "nonfinite", "zeros"])
+@pytest.mark.parametrize("with_int_sum", [True, False])
+@pytest.mark.parametrize("fixed", ["1", "0"])
+def test_groupby_fixed_point_double_sum(case, with_int_sum, fixed, monkeypatch):
+    """SUM(double) accumulated as two integer limbs (stats-gated) against the oracle's double sum:
+    negative values, 60 binades of dynamic range, denormals, and the NaN / inf fallback. The integer
+    path is also order-independent, so two runs must agree to the bit."""
+    monkeypatch.setenv("SDBG_GROUPBY_FIXED", fixed)
+    rng = np.random.default_rng(23)
+    rows = 40_003
+    key = rng.integers(0, 97, size=rows).astype(np.int64)
+    v = rng.integers(-1000, 1001, size=rows).astype(np.int64)
+    if case == "mixed":
+        w = rng.standard_normal(rows) * np.exp2(rng.integers(-30, 30, size=rows).astype(np.float64))
+    elif case == "tiny":
+        w = rng.standard_normal(rows) * 5e-324 * 1000       # denormals
+    elif case == "zeros":
+        w = np.zeros(rows)
+    else:
+        w = rng.standard_normal(rows)
+        w[5] = np.inf; w[77] = np.nan; w[78] = -np.inf
+    o = orc.Segment(rows, has_wand=False)
+    g = sdb.Segment(ctx(), rows)
+    for f, vals in {1: key, 2: v, 4: w}.items():
+        o.add_column(f, vals)
+        g.stage_column(f, vals)
+    si = 2 if with_int_sum else None
+    got = sdb.IResearchScan([g]).groupby([sdb.pred(2, "GE", -900)], 1, sum_int_field=si, avg_f64_field=4).copy()
+    again = sdb.IResearchScan([g]).groupby([sdb.pred(2, "GE", -900)], 1, sum_int_field=si, avg_f64_field=4)
+    exp = orc.filter_groupby([o], [orc.make_pred(2, "GE", -900)], 1, 2 if with_int_sum else 999, 4, cap=1000)
+    for f in ("key", "count", "sum_lo", "sum_hi", "cnt_f64"):
+        assert np.array_equal(got[f], exp[f]), f
+    if case == "nonfinite":
+        assert np.array_equal(np.isnan(got["sum_f64"]), np.isnan(exp["sum_f64"]))
+        fin = np.isfinite(exp["sum_f64"])
+        assert np.array_equal(got["sum_f64"][~fin & ~np.isnan(exp["sum_f64"])], exp["sum_f64"][~fin & ~np.isnan(exp["sum_f64"])])
+        assert np.allclose(got["sum_f64"][fin], exp["sum_f64"][fin], rtol=1e-9)
+    else:
+        # error of either side is bounded by a few ulps of the sum of magnitudes in the group
+        scale = np.zeros(len(exp))
+        sel = v >= -900
+        np.add.at(scale, np.searchsorted(exp["key"], key[sel]), np.abs(w[sel]))
+        assert np.all(np.abs(got["sum_f64"] - exp["sum_f64"]) <= 1e-12 * scale)
+        if fixed == "1":
+            assert np.array_equal(got["sum_f64"].view(np.uint64), again["sum_f64"].view(np.uint64))
+
+
 def test_groupby_nulls_and_multisegment():
     rows = 50_000
     rng = np.random.default_rng(9)
