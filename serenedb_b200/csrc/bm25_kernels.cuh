@@ -277,11 +277,12 @@ struct TopkParams {
   const uint32_t* qterm_off;   // n_queries + 1
   unsigned long long* theta;   // per query running threshold key (shared by all chains / segments)
   unsigned long long* total;   // per query matched-doc count
-  unsigned long long* cand;    // [Q][lists][cap] candidate keys, sorted descending on exit
-  uint32_t* cand_n;            // [Q][lists]
-  uint32_t lists;              // candidate lists per query = segments * chains
-  uint32_t list_base;          // this segment's first list
-  uint32_t chunk;              // docs per chain
+  unsigned long long* cand;    // [lists][cap] candidate keys, sorted descending on exit
+  uint32_t* cand_n;            // [lists]
+  // One CTA per work item {query, chain, docs per chain, candidate list}: a query is cut into as many
+  // chains (contiguous doc ranges) as its posting count warrants, and the items are ordered largest first
+  // so that the long chains do not end up running alone at the tail of the launch.
+  const uint4* work;
   uint32_t k;
   uint32_t cap;                // candidate buffer capacity, power of two, > k
   int32_t conjunction;         // 0 OR, 1 AND
@@ -331,14 +332,15 @@ bm25_topk_kernel(const TopkParams P) {
   __shared__ uint32_t s_hist[258];
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  const uint32_t q = blockIdx.y, g = blockIdx.x;
+  const uint4 work = P.work[blockIdx.x];
+  const uint32_t q = work.x, g = work.y, chunk = work.z;
   const uint32_t t0 = P.qterm_off[q];
   const uint32_t T = min(P.qterm_off[q + 1] - t0, kMaxQueryTerms);
   const uint32_t m = max(1u, kBudget / T);                       // block budget per term
-  const unsigned long long first64 = 1ull + static_cast<unsigned long long>(g) * P.chunk;
+  const unsigned long long first64 = 1ull + static_cast<unsigned long long>(g) * chunk;
   const bool chain_empty = first64 > P.seg.n_docs;
   const uint32_t chain_lo = chain_empty ? 1u : uint32_t(first64);
-  const uint32_t chain_hi = chain_empty ? 0u : uint32_t(min(static_cast<unsigned long long>(P.seg.n_docs), first64 + P.chunk - 1ull));
+  const uint32_t chain_hi = chain_empty ? 0u : uint32_t(min(static_cast<unsigned long long>(P.seg.n_docs), first64 + chunk - 1ull));
 
   for (uint32_t i = tid; i < P.cap; i += blockDim.x) cand[i] = 0ull;
   if (tid < T) s_qt[tid] = P.qterms[t0 + tid];
@@ -639,11 +641,48 @@ bm25_topk_kernel(const TopkParams P) {
     const uint32_t n_entries = n_items * 128u;
     const uint32_t emit_begin = P.conjunction ? s_phase[buf][T - 1u] * 128u : 0u;  // AND: only the last term's slots can be complete (never in driver mode)
     bool first_pass = true;
+    const bool plain = !P.conjunction && P.filt.values == nullptr;   // disjunction without a table filter: 4 entries per lane
     for (;;) {
       const unsigned long long theta = s_theta;
       const uint32_t theta_hi = uint32_t(theta >> 32);
       uint32_t matched = 0;
       bool pending = false;
+      if (plain) {
+        // Vector pass: one 16-byte load of docs and of scores per lane; the score bits are tested against the
+        // threshold's score half, and only a warp that holds at least one possible candidate enters the append path.
+        for (uint32_t e0 = 0; e0 < n_entries; e0 += blockDim.x * 4u) {
+          const uint32_t e = e0 + tid * 4u;                    // n_entries is a multiple of 128
+          uint4 d4 = make_uint4(kPadDoc, kPadDoc, kPadDoc, kPadDoc);
+          uint4 s4 = make_uint4(0u, 0u, 0u, 0u);
+          if (e < n_entries) {
+            d4 = *reinterpret_cast<const uint4*>(e_doc + e);
+            s4 = *reinterpret_cast<const uint4*>(e_score + e);
+          }
+          const uint32_t span = hi - lo;
+          const bool l0 = d4.x - lo <= span, l1 = d4.y - lo <= span, l2 = d4.z - lo <= span, l3 = d4.w - lo <= span;
+          if (first_pass) matched += uint32_t(l0) + uint32_t(l1) + uint32_t(l2) + uint32_t(l3);
+          const bool w0 = l0 && s4.x >= theta_hi, w1 = l1 && s4.y >= theta_hi, w2 = l2 && s4.z >= theta_hi, w3 = l3 && s4.w >= theta_hi;
+          if (!__any_sync(kFull, w0 | w1 | w2 | w3)) continue;   // the common case once the threshold is up
+          const uint32_t dd[4] = {d4.x, d4.y, d4.z, d4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+          const bool ww[4] = {w0, w1, w2, w3};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            bool want = ww[j];
+            unsigned long long key = 0ull;
+            if (want) { key = make_key(__uint_as_float(ss[j]), P.seg.ordinal_base + dd[j]); want = key > theta; }
+            const uint32_t wb = __ballot_sync(kFull, want);
+            if (!wb) continue;
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&s_ncand, uint32_t(__popc(wb)));
+            base = __shfl_sync(kFull, base, 0);
+            if (want) {
+              const uint32_t pos = base + __popc(wb & ((1u << lane) - 1u));
+              if (pos < P.cap) { cand[pos] = key; e_doc[e + j] = kPadDoc; }   // stored: tombstone so that a retry skips it
+              else pending = true;
+            }
+          }
+        }
+      } else {
       for (uint32_t e0 = emit_begin; e0 < n_entries; e0 += blockDim.x) {
         const uint32_t e = e0 + tid;
         const uint32_t d = e < n_entries ? e_doc[e] : kPadDoc;
@@ -652,7 +691,6 @@ bm25_topk_kernel(const TopkParams P) {
         if (live && P.filt.values != nullptr) live = filter_pass(P.filt, d);
         // cheap pre-test on the score bits alone; the full 64-bit key only for the few that may qualify
         const uint32_t sbits = live ? __float_as_uint(e_score[e]) : 0u;
-        if (sbits & 0x80000000u) live = false;               // filler of a pruned block (negative score)
         matched += (live && first_pass) ? 1u : 0u;
         bool want = live && sbits >= theta_hi;
         unsigned long long key = 0ull;
@@ -669,6 +707,7 @@ bm25_topk_kernel(const TopkParams P) {
           }
         }
       }
+      }
       matched = warp_sum(matched);
       if (lane == 0 && matched) atomicAdd(&s_matched, matched);
       if (!__syncthreads_or(int(pending))) break;
@@ -684,9 +723,9 @@ bm25_topk_kernel(const TopkParams P) {
   uint32_t sort_n = 256u;
   while (sort_n < n_out) sort_n <<= 1;      // compact() left the survivors in [0, n_out) and zeros behind them
   block_sort_desc(cand, sort_n);
-  const size_t list = size_t(q) * P.lists + P.list_base + g;
+  const size_t list = work.w;
   unsigned long long* out = P.cand + list * P.cap;
-  for (uint32_t i = tid; i < P.cap; i += blockDim.x) out[i] = i < n_out ? cand[i] : 0ull;
+  for (uint32_t i = tid; i < n_out; i += blockDim.x) out[i] = cand[i];   // the merge reads cand_n entries only
   if (tid == 0) {
     P.cand_n[list] = n_out;
     if (s_matched) atomicAdd(P.total + q, static_cast<unsigned long long>(s_matched));
@@ -700,8 +739,9 @@ bm25_topk_kernel(const TopkParams P) {
 // Lists are sorted descending, so a list whose head is below the current k-th is skipped outright.
 // ------------------------------------------------------------------------------------------
 struct MergeParams {
-  const unsigned long long* cand;  // [Q][G][stride]
-  const uint32_t* cand_n;          // [Q][G] (null => every list holds `stride` entries, zeros = empty)
+  const unsigned long long* cand;  // [lists][stride]; query q owns lists [list_off[q], list_off[q+1]), or [q*G, (q+1)*G) when list_off is null
+  const uint32_t* cand_n;          // [lists] (null => every list holds `stride` entries, zeros = empty)
+  const uint32_t* list_off;        // [Q+1] or null
   uint32_t G, stride, k, cap;      // cap = power of two > k, multiple of the CTA size
   unsigned long long* keys_out;    // [Q][k]
   uint32_t* n_out;                 // [Q]
@@ -718,9 +758,10 @@ topk_merge_kernel(const MergeParams P) {
   for (uint32_t i = tid; i < P.cap; i += blockDim.x) buf[i] = 0ull;
   if (tid == 0) { s_n = 0u; s_kth = 0ull; }
   __syncthreads();
-  for (uint32_t g = 0; g < P.G; ++g) {
-    const unsigned long long* src = P.cand + (size_t(q) * P.G + g) * P.stride;
-    const uint32_t n = P.cand_n ? min(P.cand_n[size_t(q) * P.G + g], P.stride) : P.stride;
+  const uint32_t l_begin = P.list_off ? P.list_off[q] : q * P.G, l_end = P.list_off ? P.list_off[q + 1] : (q + 1u) * P.G;
+  for (uint32_t g = l_begin; g < l_end; ++g) {
+    const unsigned long long* src = P.cand + size_t(g) * P.stride;
+    const uint32_t n = P.cand_n ? min(P.cand_n[g], P.stride) : P.stride;
     uint32_t base = 0;
     while (base < n) {
       const uint32_t have = s_n;

@@ -428,7 +428,12 @@ __device__ __forceinline__ uint32_t range2(const unsigned char* col, uint32_t r,
   return (static_cast<unsigned long long>(v[0] - lo) <= span ? 1u : 0u) | (static_cast<unsigned long long>(v[1] - lo) <= span ? 2u : 0u);
 }
 
-template <int kStages, int kTileRows, int kConsumerWarps, bool kPacked, bool kFix>
+// kQuad (opt-in, SDBG_GROUPBY_QUAD=1): every accumulator of the slot is an integer (fixed-point SUM(double) or
+// no double sum), and the four words of a row's slot are updated by four adjacent lanes of ONE RED
+// instruction: one L2 request per passing row, sums independent of update order (bit-reproducible). Measured
+// slower than separate REDs on configs[1] (1.04 vs 0.87 ms): the compaction through shared memory and the
+// limb arithmetic cost the consumer warps more than the saved requests (profiles/r1_groupby_red_experiments.txt).
+template <int kStages, int kTileRows, int kConsumerWarps, bool kPacked, bool kQuad>
 __global__ void __launch_bounds__((kConsumerWarps + 1) * 32)
 filter_groupby_tma_kernel(const TmaGroupByParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -466,6 +471,9 @@ filter_groupby_tma_kernel(const TmaGroupByParams P) {
   }
 
   // ===== consumers =====
+  // quad mode: per-warp staging area behind the ring, 64 entries x (4 addends + slot index)
+  unsigned long long* const q_words = reinterpret_cast<unsigned long long*>(smem + size_t(kStages) * stage_bytes) + size_t(warp) * 256u;
+  uint32_t* const q_idx = reinterpret_cast<uint32_t*>(smem + size_t(kStages) * stage_bytes + size_t(kConsumerWarps) * 2048u) + size_t(warp) * 64u;
   // Each lane owns two consecutive rows of a 64-row strip, so every staged column is read with one
   // 16-byte (8-byte for int32) shared load per lane and the column type is a warp-uniform switch
   // outside the per-row work.
@@ -477,8 +485,9 @@ filter_groupby_tma_kernel(const TmaGroupByParams P) {
     const uint64_t row0 = tile * kTileRows;
     const uint32_t nrows = uint32_t(min(static_cast<unsigned long long>(kTileRows), static_cast<unsigned long long>(P.rows - row0)));
     const uint32_t pack_word = kPacked ? uint32_t(tile % uint64_t(P.pack_tables)) : 0u;   // words 0..2 of a slot: count / sum_lo / sum_hi
-    for (uint32_t r = warp * 64u + 2u * lane; r < nrows; r += kConsumerWarps * 64u) {
-      uint32_t m = r + 1u < nrows ? 3u : 1u;   // bit j: row r + j exists and still passes
+    for (uint32_t rb = warp * 64u; rb < nrows; rb += kConsumerWarps * 64u) {   // warp-uniform trip count
+      const uint32_t r = rb + 2u * lane;
+      uint32_t m = r + 1u < nrows ? 3u : r < nrows ? 1u : 0u;   // bit j: row r + j exists and still passes
 #pragma unroll
       for (int i = 0; i < kMaxPreds; ++i) {
         if (i < P.n_preds) {
@@ -492,16 +501,69 @@ filter_groupby_tma_kernel(const TmaGroupByParams P) {
           m &= P.pred_negate[i] ? ~in : in;
         }
       }
-      if (m == 0u) continue;
+      if (!kQuad && m == 0u) continue;          // quad mode: every lane takes part in the warp-wide compaction
       long long key[2], v[2] = {0, 0};
       double w[2] = {0.0, 0.0};
       if (P.key_type == 2) load2<2>(base + P.key_off, r, key); else load2<0>(base + P.key_off, r, key);
       if (kPacked || P.has_sum_i) {
         if (P.sum_i_type == 2) load2<2>(base + P.sum_i_off, r, v); else load2<0>(base + P.sum_i_off, r, v);
       }
-      if (kFix || P.has_sum_f) {
+      if (P.has_sum_f) {
         const double2 x = *reinterpret_cast<const double2*>(base + P.sum_f_off + size_t(r) * 8u);
         w[0] = x.x; w[1] = x.y;
+      }
+      if (kQuad) {
+        // Stage {slot index, 4 addends} of every passing row compacted in shared memory, then let lane
+        // 4q + f add word f of entry q: eight sectors per RED instruction, one request per passing row.
+        unsigned long long a[2][4];
+        uint32_t gi[2] = {0u, 0u};
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (!(m & (1u << j))) continue;
+          const unsigned long long idx = static_cast<unsigned long long>(key[j] - P.key_min);
+          if (idx >= P.key_span) { atomicAdd(P.out_of_range, 1ull); m &= ~(1u << j); continue; }
+          gi[j] = uint32_t(idx);                                   // dense tables span <= 2^26 groups
+          if (kPacked) {
+            const unsigned long long pk = (1ull << P.pack_shift) + static_cast<unsigned long long>(v[j] - P.pack_bias);
+            a[j][0] = pack_word == 0u ? pk : 0ull;
+            a[j][1] = pack_word == 1u ? pk : 0ull;
+            a[j][2] = pack_word == 2u ? pk : 0ull;
+          } else {
+            a[j][0] = 1ull;
+            a[j][1] = !P.has_sum_i ? 0ull : P.wide_int ? (static_cast<unsigned long long>(v[j]) & 0xFFFFFFFFull) : static_cast<unsigned long long>(v[j]);
+            a[j][2] = P.has_sum_i && P.wide_int ? static_cast<unsigned long long>(v[j] >> 32) : 0ull;
+          }
+          a[j][3] = 0ull;
+          if (P.fix_limb) {                                        // fixed-point SUM(double): words 2 and 3
+            long long l0, l1;
+            fix_limbs(w[j], P.fix_limb, P.fix_eunit, l0, l1);
+            a[j][2] = static_cast<unsigned long long>(l0);
+            a[j][3] = static_cast<unsigned long long>(l1);
+          }
+        }
+        const uint32_t b0 = __ballot_sync(kFull, (m & 1u) != 0u), b1 = __ballot_sync(kFull, (m & 2u) != 0u);
+        const uint32_t lt = (1u << lane) - 1u;
+        uint32_t pos = __popc(b0 & lt) + __popc(b1 & lt);
+        const uint32_t total = __popc(b0) + __popc(b1);
+        if (m & 1u) {
+          reinterpret_cast<ulonglong2*>(q_words)[pos * 2u] = make_ulonglong2(a[0][0], a[0][1]);
+          reinterpret_cast<ulonglong2*>(q_words)[pos * 2u + 1u] = make_ulonglong2(a[0][2], a[0][3]);
+          q_idx[pos++] = gi[0];
+        }
+        if (m & 2u) {
+          reinterpret_cast<ulonglong2*>(q_words)[pos * 2u] = make_ulonglong2(a[1][0], a[1][1]);
+          reinterpret_cast<ulonglong2*>(q_words)[pos * 2u + 1u] = make_ulonglong2(a[1][2], a[1][3]);
+          q_idx[pos] = gi[1];
+        }
+        __syncwarp();
+        if (!(P.debug_skip & 7)) {
+          for (uint32_t e = lane >> 2; e < total; e += 8u) {
+            const unsigned long long val = q_words[e * 4u + (lane & 3u)];
+            if (val) atomicAdd(reinterpret_cast<unsigned long long*>(P.table + q_idx[e]) + (lane & 3u), val);
+          }
+        }
+        __syncwarp();
+        continue;
       }
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
@@ -523,16 +585,7 @@ filter_groupby_tma_kernel(const TmaGroupByParams P) {
             }
           }
         }
-        if (kFix) {
-          long long l0, l1;
-          fix_limbs(w[j], P.fix_limb, P.fix_eunit, l0, l1);
-          if (!(P.debug_skip & 4)) {
-            atomicAdd(g + 2, static_cast<unsigned long long>(l0));
-            atomicAdd(g + 3, static_cast<unsigned long long>(l1));
-          }
-        } else if (P.has_sum_f && !(P.debug_skip & 4)) {
-          atomicAdd(reinterpret_cast<double*>(g + 3), w[j]);
-        }
+        if (P.has_sum_f && !(P.debug_skip & 4)) atomicAdd(reinterpret_cast<double*>(g + 3), w[j]);
       }
     }
     __syncwarp();

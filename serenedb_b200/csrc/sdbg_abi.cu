@@ -451,7 +451,7 @@ int filter_view(sdbg_segment* s, const sdbg_col_pred* f, FilterDev* out) {
 }
 
 struct TopkPlan {
-  uint32_t G, lists, cap, k, chunk, budget;
+  uint32_t G, cap, k, budget;
   size_t smem;
 };
 
@@ -490,21 +490,57 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
   // ranges) only when the batch alone cannot do that.
   const uint32_t target_ctas = uint32_t(c->sm_count) * 8u;
   pl.G = uint32_t(std::max<size_t>(1, (target_ctas + nq - 1) / nq));
-  pl.G = std::min(pl.G, uint32_t(env_int("SDBG_TOPK_MAX_CHAINS", 296)));
-  pl.G = std::min(pl.G, std::max(1u, max_docs / 4096u));
-  pl.chunk = (max_docs + pl.G - 1) / pl.G;
-  pl.lists = pl.G * uint32_t(n_segs);
+  const uint32_t max_chains = uint32_t(env_int("SDBG_TOPK_MAX_CHAINS", 296));
+  // Work list: (segment, query) pairs get max(G, postings / target) chains, so that a query over a 5 M-doc
+  // list is not one CTA-long critical path next to thousands of short ones; largest chains are issued first.
+  uint64_t batch_postings = 0;
+  for (size_t si = 0; si < n_segs; ++si)
+    for (uint32_t i = 0; i < total_terms; ++i)
+      if (terms[i].term < segs[si]->term_docs.size()) batch_postings += segs[si]->term_docs[terms[i].term];
+  const uint64_t chain_target = std::max<uint64_t>(uint64_t(env_int("SDBG_TOPK_CHAIN_MIN", 65536)), batch_postings / (uint64_t(c->sm_count) * 16u));
+  struct WorkItem { uint32_t q, g, chunk, list; uint64_t weight; };
+  std::vector<std::vector<WorkItem>> seg_work(n_segs);
+  std::vector<uint32_t> list_off(nq + 1, 0);
+  for (size_t q = 0; q < nq; ++q) {          // lists of one query are contiguous: [segment 0 chains | segment 1 chains | ...]
+    uint32_t lists = 0;
+    for (size_t si = 0; si < n_segs; ++si) {
+      const sdbg_segment* s = segs[si];
+      uint64_t postings = 0;
+      for (uint32_t i = term_off[q]; i < term_off[q + 1]; ++i)
+        if (terms[i].term < s->term_docs.size()) postings += s->term_docs[terms[i].term];
+      uint32_t g = uint32_t(std::max<uint64_t>(pl.G, (postings + chain_target - 1) / chain_target));
+      g = std::min(g, max_chains);
+      g = std::min(g, std::max(1u, s->n_docs / 4096u));
+      const uint32_t chunk = (s->n_docs + g - 1) / g;
+      for (uint32_t j = 0; j < g; ++j) seg_work[si].push_back({uint32_t(q), j, chunk, list_off[q] + lists + j, postings / g});
+      lists += g;
+    }
+    list_off[q + 1] = list_off[q] + lists;
+  }
+  const uint32_t total_lists = list_off[nq];
+  size_t total_work = 0;
+  for (auto& w : seg_work) {
+    std::stable_sort(w.begin(), w.end(), [](const WorkItem& a, const WorkItem& b) { return a.weight > b.weight; });
+    total_work += w.size();
+  }
   pl.smem = size_t(entries) * 8 + (kind == SDBG_QUERY_AND ? entries : 0) + size_t(pl.cap) * 8 + (c->wand >= 2 ? size_t(entries) * 2 : 0);
   if (pl.smem > 200 * 1024) return fail(c, SDBG_EUNSUPPORTED, "hash window + candidate buffer exceed shared memory");
 
   // host-side query descriptors, per segment, sorted by ascending docs_count (conjunction.hpp:520-523)
   const size_t qt_bytes = size_t(total_terms) * sizeof(QTermDev) * n_segs;
   const size_t off_bytes = (nq + 1) * sizeof(uint32_t);
-  int rc = ensure_pinned(c, qt_bytes + off_bytes);
+  const size_t work_bytes = total_work * sizeof(uint4);
+  const size_t qt_pad = (qt_bytes + off_bytes + 15) & ~size_t(15);   // work items are 16-byte loads
+  int rc = ensure_pinned(c, qt_pad + work_bytes + off_bytes);
   if (rc) return rc;
   auto* h_qt = static_cast<QTermDev*>(c->h_pinned);
   auto* h_off = reinterpret_cast<uint32_t*>(static_cast<char*>(c->h_pinned) + qt_bytes);
   std::memcpy(h_off, term_off, off_bytes);
+  {
+    auto* h_work = reinterpret_cast<uint4*>(static_cast<char*>(c->h_pinned) + qt_pad);
+    for (auto& w : seg_work) for (const WorkItem& it : w) *h_work++ = make_uint4(it.q, it.g, it.chunk, it.list);
+    std::memcpy(static_cast<char*>(c->h_pinned) + qt_pad + work_bytes, list_off.data(), off_bytes);
+  }
   for (size_t si = 0; si < n_segs; ++si) {
     const sdbg_segment* s = segs[si];
     QTermDev* dst = h_qt + si * total_terms;
@@ -526,13 +562,13 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
   }
   DevBuf& b_qt = c->scratch[0]; DevBuf& b_theta = c->scratch[1]; DevBuf& b_cand = c->scratch[2];
   DevBuf& b_candn = c->scratch[3]; DevBuf& b_keys = c->scratch[4]; DevBuf& b_small = c->scratch[5];
-  if ((rc = ensure(c, b_qt, qt_bytes + off_bytes))) return rc;
+  if ((rc = ensure(c, b_qt, qt_pad + work_bytes + off_bytes))) return rc;
   if ((rc = ensure(c, b_theta, nq * 16))) return rc;  // theta[nq] | total[nq]
-  if ((rc = ensure(c, b_cand, nq * size_t(pl.lists) * pl.cap * 8))) return rc;
-  if ((rc = ensure(c, b_candn, nq * size_t(pl.lists) * 4))) return rc;
+  if ((rc = ensure(c, b_cand, size_t(total_lists) * pl.cap * 8))) return rc;
+  if ((rc = ensure(c, b_candn, size_t(total_lists) * 4))) return rc;
   if ((rc = ensure(c, b_keys, nq * size_t(k) * 8))) return rc;
   if ((rc = ensure(c, b_small, nq * 4))) return rc;
-  CU(c, cudaMemcpyAsync(b_qt.p, c->h_pinned, qt_bytes + off_bytes, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(b_qt.p, c->h_pinned, qt_pad + work_bytes + off_bytes, cudaMemcpyHostToDevice, c->stream));
   auto* d_theta = static_cast<unsigned long long*>(b_theta.p);
   auto* d_total = d_theta + nq;
   uint32_t thr_bits; std::memcpy(&thr_bits, &threshold_in, 4);
@@ -550,6 +586,7 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
     c->topk_attr_set = true;
   }
   uint32_t base = 0;
+  size_t work_done = 0;
   for (size_t si = 0; si < n_segs; ++si) {
     sdbg_segment* s = segs[si];
     TopkParams P;
@@ -560,12 +597,12 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
     P.theta = d_theta; P.total = d_total;
     P.cand = static_cast<unsigned long long*>(b_cand.p);
     P.cand_n = static_cast<uint32_t*>(b_candn.p);
-    P.lists = pl.lists; P.list_base = uint32_t(si) * pl.G;
-    P.chunk = pl.chunk;
+    P.work = reinterpret_cast<const uint4*>(static_cast<const char*>(b_qt.p) + qt_pad) + work_done;
+    work_done += seg_work[si].size();
     P.k = k; P.cap = pl.cap; P.conjunction = kind == SDBG_QUERY_AND ? 1 : 0;
     P.wand = (c->wand && s->has_wand) ? c->wand : 0;
     { ProfScope ps_(c, kProfTopk);
-      const dim3 grid(pl.G, unsigned(nq));
+      const dim3 grid(unsigned(seg_work[si].size()));
       const bool drive = c->wand >= 2 && kind != SDBG_QUERY_AND;
       if (pl.budget == 16) { if (drive) bm25_topk_kernel<16, true><<<grid, kTopkThreads, pl.smem, c->stream>>>(P);
                              else bm25_topk_kernel<16, false><<<grid, kTopkThreads, pl.smem, c->stream>>>(P); }
@@ -578,7 +615,8 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
   MergeParams M;
   M.cand = static_cast<const unsigned long long*>(b_cand.p);
   M.cand_n = static_cast<const uint32_t*>(b_candn.p);
-  M.G = pl.lists; M.stride = pl.cap; M.k = k; M.cap = pl.cap;
+  M.list_off = reinterpret_cast<const uint32_t*>(static_cast<const char*>(b_qt.p) + qt_pad + work_bytes);
+  M.G = 0; M.stride = pl.cap; M.k = k; M.cap = pl.cap;
   M.keys_out = static_cast<unsigned long long*>(b_keys.p);
   M.n_out = static_cast<uint32_t*>(b_small.p);
   { ProfScope ps_(c, kProfMerge);
@@ -716,7 +754,7 @@ extern "C" int sdbg_topk_merge_gathered(sdbg_ctx* c, const void* d_keys_all, uin
     c->merge_attr_set = true;
   }
   MergeParams M;
-  M.cand = static_cast<const unsigned long long*>(b_in.p); M.cand_n = nullptr;
+  M.cand = static_cast<const unsigned long long*>(b_in.p); M.cand_n = nullptr; M.list_off = nullptr;
   M.G = n_ranks; M.stride = k; M.k = k; M.cap = cap;
   M.keys_out = static_cast<unsigned long long*>(b_keys.p); M.n_out = static_cast<uint32_t*>(b_small.p);
   topk_merge_kernel<<<unsigned(nq), kTopkThreads, size_t(cap) * 8, c->stream>>>(M);
@@ -922,7 +960,8 @@ extern "C" int sdbg_filter_count_sum(sdbg_segment* const* segs, size_t n_segs, c
 
 namespace {
 
-struct GroupPlan { int wide_int = 0; int count_f = 0; int pack_shift = 0; int pack_tables = 0; int64_t pack_bias = 0; int fix_limb = 0; int fix_eunit = 0; };
+struct GroupPlan { int wide_int = 0; int count_f = 0; int pack_shift = 0; int pack_tables = 0; int64_t pack_bias = 0; int fix_limb = 0; int fix_eunit = 0; int quad = 0; };
+constexpr int kGroupByDefaultStages = 3;   // 3 x 20 KB stages -> 3 CTAs (24 consumer warps) per SM; measured best of 2/3/4
 constexpr int kGroupByTileRows = 512;   // tile of the default TMA shape; packed accumulators are only planned for it
 
 int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred* preds, size_t n_preds, uint64_t key_field,
@@ -992,7 +1031,7 @@ int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred
   // Fixed-point SUM(double): two integer limb REDs instead of one floating-point RED (see TmaGroupByParams).
   // Needs words 2 and 3 of the slot (no wide integer sum, at most two packed words) and a finite column.
   if (avg_f64_field != UINT64_MAX && all_tma && !plan.wide_int && total_rows && absmax_bits < 0x7FF0000000000000ull &&
-      env_int("SDBG_GROUPBY_FIXED", 0)) {   // opt-in: bit-reproducible sums, but two integer REDs measure slower than one f64 RED
+      env_int("SDBG_GROUPBY_FIXED", 1)) {
     int row_bits = 1;
     while ((1ull << row_bits) <= total_rows) ++row_bits;
     plan.fix_limb = std::min(37, 63 - row_bits);                     // |limb sum| <= rows * 2^limb < 2^63
@@ -1001,6 +1040,9 @@ int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred
     if (mx > 0) std::frexp(mx, &e);                                  // mx < 2^e
     plan.fix_eunit = e - 2 * plan.fix_limb;                          // |w| / 2^eunit < 2^(2*limb)
   }
+  // All accumulators integer => the four words of a slot go out as one RED request per passing row.
+  plan.quad = all_tma && (avg_f64_field == UINT64_MAX || plan.fix_limb) && env_int("SDBG_GROUPBY_QUAD", 0);
+  if (!plan.quad) plan.fix_limb = 0, plan.fix_eunit = 0;            // separate REDs: one f64 RED beats two integer ones
   for (size_t si = 0; si < n_segs; ++si) {
     sdbg_segment* s = segs[si];
     GroupByParams P;
@@ -1108,9 +1150,10 @@ int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred
         T.sum_f_off = sum_f_s >= 0 ? T.off[sum_f_s] : 0;
       };
       const int shape = env_int("SDBG_GROUPBY_TMA_SHAPE", 0);
+      const bool quad = plan.quad != 0;
       auto launch = [&](auto kern, int stages, int tile_rows, int consumer_warps) -> int {
         set_offsets(tile_rows);
-        const size_t smem = size_t(stages) * size_t(T.off[T.n_streams]);
+        const size_t smem = size_t(stages) * size_t(T.off[T.n_streams]) + (quad ? size_t(consumer_warps) * (2048 + 256) : 0);
         CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         const size_t fit = std::max<size_t>(1, (220 * 1024) / (smem + 2048));
         const size_t by_threads = std::max<size_t>(1, 2048 / (size_t(consumer_warps + 1) * 32));
@@ -1126,12 +1169,19 @@ int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred
         case 2: lrc = launch(filter_groupby_tma_kernel<4, 512, 16, false, false>, 4, 512, 16); break;
         case 3: lrc = launch(filter_groupby_tma_kernel<3, 256, 8, false, false>, 3, 256, 8); break;
         case 4: lrc = launch(filter_groupby_tma_kernel<4, 1024, 16, false, false>, 4, 1024, 16); break;
-        default:
-          if (plan.pack_tables) lrc = plan.fix_limb ? launch(filter_groupby_tma_kernel<4, kGroupByTileRows, 8, true, true>, 4, kGroupByTileRows, 8)
-                                                    : launch(filter_groupby_tma_kernel<4, kGroupByTileRows, 8, true, false>, 4, kGroupByTileRows, 8);
-          else lrc = plan.fix_limb ? launch(filter_groupby_tma_kernel<4, kGroupByTileRows, 8, false, true>, 4, kGroupByTileRows, 8)
-                                   : launch(filter_groupby_tma_kernel<4, kGroupByTileRows, 8, false, false>, 4, kGroupByTileRows, 8);
+        default: {
+          // default shape: 512-row tiles, 8 consumer warps; ring depth by SDBG_GROUPBY_TMA_STAGES (the CTAs per
+          // SM follow from the shared-memory footprint, so fewer stages = more resident consumer warps)
+          const int stages = env_int("SDBG_GROUPBY_TMA_STAGES", kGroupByDefaultStages);
+#define SDBG_GB_LAUNCH(ST) \
+          (plan.pack_tables ? (quad ? launch(filter_groupby_tma_kernel<ST, kGroupByTileRows, 8, true, true>, ST, kGroupByTileRows, 8) \
+                                    : launch(filter_groupby_tma_kernel<ST, kGroupByTileRows, 8, true, false>, ST, kGroupByTileRows, 8)) \
+                            : (quad ? launch(filter_groupby_tma_kernel<ST, kGroupByTileRows, 8, false, true>, ST, kGroupByTileRows, 8) \
+                                    : launch(filter_groupby_tma_kernel<ST, kGroupByTileRows, 8, false, false>, ST, kGroupByTileRows, 8)))
+          lrc = stages == 2 ? SDBG_GB_LAUNCH(2) : stages == 3 ? SDBG_GB_LAUNCH(3) : SDBG_GB_LAUNCH(4);
+#undef SDBG_GB_LAUNCH
           break;
+        }
       }
       if (lrc) return lrc;
     } else {

@@ -128,7 +128,10 @@ def test_groupby_matches_oracle(rows):
 
 
 @pytest.mark.parametrize("env", [{"SDBG_GROUPBY_PACKED": "0"}, {}, {"SDBG_GROUPBY_PACK_TABLES_MIN": "2"},
-                                 {"SDBG_GROUPBY_PACK_TABLES_MIN": "3"}])
+                                 {"SDBG_GROUPBY_PACK_TABLES_MIN": "3"}, {"SDBG_GROUPBY_QUAD": "1"},
+                                 {"SDBG_GROUPBY_QUAD": "1", "SDBG_GROUPBY_PACKED": "0"},
+                                 {"SDBG_GROUPBY_QUAD": "1", "SDBG_GROUPBY_PACK_TABLES_MIN": "2"},
+                                 {"SDBG_GROUPBY_QUAD": "1", "SDBG_GROUPBY_FIXED": "0"}, {"SDBG_GROUPBY_TMA_STAGES": "2"}])
 @pytest.mark.parametrize("sum_dtype", [np.int64, np.int32])
 def test_groupby_packed_accumulators(env, sum_dtype, monkeypatch):
     """COUNT and SUM(int) sharing one RED word (stats-gated) must give the same result as separate
@@ -177,7 +180,7 @@ def test_groupby_fixed_point_double_sum(case, with_int_sum, fixed, monkeypatch):
     """SUM(double) accumulated as two integer limbs (stats-gated) against the oracle's double sum:
     negative values, 60 binades of dynamic range, denormals, and the NaN / inf fallback. The integer
     path is also order-independent, so two runs must agree to the bit."""
-    monkeypatch.setenv("SDBG_GROUPBY_FIXED", fixed)
+    monkeypatch.setenv("SDBG_GROUPBY_QUAD", fixed)     # the fixed-point limbs ride on the one-request-per-row (quad) update path
     rng = np.random.default_rng(23)
     rows = 40_003
     key = rng.integers(0, 97, size=rows).astype(np.int64)
