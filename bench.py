@@ -101,6 +101,17 @@ def merge_clocks(a, b):
             "reasons": sorted(set(a["reasons"]) | set(b["reasons"])), "samples": a["samples"] + b["samples"]}
 
 
+def ncu_traffic(kernel, units):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed `ncu --set full`
+    capture of this command (profiles/traffic.json names the capture); null when the workload size differs
+    from the captured one or no capture is recorded."""
+    try:
+        t = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")))[kernel]
+        return t["dram_bytes"] if int(t["units"]) == int(units) else None
+    except Exception:
+        return None
+
+
 def make_queries(nq):
     """Two-term disjunctions, pairs drawn from the 256 synthetic terms; query 0 is the named
     case p = (0.10, 0.01) => terms 5 and 59."""
@@ -385,7 +396,7 @@ def main():
                                                "ms_per_step": round(e_ms, 3), "steps": e_steps},
         "gpu_launches": int(gb_launches),
         "roofline": {"bound": "hbm", "achieved": round(gb_ach, 1), "peak": hbm_peak, "unit": "GB/s",
-                     "frac": round(gb_ach / hbm_peak, 4), "traffic": None, "kernel": "filter_groupby_kernel",
+                     "frac": round(gb_ach / hbm_peak, 4), "traffic": ncu_traffic("filter_groupby_tma_kernel", rows), "kernel": "filter_groupby_tma_kernel",
                      "kernel_ms": round(gb_kernel_ms, 4), "algorithmic_bytes": gb_alg_bytes, "peak_source": peak_src},
     }
     if cpu_gb:
@@ -465,7 +476,7 @@ def main():
                     "d2h_bytes_per_step": nq * TOPK * 8 + nq * 12, "ms_per_step": round(be_ms, 3)},
             "gpu_launches": int(bm_launches),
             "roofline": {"bound": "hbm", "achieved": round(alg_bytes / (tk_ms / max(tk_n, 1) * 1e-3) / 1e9, 1), "peak": hbm_peak, "unit": "GB/s",
-                         "frac": round(alg_bytes / (tk_ms / max(tk_n, 1) * 1e-3) / 1e9 / hbm_peak, 4), "traffic": None,
+                         "frac": round(alg_bytes / (tk_ms / max(tk_n, 1) * 1e-3) / 1e9 / hbm_peak, 4), "traffic": ncu_traffic("bm25_topk_kernel", n_docs),
                          "kernel": "bm25_topk_kernel", "kernel_ms": round(tk_ms / max(tk_n, 1), 3), "merge_kernel_ms": round(mg_ms / max(mg_n, 1), 3),
                          "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                          "note": "touched bytes = encoded doc+freq blocks of every list scanned + 1 B norm per posting + 12 B per hit"},

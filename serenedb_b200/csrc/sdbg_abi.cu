@@ -497,7 +497,7 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
   for (size_t si = 0; si < n_segs; ++si)
     for (uint32_t i = 0; i < total_terms; ++i)
       if (terms[i].term < segs[si]->term_docs.size()) batch_postings += segs[si]->term_docs[terms[i].term];
-  const uint64_t chain_target = std::max<uint64_t>(uint64_t(env_int("SDBG_TOPK_CHAIN_MIN", 65536)), batch_postings / (uint64_t(c->sm_count) * 16u));
+  const uint64_t chain_target = std::max<uint64_t>(uint64_t(env_int("SDBG_TOPK_CHAIN_MIN", 65536)), batch_postings / (uint64_t(c->sm_count) * uint64_t(std::max(1, env_int("SDBG_TOPK_CHAIN_DIV", 4)))));
   struct WorkItem { uint32_t q, g, chunk, list; uint64_t weight; };
   std::vector<std::vector<WorkItem>> seg_work(n_segs);
   std::vector<uint32_t> list_off(nq + 1, 0);
@@ -681,10 +681,21 @@ extern "C" int sdbg_bm25_topk_batch(sdbg_segment* const* segs, size_t n_segs, in
   const auto* keys = reinterpret_cast<const unsigned long long*>(h);
   const auto* tot = reinterpret_cast<const unsigned long long*>(h + kb);
   const auto* cnt = reinterpret_cast<const uint32_t*>(h + kb + tb);
-  for (size_t q = 0; q < nq; ++q) {
-    n_out[q] = cnt[q];
-    keys_to_hits(keys + q * k, cnt[q], bases, out + q * k);
-    if (total_matches) total_matches[q] = tot[q];
+  auto convert = [&](size_t q0, size_t q1) {
+    for (size_t q = q0; q < q1; ++q) {
+      n_out[q] = cnt[q];
+      keys_to_hits(keys + q * k, cnt[q], bases, out + q * k);
+      if (total_matches) total_matches[q] = tot[q];
+    }
+  };
+  // key -> {segment, doc, score} is a few ns per hit; a large batch (millions of hits) is split over host threads
+  const size_t n_thr = std::min<size_t>(size_t(env_int("SDBG_HOST_THREADS", 8)), (nq * size_t(k)) / 65536);
+  if (n_thr <= 1) {
+    convert(0, nq);
+  } else {
+    std::vector<std::thread> pool;
+    for (size_t t = 0; t < n_thr; ++t) pool.emplace_back(convert, nq * t / n_thr, nq * (t + 1) / n_thr);
+    for (auto& th : pool) th.join();
   }
   return SDBG_OK;
 }
@@ -1000,7 +1011,7 @@ int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred
       if (it == s->cols.end()) return fail(c, SDBG_ENOTFOUND, "avg column not staged");
       if (it->second.d_validity) { plan.count_f = 1; all_tma = false; }
       uint64_t ab = 0;
-      if (it->second.type == SDBG_F64 && all_tma) { if ((rc = column_absmax(s, avg_f64_field, &ab))) return rc; }
+      if (it->second.type == SDBG_F64 && all_tma && env_int("SDBG_GROUPBY_QUAD", 0)) { if ((rc = column_absmax(s, avg_f64_field, &ab))) return rc; }   // statistic only the fixed-point path needs
       absmax_bits = std::max(absmax_bits, ab);
     }
     auto kit = s->cols.find(key_field);
