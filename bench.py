@@ -216,10 +216,32 @@ def run_reference(args, rank):
                         "cpu_baseline": {"value": round(postings / np.mean(t) / 1e6, 2), "unit": "Mdocs/s", "cores": threads, "kind": "port",
                                          "sample": "%d of the %d two-term OR queries per step, block-max pruned oracle, simdcomp unpack from oracle/_ref"
                                                    % (len(qs), args.queries)}}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
+
+
+_JSON_FD = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout. Libraries (NCCL prints its version banner there) get stderr:
+    fd 1 is pointed at fd 2 for the whole run and the line is written to the saved descriptor."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -565,7 +587,7 @@ def main():
                                                 "sample": "%d concurrent copies of the query" % ncpu4}}
         line["other_configs"] = other
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
