@@ -86,8 +86,12 @@ typedef struct {
 int sdbg_segment_create(sdbg_ctx*, uint32_t docs_count, sdbg_segment** out);
 void sdbg_segment_destroy(sdbg_segment*);
 /* doc_file: the ".doc" stream (posting blocks + skip data, format "1_5simd"); has_wand != 0 when
- * the field was indexed with block-max data (optimize_top_k). Builds the per-block offset table
- * and copies 16-byte-aligned block payloads to HBM. */
+ * the field was indexed with block-max data (optimize_top_k) in the (freq, norm) pair layout
+ * (WandType::MinNorm / DivNorm, wand_writer.hpp:302-381). The pairs only bound the scores of the scorer
+ * they were written for: as in the reference (the field's wand scorers are matched with Scorer::equals),
+ * the caller enables pruning (sdbg_set_wand) only for queries of that scorer; pass 0 for a field whose wand
+ * payload has another layout (BM15's freq-only entries). Builds the per-block offset table and copies
+ * 16-byte-aligned block payloads to HBM. */
 int sdbg_stage_postings(sdbg_segment*, const uint8_t* doc_file, size_t n, const sdbg_term_meta* terms,
                         size_t n_terms, int has_wand);
 typedef struct { uint8_t byte_size; uint32_t row_count; uint64_t file_offset; } sdbg_norm_rg; /* norm_writer.hpp:41-48 */
@@ -131,23 +135,27 @@ typedef struct { float score; uint32_t doc; uint32_t seg; } sdbg_hit;           
 int sdbg_bm25_collect(uint64_t docs_with_field, uint64_t total_term_freq, uint64_t docs_with_term, float k,
                       float b, sdbg_bm25_term* out);
 
-/* One query over the segments of this GPU. Accepts docs with score > threshold_in (seed it with
+/* (k1, b) are the scorer's parameters (BM25::k(), BM25::b()): like BM25::PrepareScorer (bm25.cpp:312-365) they
+ * select the scoring form -- k1 == 0: BM1 (every score 0 without a filter boost, :112-126), b == 0: BM15
+ * (c0 - c0 / (1 + freq / k1), no norms, :70-87), otherwise BM25 (:90-107). Block-max pruning is applied only to
+ * the BM25 form: the staged (freq, norm) pairs were chosen for it (wand_type() differs per form, bm25.cpp:407-418).
+ * One query over the segments of this GPU. Accepts docs with score > threshold_in (seed it with
  * FLT_MIN like doc_collector.hpp:102, or with the cross-worker threshold). out has room for k hits,
  * returned sorted by (score desc, seg asc, doc asc); *threshold_out = k-th score if k hits exist. */
 int sdbg_bm25_topk(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25_term* terms,
-                   size_t n_terms, float k1, const sdbg_col_pred* filt, uint32_t k, float threshold_in,
+                   size_t n_terms, float k1, float b, const sdbg_col_pred* filt, uint32_t k, float threshold_in,
                    sdbg_hit* out, uint32_t* n_out, uint64_t* total_matches, float* threshold_out);
 /* A batch of independent queries in one launch set (the benchmark-game / many-workers shape).
  * Query q uses terms[term_off[q] .. term_off[q+1]); out holds n_queries*k hits, n_out/total per query. */
 int sdbg_bm25_topk_batch(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25_term* terms,
-                         const uint32_t* term_off, size_t n_queries, float k1, const sdbg_col_pred* filt,
+                         const uint32_t* term_off, size_t n_queries, float k1, float b, const sdbg_col_pred* filt,
                          uint32_t k, float threshold_in, sdbg_hit* out, uint32_t* n_out,
                          uint64_t* total_matches);
 /* Multi-GPU: leave each query's top-k on the device as sortable 64-bit keys + a base ordinal so a
  * collective can gather them; merge gathered keys from `n_ranks` ranks. */
 int sdbg_bm25_topk_batch_device(sdbg_segment* const* segs, size_t n_segs, int kind,
                                 const sdbg_bm25_term* terms, const uint32_t* term_off, size_t n_queries,
-                                float k1, const sdbg_col_pred* filt, uint32_t k, float threshold_in,
+                                float k1, float b, const sdbg_col_pred* filt, uint32_t k, float threshold_in,
                                 uint32_t rank, void* d_keys /* n_queries*k u64 */,
                                 void* d_totals /* n_queries u64 */);
 /* out may be NULL: the merged keys then stay in HBM (device-resident pipelines / timing). */

@@ -612,8 +612,14 @@ void bm25_collect(uint64_t docs_with_field, uint64_t total_term_freq, uint64_t d
   }
 }
 inline float bm25_num(float k, float boost, float idf) { return boost * (k + 1) * idf; }  // :224
-// Bm25<MergeType,false> :90-107
-inline float bm25_one(uint32_t freq, uint32_t norm, float c0, float norm_const, float norm_length) {
+// The scoring form BM25::PrepareScorer picks (bm25.cpp:312-365): k == 0 -> Bm1Score, b == 0 -> Bm15Score, else Bm25Score.
+enum ScoreForm { kFormBm25 = 0, kFormBm15 = 1, kFormBm1 = 2 };
+inline int score_form(float k, float b) { return k == 0.f ? kFormBm1 : b == 0.f ? kFormBm15 : kFormBm25; }
+// Bm25<MergeType,false> :90-107; Bm15<MergeType,false> :70-87 (c1 = norm_const = k, norms unused);
+// Bm1Score without a filter boost zero-fills (:118-126).
+inline float bm25_one(uint32_t freq, uint32_t norm, float c0, float norm_const, float norm_length, int form = kFormBm25) {
+  if (form == kFormBm1) return 0.f;
+  if (form == kFormBm15) return c0 - c0 / (1.f + float(freq) / norm_const);
   const float c1 = norm_const + norm_length * float(norm);
   return c0 - c0 * c1 / (c1 + float(freq));
 }
@@ -717,6 +723,7 @@ struct Cursor {
   uint32_t blk = 0;            // index of the NEXT block to decode
   SkipInfo skip;               // filled when pruning is wanted
   float c0 = 0, norm_const = 0, norm_length = 0;
+  int form = kFormBm25;
   uint64_t scored = 0;
 
   void open(const orc_segment& s, uint32_t term, bool want_skip) {
@@ -741,11 +748,11 @@ struct Cursor {
   uint32_t doc() { if (pos == len && !next_block()) return 0xFFFFFFFFu; return docs[pos]; }
   float score_at(uint32_t i) {
     ++scored;
-    return bm25_one(freqs[i], seg->norm(docs[i]), c0, norm_const, norm_length);
+    return bm25_one(freqs[i], seg->norm(docs[i]), c0, norm_const, norm_length, form);
   }
   // Upper bound of the NEXT (undecoded) block and its last doc; blocks without a level-0 entry
   // (the final one) fall back to the list maximum (WandReadSkip::GetMaxScore, iterator_score.hpp:289-296).
-  float bound_of(const WandEntry& e) const { return bm25_one(e.freq, e.norm, c0, norm_const, norm_length); }
+  float bound_of(const WandEntry& e) const { return bm25_one(e.freq, e.norm, c0, norm_const, norm_length, form); }
   float next_block_bound() const { return blk < skip.wand.size() ? bound_of(skip.wand[blk]) : bound_of(skip.root); }
   uint32_t next_block_last() const { return blk < skip.last_doc.size() ? skip.last_doc[blk] : 0xFFFFFFFFu; }
   // Skip the next block entirely (only valid when it has a level-0 entry).
@@ -757,12 +764,12 @@ struct Cursor {
   }
 };
 
-struct QTerm { orc_bm25_term t; uint32_t docs_count; size_t order; };
+struct QTerm { orc_bm25_term t; uint32_t docs_count; size_t order; int form = kFormBm25; };
 
 // Terms of one segment sorted by ascending docs_count (MakeConjunction, conjunction.hpp:520-523).
-std::vector<QTerm> order_terms(const orc_segment& s, const orc_bm25_term* terms, size_t n) {
+std::vector<QTerm> order_terms(const orc_segment& s, const orc_bm25_term* terms, size_t n, int form) {
   std::vector<QTerm> q;
-  for (size_t i = 0; i < n; ++i) q.push_back({terms[i], s.terms[terms[i].term].docs_count, i});
+  for (size_t i = 0; i < n; ++i) q.push_back({terms[i], s.terms[terms[i].term].docs_count, i, form});
   std::stable_sort(q.begin(), q.end(), [](const QTerm& a, const QTerm& b) { return a.docs_count < b.docs_count; });
   return q;
 }
@@ -786,7 +793,7 @@ void topk_dense(const orc_segment& s, uint32_t seg_idx, int kind, const std::vec
     segment_decode_term(s, qt.t.term, docs.data(), freqs.data());
     const float c0 = bm25_num(k1, qt.t.boost, qt.t.idf);
     for (uint32_t i = 0; i < m.docs_count; ++i) {
-      acc[docs[i]] = acc[docs[i]] + bm25_one(freqs[i], s.norm(docs[i]), c0, qt.t.norm_const, qt.t.norm_length);
+      acc[docs[i]] = acc[docs[i]] + bm25_one(freqs[i], s.norm(docs[i]), c0, qt.t.norm_const, qt.t.norm_length, qt.form);
       ++cnt[docs[i]];
     }
     *scored += m.docs_count;
@@ -813,6 +820,7 @@ void topk_windows(const orc_segment& s, uint32_t seg_idx, int kind, const std::v
     Cursor& c = *cur.back();
     c.open(s, qt.t.term, prune);
     c.c0 = bm25_num(k1, qt.t.boost, qt.t.idf);
+    c.form = qt.form;
     c.norm_const = qt.t.norm_const; c.norm_length = qt.t.norm_length;
   }
   float acc[W]; uint8_t cnt[W];
@@ -1003,14 +1011,16 @@ int orc_segment_add_column(orc_segment* s, uint64_t field, int type, const void*
 }
 
 int orc_bm25_topk(orc_segment* const* segs, size_t n_segs, int kind, const orc_bm25_term* terms, size_t n_terms,
-                  float k1, const orc_pred* filt, uint32_t k, float threshold_in, int mode, orc_hit* out,
+                  float k1, float b, const orc_pred* filt, uint32_t k, float threshold_in, int mode, orc_hit* out,
                   uint32_t* n_out, uint64_t* total_matches, uint64_t* postings_scored) {
   if (!k || !n_terms) { *n_out = 0; if (total_matches) *total_matches = 0; return 0; }
+  const int form = score_form(k1, b);
+  if (form != kFormBm25 && mode == 2) mode = 1;   // the index's block-max pairs were chosen for the BM25 form (wand_type(), bm25.cpp:407-418)
   CanonCollector col(k, threshold_in);
   uint64_t scored = 0;
   for (size_t si = 0; si < n_segs; ++si) {
     const orc_segment& s = *segs[si];
-    const auto q = order_terms(s, terms, n_terms);
+    const auto q = order_terms(s, terms, n_terms, form);
     if (mode == 0) topk_dense(s, uint32_t(si), kind, q, k1, filt, col, &scored);
     else topk_windows(s, uint32_t(si), kind, q, k1, filt, mode == 2, col, &scored);
   }
@@ -1227,7 +1237,7 @@ uint32_t orc_synth_term(uint32_t t, uint64_t doc0, uint32_t n, const uint32_t* d
 extern "C" {
 
 int orc_bm25_topk_batch(orc_segment* const* segs, size_t n_segs, int kind, const orc_bm25_term* terms,
-                        const uint32_t* term_off, size_t n_queries, float k1, const orc_pred* filt, uint32_t k,
+                        const uint32_t* term_off, size_t n_queries, float k1, float b, const orc_pred* filt, uint32_t k,
                         float threshold_in, int mode, int threads, orc_hit* out, uint32_t* n_out,
                         uint64_t* total_matches, uint64_t* postings_scored) {
   threads = std::max(threads, 1);
@@ -1238,7 +1248,7 @@ int orc_bm25_topk_batch(orc_segment* const* segs, size_t n_segs, int kind, const
       const size_t q = next.fetch_add(1);
       if (q >= n_queries) break;
       uint64_t scored = 0, tot = 0;
-      orc_bm25_topk(segs, n_segs, kind, terms + term_off[q], term_off[q + 1] - term_off[q], k1, filt, k, threshold_in,
+      orc_bm25_topk(segs, n_segs, kind, terms + term_off[q], term_off[q + 1] - term_off[q], k1, b, filt, k, threshold_in,
                     mode, out + q * size_t(k), n_out + q, &tot, &scored);
       if (total_matches) total_matches[q] = tot;
       scored_all += scored;

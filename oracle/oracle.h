@@ -127,15 +127,17 @@ typedef struct { float idf, norm_const, norm_length, boost; uint32_t term; } orc
  *       2 = block-max pruned (single term: SingleWandIterator semantics; multi-term OR: window
  *           skipping by summed block-max), used for the "pruned == exhaustive" differential.
  * Results: hits sorted by (score desc, seg asc, doc asc); n_out = min(k, matches above threshold_in).
+ * (k1, b) select the scoring form like BM25::PrepareScorer: k1 == 0 BM1 (scores 0), b == 0 BM15, else BM25;
+ * block-max pruning (mode 2) only applies to the BM25 form.
  * Sum order for multi-term: ascending docs_count, ties by position in `terms` (conjunction.hpp:520-523). */
 int orc_bm25_topk(orc_segment* const* segs, size_t n_segs, int kind, const orc_bm25_term* terms,
-                  size_t n_terms, float k1, const orc_pred* filt, uint32_t k, float threshold_in,
+                  size_t n_terms, float k1, float b, const orc_pred* filt, uint32_t k, float threshold_in,
                   int mode, orc_hit* out, uint32_t* n_out, uint64_t* total_matches,
                   uint64_t* postings_scored);
 
 /* Many queries on `threads` host cores (one query per thread at a time). out: n_queries*k hits. */
 int orc_bm25_topk_batch(orc_segment* const* segs, size_t n_segs, int kind, const orc_bm25_term* terms,
-                        const uint32_t* term_off, size_t n_queries, float k1, const orc_pred* filt, uint32_t k,
+                        const uint32_t* term_off, size_t n_queries, float k1, float b, const orc_pred* filt, uint32_t k,
                         float threshold_in, int mode, int threads, orc_hit* out, uint32_t* n_out,
                         uint64_t* total_matches, uint64_t* postings_scored);
 

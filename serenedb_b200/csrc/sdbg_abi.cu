@@ -13,6 +13,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <limits>
 #include <thread>
 #include <vector>
 
@@ -459,7 +460,7 @@ struct TopkPlan {
 struct TopkDevOut { unsigned long long* keys; uint32_t* n_out; unsigned long long* total; };
 
 int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25_term* terms, const uint32_t* term_off,
-             size_t nq, float k1, const sdbg_col_pred* filt, uint32_t k, float threshold_in, TopkDevOut* dev) {
+             size_t nq, float k1, float b, const sdbg_col_pred* filt, uint32_t k, float threshold_in, TopkDevOut* dev) {
   if (!segs || !n_segs || !terms || !term_off || !nq || !k) return SDBG_EINVAL;
   sdbg_ctx* c = segs[0]->ctx;
   if (k > 8192) return fail(c, SDBG_EUNSUPPORTED, "k > 8192");
@@ -554,6 +555,8 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
         d.nblk = s->term_blk_begin[t.term + 1] - d.blk_begin;
         d.c0 = t.boost * (k1 + 1) * t.idf;  // bm25.cpp:224
         d.norm_const = t.norm_const; d.norm_length = t.norm_length;
+        if (k1 == 0.f) d.c0 = 0.f;                                            // BM1: Bm1Score without a filter boost scores 0 (bm25.cpp:118-126)
+        else if (b == 0.f) d.norm_length = std::numeric_limits<float>::quiet_NaN();   // BM15 form (device-side marker, see bm25())
         d.docs_count = s->term_docs[t.term];
         d.root_freq = s->term_max[t.term].freq; d.root_norm = s->term_max[t.term].norm;
       }
@@ -600,7 +603,7 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
     P.work = reinterpret_cast<const uint4*>(static_cast<const char*>(b_qt.p) + qt_pad) + work_done;
     work_done += seg_work[si].size();
     P.k = k; P.cap = pl.cap; P.conjunction = kind == SDBG_QUERY_AND ? 1 : 0;
-    P.wand = (c->wand && s->has_wand) ? c->wand : 0;
+    P.wand = (c->wand && s->has_wand && k1 != 0.f && b != 0.f) ? c->wand : 0;   // the staged block-max pairs are BM25's
     { ProfScope ps_(c, kProfTopk);
       const dim3 grid(unsigned(seg_work[si].size()));
       const bool drive = c->wand >= 2 && kind != SDBG_QUERY_AND;
@@ -659,12 +662,12 @@ extern "C" int sdbg_bm25_collect(uint64_t docs_with_field, uint64_t total_term_f
 }
 
 extern "C" int sdbg_bm25_topk_batch(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25_term* terms,
-                                    const uint32_t* term_off, size_t nq, float k1, const sdbg_col_pred* filt,
+                                    const uint32_t* term_off, size_t nq, float k1, float b, const sdbg_col_pred* filt,
                                     uint32_t k, float threshold_in, sdbg_hit* out, uint32_t* n_out,
                                     uint64_t* total_matches) {
   if (!out || !n_out) return SDBG_EINVAL;
   TopkDevOut dev{};
-  int rc = topk_run(segs, n_segs, kind, terms, term_off, nq, k1, filt, k, threshold_in, &dev);
+  int rc = topk_run(segs, n_segs, kind, terms, term_off, nq, k1, b, filt, k, threshold_in, &dev);
   if (rc) return rc;
   sdbg_ctx* c = segs[0]->ctx;
   const size_t kb = nq * size_t(k) * 8, nb = nq * 4, tb = nq * 8;
@@ -676,8 +679,8 @@ extern "C" int sdbg_bm25_topk_batch(sdbg_segment* const* segs, size_t n_segs, in
   CU(c, cudaMemcpyAsync(h + kb + tb, dev.n_out, nb, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   std::vector<uint64_t> bases(n_segs);
-  uint64_t b = 0;
-  for (size_t si = 0; si < n_segs; ++si) { bases[si] = b; b += segs[si]->n_docs; }
+  uint64_t ord0 = 0;
+  for (size_t si = 0; si < n_segs; ++si) { bases[si] = ord0; ord0 += segs[si]->n_docs; }
   const auto* keys = reinterpret_cast<const unsigned long long*>(h);
   const auto* tot = reinterpret_cast<const unsigned long long*>(h + kb);
   const auto* cnt = reinterpret_cast<const uint32_t*>(h + kb + tb);
@@ -701,11 +704,11 @@ extern "C" int sdbg_bm25_topk_batch(sdbg_segment* const* segs, size_t n_segs, in
 }
 
 extern "C" int sdbg_bm25_topk(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25_term* terms,
-                              size_t n_terms, float k1, const sdbg_col_pred* filt, uint32_t k, float threshold_in,
+                              size_t n_terms, float k1, float b, const sdbg_col_pred* filt, uint32_t k, float threshold_in,
                               sdbg_hit* out, uint32_t* n_out, uint64_t* total_matches, float* threshold_out) {
   const uint32_t off[2] = {0, uint32_t(n_terms)};
   uint64_t tot = 0;
-  const int rc = sdbg_bm25_topk_batch(segs, n_segs, kind, terms, off, 1, k1, filt, k, threshold_in, out, n_out, &tot);
+  const int rc = sdbg_bm25_topk_batch(segs, n_segs, kind, terms, off, 1, k1, b, filt, k, threshold_in, out, n_out, &tot);
   if (rc) return rc;
   if (total_matches) *total_matches = tot;
   if (threshold_out) *threshold_out = (*n_out == k) ? out[k - 1].score : threshold_in;
@@ -724,11 +727,11 @@ __global__ void shift_keys_kernel(const unsigned long long* __restrict__ in, uns
 }  // namespace
 
 extern "C" int sdbg_bm25_topk_batch_device(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25_term* terms,
-                                           const uint32_t* term_off, size_t nq, float k1, const sdbg_col_pred* filt,
+                                           const uint32_t* term_off, size_t nq, float k1, float b, const sdbg_col_pred* filt,
                                            uint32_t k, float threshold_in, uint32_t rank, void* d_keys, void* d_totals) {
   if (!d_keys) return SDBG_EINVAL;
   TopkDevOut dev{};
-  int rc = topk_run(segs, n_segs, kind, terms, term_off, nq, k1, filt, k, threshold_in, &dev);
+  int rc = topk_run(segs, n_segs, kind, terms, term_off, nq, k1, b, filt, k, threshold_in, &dev);
   if (rc) return rc;
   sdbg_ctx* c = segs[0]->ctx;
   // Each rank owns a 2^28-ordinal slot in the merged key space: rank r's docs sort after rank r-1's on ties.

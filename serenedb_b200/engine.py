@@ -319,7 +319,7 @@ def ExecuteTopKBatch(reader, queries, kind, scorer, k, filt=None, threshold=FLT_
     ctx = reader.segments[0].ctx
     fp = C.byref(filt) if filt is not None else None
     N.check(N.lib().sdbg_bm25_topk_batch(_seg_array(reader.segments), len(reader.segments), int(kind), terms,
-                                         _ptr(off), nq, scorer.k, fp, int(k), float(threshold), _ptr(hits),
+                                         _ptr(off), nq, scorer.k, scorer.b, fp, int(k), float(threshold), _ptr(hits),
                                          _ptr(n_out), _ptr(total)), ctx._h)
     return hits, n_out, total
 
@@ -350,7 +350,7 @@ class PreparedBatch:
         r = self.reader
         fp = C.byref(self.filt) if self.filt is not None else None
         N.check(N.lib().sdbg_bm25_topk_batch(_seg_array(r.segments), len(r.segments), self.kind, self.terms,
-                                             _ptr(self.off), self.nq, self.scorer.k, fp, self.k, self.threshold,
+                                             _ptr(self.off), self.nq, self.scorer.k, self.scorer.b, fp, self.k, self.threshold,
                                              _ptr(self.hits), _ptr(self.n_out), _ptr(self.total)), r.segments[0].ctx._h)
         return self.hits, self.n_out, self.total
 
@@ -359,7 +359,7 @@ class PreparedBatch:
         r = self.reader
         fp = C.byref(self.filt) if self.filt is not None else None
         N.check(N.lib().sdbg_bm25_topk_batch_device(_seg_array(r.segments), len(r.segments), self.kind, self.terms,
-                                                    _ptr(self.off), self.nq, self.scorer.k, fp, self.k, self.threshold,
+                                                    _ptr(self.off), self.nq, self.scorer.k, self.scorer.b, fp, self.k, self.threshold,
                                                     int(rank), C.c_void_p(int(d_keys_ptr)),
                                                     C.c_void_p(int(d_totals_ptr)) if d_totals_ptr else None),
                 r.segments[0].ctx._h)

@@ -33,7 +33,7 @@ int main(int argc, char** argv) {
   const uint32_t ids[2] = {2, 5};
   for (int i = 0; i < 2; ++i) { sdbg_bm25_collect(n_docs, sum_dl, dc[ids[i]], 1.2f, 0.75f, &terms[size_t(i)]); terms[size_t(i)].term = ids[i]; }
   sdbg_col_pred filt{}; filt.field = 9; filt.op = SDBG_OP_BETWEEN; filt.lo_i = 250000; filt.hi_i = 749999;
-  sdbg_host::GpuTopKIterator it(seg, SDBG_QUERY_OR, terms, 1.2f, 100, &filt);
+  sdbg_host::GpuTopKIterator it(seg, SDBG_QUERY_OR, terms, 1.2f, 0.75f, 100, &filt);
   ListCollector col;
   irs::ScoreFunction sf; irs::ColumnArgsFetcher fetcher;
   it.Collect(sf, fetcher, col);

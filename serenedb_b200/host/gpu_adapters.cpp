@@ -11,9 +11,9 @@ void check(int rc, const char* what) {
 }
 }  // namespace
 
-GpuTopKIterator::GpuTopKIterator(sdbg_segment* segment, int kind, std::vector<sdbg_bm25_term> terms, float k1, uint32_t k,
-                                 const sdbg_col_pred* table_filter)
-    : seg_(segment), kind_(kind), terms_(std::move(terms)), k1_(k1), k_(k), has_filter_(table_filter != nullptr) {
+GpuTopKIterator::GpuTopKIterator(sdbg_segment* segment, int kind, std::vector<sdbg_bm25_term> terms, float k1, float b,
+                                 uint32_t k, const sdbg_col_pred* table_filter)
+    : seg_(segment), kind_(kind), terms_(std::move(terms)), k1_(k1), b_(b), k_(k), has_filter_(table_filter != nullptr) {
   if (table_filter) filter_ = *table_filter;
   threshold_.value = FLT_MIN;  // doc_collector.hpp:102
 }
@@ -24,7 +24,7 @@ void GpuTopKIterator::run() {
   uint32_t n = 0;
   float thr_out = 0;
   sdbg_segment* segs[1] = {seg_};
-  check(sdbg_bm25_topk(segs, 1, kind_, terms_.data(), terms_.size(), k1_, has_filter_ ? &filter_ : nullptr, k_,
+  check(sdbg_bm25_topk(segs, 1, kind_, terms_.data(), terms_.size(), k1_, b_, has_filter_ ? &filter_ : nullptr, k_,
                        threshold_.value, hits_.data(), &n, &total_, &thr_out),
         "sdbg_bm25_topk");
   hits_.resize(n);

@@ -33,7 +33,8 @@ struct GpuError : std::runtime_error {
 class GpuTopKIterator final : public irs::DocIterator {
  public:
   GpuTopKIterator(sdbg_segment* segment, int kind /* SDBG_QUERY_OR | SDBG_QUERY_AND */,
-                  std::vector<sdbg_bm25_term> terms /* BM25Stats per term + boost */, float k1, uint32_t k,
+                  std::vector<sdbg_bm25_term> terms /* BM25Stats per term + boost */, float k1 /* BM25::k() */,
+                  float b /* BM25::b() */, uint32_t k,
                   const sdbg_col_pred* table_filter /* nullable: the ColFilter wrap */);
 
   // Scored top-k: the hot path.
@@ -55,7 +56,7 @@ class GpuTopKIterator final : public irs::DocIterator {
   sdbg_segment* seg_;
   int kind_;
   std::vector<sdbg_bm25_term> terms_;
-  float k1_;
+  float k1_, b_;
   uint32_t k_;
   bool has_filter_;
   sdbg_col_pred filter_{};

@@ -120,9 +120,9 @@ def lib():
     L.orc_segment_skip_level0.argtypes = [vp, C.c_uint32, vp, vp, vp, vp, u32p, u32p, u32p]
     L.orc_segment_skip_level0.restype = C.c_uint32
     L.orc_segment_add_column.argtypes = [vp, C.c_uint64, C.c_int, vp, vp, C.c_uint64]
-    L.orc_bm25_topk.argtypes = [vp, C.c_size_t, C.c_int, vp, C.c_size_t, C.c_float, vp, C.c_uint32,
+    L.orc_bm25_topk.argtypes = [vp, C.c_size_t, C.c_int, vp, C.c_size_t, C.c_float, C.c_float, vp, C.c_uint32,
                                 C.c_float, C.c_int, vp, u32p, u64p, u64p]
-    L.orc_bm25_topk_batch.argtypes = [vp, C.c_size_t, C.c_int, vp, vp, C.c_size_t, C.c_float, vp, C.c_uint32,
+    L.orc_bm25_topk_batch.argtypes = [vp, C.c_size_t, C.c_int, vp, vp, C.c_size_t, C.c_float, C.c_float, vp, C.c_uint32,
                                       C.c_float, C.c_int, C.c_int, vp, vp, vp, u64p]
     L.orc_synth_segment.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, vp, u64p]
     L.orc_synth_segment.restype = vp
@@ -335,20 +335,20 @@ def term_array(terms):
     return arr
 
 
-def bm25_topk(segs, kind, terms, k, k1=1.2, filt=None, threshold_in=np.finfo(np.float32).tiny, mode=0):
+def bm25_topk(segs, kind, terms, k, k1=1.2, filt=None, threshold_in=np.finfo(np.float32).tiny, mode=0, b=0.75):
     """terms: list of BM25Term. Returns (hits ndarray, total_matches, postings_scored)."""
     hits = np.zeros(max(k, 1), dtype=HIT_DTYPE)
     n_out, total, scored = C.c_uint32(), C.c_uint64(), C.c_uint64()
     fp = C.byref(filt) if filt is not None else None
     rc = lib().orc_bm25_topk(_seg_array(segs), len(segs), 1 if kind in (1, "AND") else 0, term_array(terms),
-                             len(terms), k1, fp, k, threshold_in, mode, ptr(hits), C.byref(n_out),
+                             len(terms), k1, b, fp, k, threshold_in, mode, ptr(hits), C.byref(n_out),
                              C.byref(total), C.byref(scored))
     assert rc == 0
     return hits[:n_out.value].copy(), total.value, scored.value
 
 
 def bm25_topk_batch(segs, kind, queries_terms, k, k1=1.2, filt=None, threshold_in=np.finfo(np.float32).tiny,
-                    mode=2, threads=1):
+                    mode=2, threads=1, b=0.75):
     """queries_terms: list of lists of BM25Term. Returns (hits [Q,k], n_out, total, postings_scored)."""
     nq = len(queries_terms)
     flat = [t for q in queries_terms for t in q]
@@ -360,7 +360,7 @@ def bm25_topk_batch(segs, kind, queries_terms, k, k1=1.2, filt=None, threshold_i
     scored = C.c_uint64()
     fp = C.byref(filt) if filt is not None else None
     rc = lib().orc_bm25_topk_batch(_seg_array(segs), len(segs), 1 if kind in (1, "AND") else 0, term_array(flat),
-                                   ptr(off), nq, k1, fp, k, threshold_in, mode, threads, ptr(hits), ptr(n_out),
+                                   ptr(off), nq, k1, b, fp, k, threshold_in, mode, threads, ptr(hits), ptr(n_out),
                                    ptr(total), C.byref(scored))
     assert rc == 0
     return hits, n_out, total, scored.value

@@ -215,3 +215,26 @@ def test_property_checks_at_scale():
     lo_first = dc[12] <= dc[3]   # sum order: ascending docs_count
     tot = (exp2 + exp) if lo_first else (exp + exp2)
     assert np.array_equal(h_and["score"], tot)
+
+
+@pytest.mark.parametrize("k1,b", [(1.2, 0.0), (0.0, 0.75), (2.0, 1.0)])
+@pytest.mark.parametrize("kind,tis,k", [("OR", [3], 100), ("OR", [0, 4], 1000), ("OR", [2, 5, 6], 300), ("AND", [0, 1, 2], 50)])
+def test_scorer_forms(corpus, k1, b, kind, tis, k):
+    """BM25::PrepareScorer's three forms (bm25.cpp:312-365): b == 0 -> Bm15 (no norms, its own operation
+    order), k == 0 -> Bm1 (all scores 0: no hit beats the FLT_MIN seed, matches still counted), b == 1 -> the
+    BM25 form (BM11). Bit-exact against the oracle with block-max pruning left on (it must disable itself for
+    the non-BM25 forms: the staged pairs are BM25's)."""
+    scorer = sdb.BM25(k1, b)
+    # pruning stays switched on only where it has to disable itself; for (2.0, 1.0) the corpus' block-max pairs
+    # (written for k = 1.2, b = 0.75) would not be valid bounds -- the reference only uses wand data of an
+    # index-time scorer that equals the query's (Scorer::equals), which is the caller's side of has_wand
+    ctx().set_wand(1 if (b == 0.0 or k1 == 0.0) else 0)
+    try:
+        hits, total = sdb.ExecuteTopK(corpus["reader"], tis, sdb.AND if kind == "AND" else sdb.OR, scorer, k)
+    finally:
+        ctx().set_wand(0)
+    oh, ototal, _ = orc.bm25_topk([corpus["oseg"]], kind, oracle_terms(corpus["reader"], scorer, tis), k, k1=k1, b=b, mode=1)
+    assert_hits_equal(hits, oh)
+    if k1 == 0.0:
+        assert len(hits) == 0
+    assert total == ototal

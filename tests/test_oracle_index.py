@@ -155,3 +155,40 @@ def test_hybrid_filter_and_multisegment(corpus):
     h2, t2, _ = orc.bm25_topk([segA, segB], "AND", two, 100, filt=filt, mode=0)
     glob = np.where(h2["seg"] == 0, h2["doc"], h2["doc"] + half)
     assert np.array_equal(glob, ed) and np.array_equal(h2["score"], es) and t2 == etotal
+
+
+def _f32(x):
+    return np.float32(x)
+
+
+@pytest.mark.parametrize("kind,tis", [("OR", [3]), ("OR", [0, 4]), ("AND", [0, 1, 2])])
+def test_bm15_and_bm1_forms(corpus, kind, tis):
+    """b == 0 selects Bm15 (bm25.cpp:70-87: c0 - c0 / (1 + freq / c1), c1 = k, no norms) and k == 0 Bm1
+    (:112-126: every score 0 without a filter boost, so nothing beats the FLT_MIN seed). Numpy float32
+    arithmetic is IEEE single without contraction, i.e. the reference's operation order."""
+    seg, n, total_tf = corpus["seg"], corpus["n"], corpus["total_tf"]
+    k1 = 1.2
+    terms = [_q(seg, t, n, total_tf, k=k1, b=0.0) for t in tis]
+    acc = np.zeros(n + 1, np.float32)
+    cnt = np.zeros(n + 1, np.int32)
+    order = sorted(range(len(tis)), key=lambda i: (len(corpus["lists"][tis[i]][0]), i))
+    for i in order:
+        docs, freqs = corpus["lists"][tis[i]]
+        q = terms[i]
+        assert q.norm_length == 0.0 and q.norm_const == _f32(k1)
+        c0 = _f32(_f32(_f32(q.boost) * _f32(_f32(k1) + _f32(1))) * _f32(q.idf))
+        s = c0 - c0 / (_f32(1) + freqs.astype(np.float32) / _f32(q.norm_const))
+        assert s.dtype == np.float32
+        acc[docs] = acc[docs] + s
+        cnt[docs] += 1
+    m = cnt >= (len(tis) if kind == "AND" else 1)
+    d = np.nonzero(m)[0]
+    o = np.lexsort((d, -acc[d].astype(np.float64)))[:500]
+    for mode in (0, 1, 2):        # mode 2 must fall back to an exhaustive scan: the block-max pairs are BM25's
+        hits, total, _ = orc.bm25_topk([seg], kind, terms, 500, k1=k1, b=0.0, mode=mode)
+        assert np.array_equal(hits["doc"], d[o]) and np.array_equal(hits["score"], acc[d][o]), mode
+        assert total == int(m.sum())
+    # BM1
+    terms0 = [_q(seg, t, n, total_tf, k=0.0, b=0.75) for t in tis]
+    hits, total, _ = orc.bm25_topk([seg], kind, terms0, 500, k1=0.0, b=0.75, mode=0)
+    assert len(hits) == 0 and total == int(m.sum())
