@@ -94,6 +94,10 @@ void sdbg_segment_destroy(sdbg_segment*);
  * 16-byte-aligned block payloads to HBM. */
 int sdbg_stage_postings(sdbg_segment*, const uint8_t* doc_file, size_t n, const sdbg_term_meta* terms,
                         size_t n_terms, int has_wand);
+/* The segment's DocumentMask (index_meta.hpp:39-43: the set of deleted doc ids). Masked docs are neither
+ * scored, collected nor counted by the BM25 calls, like SegmentReaderImpl::mask wrapping the query iterator
+ * (segment_reader_impl.cpp:95-157,318-326; duckdb_search_full_scan.cpp:1898). n == 0 clears the mask. */
+int sdbg_stage_docs_mask(sdbg_segment*, const uint32_t* deleted_docs, size_t n);
 typedef struct { uint8_t byte_size; uint32_t row_count; uint64_t file_offset; } sdbg_norm_rg; /* norm_writer.hpp:41-48 */
 /* Row groups of fixed-width (1/2/4 B) little-endian field lengths; row = doc - 1. */
 int sdbg_stage_norms(sdbg_segment*, const uint8_t* bytes, size_t n, const sdbg_norm_rg* rgs, size_t n_rg);

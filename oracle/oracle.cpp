@@ -414,6 +414,7 @@ struct orc_segment {
   uint32_t norm_width = 0;
   uint64_t norm_sum = 0, norm_nonzero = 0;
   std::map<uint64_t, Column> cols;
+  std::vector<bool> deleted;       // DocumentMask (index_meta.hpp:39-43) as a bitmap over doc ids; empty = none
 
   uint32_t norm(uint32_t doc) const { return norms.empty() ? 1u : norms[doc - 1]; }
   float avg_dl() const {  // NormReader::GetAvg, irs/formats/norm_reader_impl.hpp:83-88
@@ -774,7 +775,10 @@ std::vector<QTerm> order_terms(const orc_segment& s, const orc_bm25_term* terms,
   return q;
 }
 
+// MaskDocIterator (segment_reader_impl.cpp:95-157) sits below the column filter wrap: a deleted doc is never
+// seen by the collector, the filter or the match count.
 inline bool filter_doc(const orc_segment& s, const orc_pred* filt, uint32_t doc) {
+  if (!s.deleted.empty() && s.deleted[doc]) return false;
   if (!filt) return true;
   const Column* c = find_col(s, filt->field);
   if (!c) return false;
@@ -1007,6 +1011,17 @@ int orc_segment_add_column(orc_segment* s, uint64_t field, int type, const void*
   c.data.assign(static_cast<const uint8_t*>(values), static_cast<const uint8_t*>(values) + rows * w);
   if (validity) c.validity.assign(validity, validity + (rows + 63) / 64);
   s->cols[field] = std::move(c);
+  return 0;
+}
+
+int orc_segment_set_docs_mask(orc_segment* s, const uint32_t* deleted_docs, size_t n) {
+  s->deleted.clear();
+  if (!n) return 0;
+  s->deleted.assign(size_t(s->N) + 1, false);
+  for (size_t i = 0; i < n; ++i) {
+    if (deleted_docs[i] == 0 || deleted_docs[i] > s->N) return -1;
+    s->deleted[deleted_docs[i]] = true;
+  }
   return 0;
 }
 

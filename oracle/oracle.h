@@ -106,6 +106,9 @@ uint32_t orc_segment_skip_level0(const orc_segment*, uint32_t term, uint32_t* la
                                  uint32_t* root_freq, uint32_t* root_norm, uint32_t* num_levels);
 /* INCLUDE / table columns. type: 0=int64 1=float64 2=int32. validity may be NULL (all valid);
  * otherwise bit r of validity[r/64] set => row r is NOT NULL. Values are copied. */
+/* DocumentMask of the segment (deleted doc ids): masked docs are not scored, collected or counted by the
+ * BM25 calls (SegmentReaderImpl::mask, segment_reader_impl.cpp:318-326). n == 0 clears. */
+int orc_segment_set_docs_mask(orc_segment*, const uint32_t* deleted_docs, size_t n);
 int orc_segment_add_column(orc_segment*, uint64_t field, int type, const void* values,
                            const uint64_t* validity, uint64_t rows);
 

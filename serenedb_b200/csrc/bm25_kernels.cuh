@@ -27,6 +27,7 @@ struct PostingsDev {
   const uint4* blocks;    // BlockDesc {off16, last_doc, prev_last, packed}
   const uint2* blk_max;   // {freq, norm} per block (block-max pairs), may be null
   const uint8_t* norms;   // fixed-width field lengths, row = doc-1; null => norm = 1
+  const uint32_t* deleted; // DocumentMask as a bitmap, bit `doc` set = deleted (SegmentReaderImpl::mask, segment_reader_impl.cpp:318-326); null = none
   uint32_t norm_width;    // 1, 2 or 4
   uint32_t n_docs;
   uint32_t ordinal_base;  // first global ordinal of this segment (keys carry base + doc)
@@ -644,7 +645,7 @@ bm25_topk_kernel(const TopkParams P) {
     const uint32_t n_entries = n_items * 128u;
     const uint32_t emit_begin = P.conjunction ? s_phase[buf][T - 1u] * 128u : 0u;  // AND: only the last term's slots can be complete (never in driver mode)
     bool first_pass = true;
-    const bool plain = !P.conjunction && P.filt.values == nullptr;   // disjunction without a table filter: 4 entries per lane
+    const bool plain = !P.conjunction && P.filt.values == nullptr && P.seg.deleted == nullptr;   // disjunction, no table filter, no deletes: 4 entries per lane
     for (;;) {
       const unsigned long long theta = s_theta;
       const uint32_t theta_hi = uint32_t(theta >> 32);
@@ -691,6 +692,7 @@ bm25_topk_kernel(const TopkParams P) {
         const uint32_t d = e < n_entries ? e_doc[e] : kPadDoc;
         bool live = d - lo <= hi - lo;                       // in window, not padding / folded / already stored
         if (live && P.conjunction) live = e_cnt[e] == T - 1u;
+        if (live && P.seg.deleted != nullptr) live = ((__ldg(P.seg.deleted + (d >> 5)) >> (d & 31u)) & 1u) == 0u;   // MaskDocIterator: neither scored nor counted
         if (live && P.filt.values != nullptr) live = filter_pass(P.filt, d);
         // cheap pre-test on the score bits alone; the full 64-bit key only for the few that may qualify
         const uint32_t sbits = live ? __float_as_uint(e_score[e]) : 0u;

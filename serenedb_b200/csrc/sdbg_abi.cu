@@ -85,6 +85,9 @@ struct sdbg_segment {
   // norms
   void* d_norms = nullptr;
   uint32_t norm_width = 0;
+  // deleted docs (DocumentMask) as a bitmap over doc ids 0..n_docs
+  void* d_deleted = nullptr;
+  uint64_t n_deleted = 0;
   // columns
   std::map<uint64_t, ColumnObj> cols;
 };
@@ -271,8 +274,30 @@ extern "C" void sdbg_segment_destroy(sdbg_segment* s) {
   cudaStreamSynchronize(s->ctx->stream);
   free_postings(s);
   if (s->d_norms) cudaFree(s->d_norms);
+  if (s->d_deleted) cudaFree(s->d_deleted);
   for (auto& kv : s->cols) free_column(kv.second);
   delete s;
+}
+
+extern "C" int sdbg_stage_docs_mask(sdbg_segment* s, const uint32_t* deleted_docs, size_t n) {
+  if (!s || (!deleted_docs && n)) return SDBG_EINVAL;
+  sdbg_ctx* c = s->ctx;
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (s->d_deleted) { CU(c, cudaFree(s->d_deleted)); s->d_deleted = nullptr; }
+  s->n_deleted = 0;
+  if (!n) return SDBG_OK;
+  std::vector<uint32_t> bits((size_t(s->n_docs) + 32) / 32 + 1, 0u);
+  for (size_t i = 0; i < n; ++i) {
+    const uint32_t d = deleted_docs[i];
+    if (d == 0 || d > s->n_docs) return fail(c, SDBG_EINVAL, "deleted doc id outside 1..docs_count");
+    if (!((bits[d >> 5] >> (d & 31u)) & 1u)) ++s->n_deleted;
+    bits[d >> 5] |= 1u << (d & 31u);
+  }
+  CU(c, cudaMalloc(&s->d_deleted, bits.size() * 4));
+  CU(c, cudaMemcpyAsync(s->d_deleted, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return SDBG_OK;
 }
 
 namespace {
@@ -435,6 +460,7 @@ PostingsDev postings_view(const sdbg_segment* s, uint32_t ordinal_base) {
   p.blk_max = static_cast<const uint2*>(s->d_blkmax);
   p.norms = static_cast<const uint8_t*>(s->d_norms);
   p.norm_width = s->norm_width;
+  p.deleted = static_cast<const uint32_t*>(s->d_deleted);
   p.n_docs = s->n_docs;
   p.ordinal_base = ordinal_base;
   return p;
@@ -460,7 +486,7 @@ struct TopkPlan {
 struct TopkDevOut { unsigned long long* keys; uint32_t* n_out; unsigned long long* total; };
 
 int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25_term* terms, const uint32_t* term_off,
-             size_t nq, float k1, float b, const sdbg_col_pred* filt, uint32_t k, float threshold_in, TopkDevOut* dev) {
+             size_t nq, float k1, const float b, const sdbg_col_pred* filt, uint32_t k, float threshold_in, TopkDevOut* dev) {
   if (!segs || !n_segs || !terms || !term_off || !nq || !k) return SDBG_EINVAL;
   sdbg_ctx* c = segs[0]->ctx;
   if (k > 8192) return fail(c, SDBG_EUNSUPPORTED, "k > 8192");
@@ -521,7 +547,7 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
   const uint32_t total_lists = list_off[nq];
   size_t total_work = 0;
   for (auto& w : seg_work) {
-    std::stable_sort(w.begin(), w.end(), [](const WorkItem& a, const WorkItem& b) { return a.weight > b.weight; });
+    std::stable_sort(w.begin(), w.end(), [](const WorkItem& x, const WorkItem& y) { return x.weight > y.weight; });
     total_work += w.size();
   }
   pl.smem = size_t(entries) * 8 + (kind == SDBG_QUERY_AND ? entries : 0) + size_t(pl.cap) * 8 + (c->wand >= 2 ? size_t(entries) * 2 : 0);
@@ -546,8 +572,8 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
     const sdbg_segment* s = segs[si];
     QTermDev* dst = h_qt + si * total_terms;
     for (size_t q = 0; q < nq; ++q) {
-      const uint32_t b = term_off[q], e = term_off[q + 1];
-      for (uint32_t i = b; i < e; ++i) {
+      const uint32_t t_begin = term_off[q], t_end = term_off[q + 1];
+      for (uint32_t i = t_begin; i < t_end; ++i) {
         const sdbg_bm25_term& t = terms[i];
         if (t.term + 1 >= s->term_blk_begin.size()) return fail(c, SDBG_EINVAL, "term id out of range");
         QTermDev& d = dst[i];
@@ -560,7 +586,7 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
         d.docs_count = s->term_docs[t.term];
         d.root_freq = s->term_max[t.term].freq; d.root_norm = s->term_max[t.term].norm;
       }
-      std::stable_sort(dst + b, dst + e, [](const QTermDev& x, const QTermDev& y) { return x.docs_count < y.docs_count; });
+      std::stable_sort(dst + t_begin, dst + t_end, [](const QTermDev& x, const QTermDev& y) { return x.docs_count < y.docs_count; });
     }
   }
   DevBuf& b_qt = c->scratch[0]; DevBuf& b_theta = c->scratch[1]; DevBuf& b_cand = c->scratch[2];

@@ -206,6 +206,11 @@ class Segment:
             vv = _ptr(validity)
         N.check(N.lib().sdbg_stage_column(self._h, int(field), t, vp, vv, int(rows)), self.ctx._h)
 
+    def stage_docs_mask(self, deleted_docs):
+        """DocumentMask of the segment: doc ids that queries must neither score nor count (None / empty clears)."""
+        d = np.ascontiguousarray(deleted_docs if deleted_docs is not None else [], dtype=np.uint32)
+        N.check(N.lib().sdbg_stage_docs_mask(self._h, _ptr(d) if len(d) else None, len(d)), self.ctx._h)
+
     def stage_column_device(self, field, device_ptr, dtype, rows):
         N.check(N.lib().sdbg_stage_column_device(self._h, int(field), TYPES[np.dtype(dtype)],
                                                  C.c_void_p(int(device_ptr)), int(rows)), self.ctx._h)

@@ -120,6 +120,7 @@ def lib():
     L.orc_segment_skip_level0.argtypes = [vp, C.c_uint32, vp, vp, vp, vp, u32p, u32p, u32p]
     L.orc_segment_skip_level0.restype = C.c_uint32
     L.orc_segment_add_column.argtypes = [vp, C.c_uint64, C.c_int, vp, vp, C.c_uint64]
+    L.orc_segment_set_docs_mask.argtypes = [vp, vp, C.c_size_t]
     L.orc_bm25_topk.argtypes = [vp, C.c_size_t, C.c_int, vp, C.c_size_t, C.c_float, C.c_float, vp, C.c_uint32,
                                 C.c_float, C.c_int, vp, u32p, u64p, u64p]
     L.orc_bm25_topk_batch.argtypes = [vp, C.c_size_t, C.c_int, vp, vp, C.c_size_t, C.c_float, C.c_float, vp, C.c_uint32,
@@ -309,6 +310,11 @@ class Segment:
                                           C.byref(rn), C.byref(nl))
         return dict(last_doc=last[:n], doc_ptr=dptr[:n], wand_freq=wf[:n], wand_norm=wn[:n],
                     root=(rf.value, rn.value), num_levels=nl.value)
+
+    def set_docs_mask(self, deleted_docs):
+        d = np.ascontiguousarray(deleted_docs, dtype=np.uint32)
+        rc = lib().orc_segment_set_docs_mask(self.h, ptr(d) if len(d) else None, len(d))
+        assert rc == 0
 
     def add_column(self, field, values, validity=None):
         values = np.ascontiguousarray(values)

@@ -238,3 +238,37 @@ def test_scorer_forms(corpus, k1, b, kind, tis, k):
     if k1 == 0.0:
         assert len(hits) == 0
     assert total == ototal
+
+
+def test_docs_mask(corpus):
+    """DocumentMask: deleted docs are neither scored nor counted (SegmentReaderImpl::mask). OR, AND, hybrid
+    filter and pruning on, bit-exact against the oracle; clearing the mask restores the full result."""
+    n = corpus["n"]
+    rng = np.random.default_rng(41)
+    deleted = np.unique(rng.integers(1, n + 1, size=n // 4)).astype(np.uint32)
+    scorer = sdb.BM25()
+    corpus["oseg"].set_docs_mask(deleted)
+    corpus["gseg"].stage_docs_mask(deleted)
+    try:
+        for wand in (0, 1):
+            ctx().set_wand(wand)
+            for kind, tis, k in (("OR", [0, 4], 1000), ("OR", [3], 100), ("AND", [0, 1, 2], 50), ("OR", [2, 5, 6], 300)):
+                hits, total = sdb.ExecuteTopK(corpus["reader"], tis, sdb.AND if kind == "AND" else sdb.OR, scorer, k)
+                oh, ototal, _ = orc.bm25_topk([corpus["oseg"]], kind, oracle_terms(corpus["reader"], scorer, tis), k, mode=1)
+                assert_hits_equal(hits, oh)
+                assert not np.isin(hits["doc"], deleted).any()
+                if wand == 0 or len(tis) > 1:
+                    assert total == ototal
+        ctx().set_wand(0)
+        filt = sdb.pred(9, "BETWEEN", 250000, 749999)
+        hits, total = sdb.ExecuteTopK(corpus["reader"], [0, 1], sdb.OR, scorer, 500, filt=filt)
+        oh, ototal, _ = orc.bm25_topk([corpus["oseg"]], "OR", oracle_terms(corpus["reader"], scorer, [0, 1]), 500,
+                                      filt=orc.make_pred(9, "BETWEEN", 250000, 749999), mode=1)
+        assert_hits_equal(hits, oh)
+        assert total == ototal
+    finally:
+        ctx().set_wand(0)
+        corpus["oseg"].set_docs_mask([])
+        corpus["gseg"].stage_docs_mask(None)
+    hits, total = sdb.ExecuteTopK(corpus["reader"], [3], sdb.OR, scorer, 10)
+    assert total == len(corpus["lists"][3][0])

@@ -192,3 +192,26 @@ def test_bm15_and_bm1_forms(corpus, kind, tis):
     terms0 = [_q(seg, t, n, total_tf, k=0.0, b=0.75) for t in tis]
     hits, total, _ = orc.bm25_topk([seg], kind, terms0, 500, k1=0.0, b=0.75, mode=0)
     assert len(hits) == 0 and total == int(m.sum())
+
+
+def test_docs_mask(corpus):
+    """Deleted docs (DocumentMask) are invisible to scoring, the collector and the match count
+    (MaskDocIterator wraps the query iterator, segment_reader_impl.cpp:95-157,318-326)."""
+    seg, n, total_tf = corpus["seg"], corpus["n"], corpus["total_tf"]
+    rng = np.random.default_rng(31)
+    deleted = np.unique(rng.integers(1, n + 1, size=n // 3)).astype(np.uint32)
+    keep = np.ones(n, bool)
+    keep[deleted - 1] = False
+    seg.set_docs_mask(deleted)
+    try:
+        for kind, tis, k in (("OR", [0, 4], 100), ("AND", [0, 1, 2], 50), ("OR", [7], 5000)):
+            terms = [_q(seg, t, n, total_tf) for t in tis]
+            ed, es, etotal = _expected_topk(corpus, kind, tis, k, filt_mask=keep)
+            for mode in (0, 1, 2):
+                hits, total, _ = orc.bm25_topk([seg], kind, terms, k, mode=mode)
+                assert np.array_equal(hits["doc"], ed) and np.array_equal(hits["score"], es), (kind, mode)
+                assert total == etotal if mode < 2 else total <= etotal
+    finally:
+        seg.set_docs_mask([])
+    hits, total, _ = orc.bm25_topk([seg], "OR", [_q(seg, 0, n, total_tf)], 10)
+    assert total == len(corpus["lists"][0][0])        # cleared
