@@ -490,7 +490,7 @@ def main():
             "metric": "BM25 top-1000, 2-term OR batch: postings scanned per second (BASELINE.json configs[2])",
             "value": round(world * postings / (bm_ms * 1e-3) / 1e6, 1), "unit": "Mdocs/s", "ms_per_step": round(bm_ms, 3),
             "corpus_docs_per_s_M": round(world * n_docs * nq / (bm_ms * 1e-3) / 1e6, 1),
-            "config": {"workload": "bm25: %d docs/GPU synthetic Zipf corpus, %d two-term OR queries/step over %d terms, top-%d, exhaustive scan of both lists (block-max pruning level 1 acts on single-term queries only)"
+            "config": {"workload": "bm25: %d docs/GPU synthetic Zipf corpus, %d two-term OR queries/step over %d terms, top-%d, block-max pruning level 2: queries whose largest list is bitset-encoded (dense terms) probe it per candidate instead of scanning it, all other lists are scanned in full"
                                    % (n_docs, nq, N_TERMS, TOPK), "postings_per_step": postings,
                        "l2": "256 MB write between timed steps (index ~L2-sized)"},
             "e2e": {"value": round(world * postings / (be_ms * 1e-3) / 1e6, 1), "unit": "Mdocs/s",

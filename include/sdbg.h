@@ -62,9 +62,12 @@ int sdbg_sync(sdbg_ctx*);
 uint64_t sdbg_launch_count(const sdbg_ctx*);
 /* Block-max (WAND / MaxScore) pruning, the `WandContext` of irs::ExecuteTopK (doc_collector.hpp:88). On by
  * default when the segment carries block-max data; results (hits) are identical either way, but with
- * pruning total_matches is a lower bound (wand_scoring_test.cpp:382-384). Level 1 (default): blocks / windows
- * whose block-max bound cannot beat the threshold are dropped while planning; level 2 additionally tests the
- * largest term's blocks against the exact partial scores of the smaller terms (MaxScore-style). 0 = off. */
+ * pruning total_matches is a lower bound (wand_scoring_test.cpp:382-384). Level 1: blocks / windows whose
+ * block-max bound cannot beat the threshold are dropped while planning (single-term queries:
+ * SingleWandIterator's skip). Level 2 (default) adds MaxScore's essential / non-essential split for
+ * disjunctions (max_score_iterator.hpp:406-508): once the threshold exceeds the global bound of the
+ * largest list, that list is no longer scanned but probed per surviving candidate -- used for queries whose
+ * largest list is bitset-encoded (a probe is then a bit test + popcount rank, no block decode). 0 = off. */
 int sdbg_set_wand(sdbg_ctx*, int level);
 /* Per-kernel device timing for roofline reports: when enabled, a CUDA event pair is recorded on the
  * context's stream around each hot kernel launch. kernel_id: 0 filter_groupby, 1 bm25_topk,

@@ -49,7 +49,8 @@ struct QTermDev {  // one term of one query, 32 bytes
   float norm_const;
   float norm_length;
   uint32_t docs_count;
-  uint32_t root_freq, root_norm;   // block-max pair of the whole list (0,0 = unknown)
+  uint32_t root_freq, root_norm;   // block-max pair of the whole list (0,0 = unknown); bit 31 of root_freq: the list's blocks
+                                   // are bitsets with random-access freqs, i.e. cheap to probe (driver mode is worth it)
 };
 
 constexpr uint32_t kMaxQueryTerms = 16;
@@ -305,6 +306,54 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* a, uint32_t 
   return pos;
 }
 
+// ---- random access into one block (driver-mode probes) ----
+// Frequency of posting `i` of the block without decoding the rest; false when the encoding is sequential
+// (StreamVByte tails) and the caller has to decode the block.
+__device__ __forceinline__ bool freq_at(const uint4* arena, const uint4& d, uint32_t i, uint32_t& f) {
+  const uint4* p = arena + d.x + desc_fdelta(d.w);
+  const uint32_t enc = desc_freq_enc(d.w);
+  if (enc >= 5u) {                                   // e_bitpack_b: value i = row i>>2 of lane stream i&3
+    const uint32_t b = enc - 4u, bit = (i >> 2) * b, w = bit >> 5, sh = bit & 31u;
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p) + (i & 3u);
+    const uint32_t lo = __ldg(q + 4u * w), hi = __ldg(q + 4u * min(w + 1u, b - 1u));
+    f = __funnelshift_r(lo, hi, sh) & ((1u << b) - 1u);
+    return true;
+  }
+  if (enc >= 1u && enc <= 3u) { f = same_value(p, enc); return true; }
+  if (enc == 0u) { f = __ldg(reinterpret_cast<const uint32_t*>(p) + i); return true; }
+  return false;
+}
+// Membership + rank of doc `doc` in a de_for_bitset block (bit j set <=> id prev + j): O(words) popcounts.
+__device__ __forceinline__ bool bitset_rank(const uint4* arena, const uint4& d, uint32_t doc, uint32_t& rank) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(arena + d.x);
+  const uint32_t j = doc - d.z, chunk = j >> 5;
+  if (chunk >= 2u * desc_words(d.w)) return false;
+  const uint32_t mine = __ldg(w + chunk);
+  if (!((mine >> (j & 31u)) & 1u)) return false;
+  uint32_t r = __popc(mine & ((1u << (j & 31u)) - 1u));
+  for (uint32_t c = 0; c < chunk; ++c) r += __popc(__ldg(w + c));
+  rank = r;
+  return true;
+}
+// First block in [b0, b1) whose last doc is >= doc, searched outwards from `guess` (b1 when none).
+__device__ __forceinline__ uint32_t find_block_from(const uint4* LB, uint32_t b0, uint32_t b1, uint32_t guess, uint32_t doc) {
+  uint32_t l, r;                                       // answer in [l, r]
+  if (__ldg(&LB[guess].y) >= doc) {                    // answer <= guess: gallop down
+    r = guess; l = b0;
+    for (uint32_t step = 1u; r - b0 >= step; step <<= 1) {
+      if (__ldg(&LB[r - step].y) >= doc) r -= step; else { l = r - step + 1u; break; }
+    }
+  } else {                                             // answer > guess: gallop up
+    l = guess + 1u; r = b1;
+    for (uint32_t step = 1u; l + step - 1u < b1; step <<= 1) {
+      if (__ldg(&LB[l + step - 1u].y) < doc) l += step; else { r = l + step - 1u; break; }
+    }
+    l = min(l, b1);
+  }
+  while (l < r) { const uint32_t mid = (l + r) >> 1; if (__ldg(&LB[mid].y) < doc) l = mid + 1u; else r = mid; }
+  return l;
+}
+
 // kDrive compiles the driver-mode code (pruning level 2) in; the default kernel stays free of its registers.
 template <uint32_t kBudget, bool kDrive>
 __global__ void __launch_bounds__(kTopkThreads)
@@ -316,7 +365,7 @@ bm25_topk_kernel(const TopkParams P) {
   float* e_score = reinterpret_cast<float*>(e_doc + kEntries);
   uint8_t* e_cnt = reinterpret_cast<uint8_t*>(e_score + kEntries);
   unsigned long long* cand = reinterpret_cast<unsigned long long*>(e_cnt + (P.conjunction ? kEntries : 0u));
-  uint16_t* s_probe = reinterpret_cast<uint16_t*>(cand + P.cap);   // kEntries u16, only present at wand level 2
+  uint16_t* s_probe = reinterpret_cast<uint16_t*>(cand + P.cap);   // 2 * kEntries u16 (probe list | decode-fallback list), only present at wand level 2
 
   __shared__ __align__(16) uint32_t stage[kTopkWarps][128];
   __shared__ __align__(16) uint4 s_item[2][32];        // descriptors of the window's blocks, term-major
@@ -326,7 +375,7 @@ bm25_topk_kernel(const TopkParams P) {
   __shared__ float s_item_bound[2][32];                // block-max upper bound of each item (+inf when unknown)
   __shared__ uint32_t s_driver;                        // 1: the largest list is probed per candidate instead of scanned
   __shared__ uint32_t s_Lb0[2], s_Lb1[2];              // block range of the largest list that covers the window (driver mode)
-  __shared__ uint32_t s_nprobe;
+  __shared__ uint32_t s_nprobe, s_nslow;
   __shared__ float s_ubL;                              // global block-max bound of the largest list
   __shared__ float s_term_ub[2][kMaxQueryTerms];       // max bound over the term's blocks in the window (0 if none)
   __shared__ uint32_t s_cursor[kMaxQueryTerms];
@@ -371,7 +420,9 @@ bm25_topk_kernel(const TopkParams P) {
   if (tid == 0) {
     s_driver = 0u;
     const QTermDev& L = s_qt[T - 1u];
-    s_ubL = (can_drive && L.root_freq != 0u) ? bm25(L.root_freq, L.root_norm, L.c0, L.norm_const, L.norm_length)
+    // driver mode only for a probe-friendly largest list: a probe into a bit-packed block costs a block decode
+    s_ubL = (can_drive && (L.root_freq >> 31) && (L.root_freq & 0x7FFFFFFFu) != 0u)
+                ? bm25(L.root_freq & 0x7FFFFFFFu, L.root_norm, L.c0, L.norm_const, L.norm_length)
                                               : __int_as_float(0x7f800000);
   }
   __syncthreads();
@@ -590,12 +641,50 @@ bm25_topk_kernel(const TopkParams P) {
       const uint4* LB = P.seg.blocks + L.blk_begin;
       const uint32_t Lb0 = s_Lb0[buf], Lb1 = s_Lb1[buf];
       const uint32_t n_probe = s_nprobe;
+      // (i) one candidate per lane: locate its block of L (interpolated guess + gallop: L's blocks are near
+      // uniform in doc space), block-max test, then membership + rank straight from the bitset and a
+      // random-access frequency -- no block decode. Candidates in blocks with other encodings are queued
+      // (second half of s_probe) for the warp-cooperative decode below.
+      if (tid == 0) s_nslow = 0u;
+      __syncthreads();
+      for (uint32_t c = tid; c < n_probe; c += blockDim.x) {
+        const uint32_t e = s_probe[c];
+        const uint32_t d = e_doc[e];
+        const float partial = e_score[e];
+        if (Lb1 == Lb0) continue;
+        const uint32_t nb = Lb1 - Lb0;
+        const uint32_t guess = Lb0 + min(nb - 1u, uint32_t((static_cast<unsigned long long>(d - lo) * nb) / (static_cast<unsigned long long>(hi - lo) + 1ull)));
+        const uint32_t bl = find_block_from(LB, Lb0, Lb1, guess, d);
+        if (bl >= Lb1) continue;                                          // beyond L's last block in the window
+        const uint4 pd = ld_ro_v4(LB + bl);
+        if (!(pd.z < d)) continue;
+        const uint2 fn = __ldg(P.seg.blk_max + L.blk_begin + bl);
+        if (fn.x != 0u && __fadd_rn(partial, bm25(fn.x, fn.y, L.c0, L.norm_const, L.norm_length)) < thr) {
+          e_doc[e] = kPadDoc;                                             // cannot qualify even with this block's best
+          continue;
+        }
+        uint32_t rank = 0, fr = 0;
+        bool fast = false;
+        if (desc_doc_enc(pd.w) == 4u) {
+          if (!bitset_rank(P.seg.arena, pd, d, rank)) continue;           // doc not in L: the driver score stands
+          fast = freq_at(P.seg.arena, pd, rank, fr);
+        }
+        if (fast) {
+          const float sL = bm25(fr, load_norm(P.seg.norms, P.seg.norm_width, d), L.c0, L.norm_const, L.norm_length);
+          e_score[e] = __fadd_rn(partial, sL);                            // L is last in ascending-cost order
+        } else {
+          s_probe[kEntries + atomicAdd(&s_nslow, 1u)] = uint16_t(e);      // second half of s_probe
+        }
+      }
+      __syncthreads();
+      const uint32_t n_slow = s_nslow;
       uint32_t have_blk = 0xFFFFFFFFu;
       uint32_t pdoc[4], pf[4];
       bool have_f = false;
       uint4 pd = make_uint4(0, 0, 0, 0);
-      for (uint32_t c = warp; c < n_probe; c += kTopkWarps) {
-        const uint32_t e = s_probe[c];
+      // (ii) warp per remaining candidate: decode its block
+      for (uint32_t c = warp; c < n_slow; c += kTopkWarps) {
+        const uint32_t e = s_probe[kEntries + c];
         const uint32_t d = e_doc[e];
         const float partial = e_score[e];
         // 32-ary search over L's blocks [Lb0, Lb1): first block with last_doc >= d

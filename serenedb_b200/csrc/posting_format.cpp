@@ -361,7 +361,7 @@ bool read_pair(const uint8_t*& p, const uint8_t* end, MaxPair* m) {  // FreqNorm
 std::string stage_postings(const uint8_t* doc, size_t n, const TermMeta* terms, size_t n_terms, bool has_wand,
                            StagedPostings* sp) {
   sp->arena.clear(); sp->blocks.clear(); sp->blk_max.clear(); sp->term_max.clear();
-  sp->term_blk_begin.assign(1, 0); sp->term_docs.clear(); sp->term_bytes.clear();
+  sp->term_blk_begin.assign(1, 0); sp->term_docs.clear(); sp->term_bytes.clear(); sp->term_probe.clear();
   sp->n_postings = 0; sp->has_wand = has_wand;
   Arena arena{sp->arena};
   const uint8_t* const end = doc + n;
@@ -374,6 +374,7 @@ std::string stage_postings(const uint8_t* doc, size_t n, const TermMeta* terms, 
     sp->n_postings += cnt;
     MaxPair root{0, 0};
     uint64_t enc_bytes = 0;
+    uint32_t direct_blocks = 0;   // blocks a probe can answer without a decode
     const size_t first_block = sp->blocks.size();
     if (cnt == 1) {
       // Single-doc terms live in the term meta (iterator_score.hpp:1015-1030); give them one raw block.
@@ -424,6 +425,7 @@ std::string stage_postings(const uint8_t* doc, size_t n, const TermMeta* terms, 
         prev_last = b.last_doc;
         sp->blocks.push_back(b);
         sp->blk_max.push_back(MaxPair{0, 0});
+        if (denc == kDeBitset && fenc != kESvb) ++direct_blocks;
         p = fp + 1 + fsz;
         enc_bytes += 2 + dsz + fsz;
       }
@@ -458,6 +460,10 @@ std::string stage_postings(const uint8_t* doc, size_t n, const TermMeta* terms, 
     }
     sp->term_max.push_back(root);
     sp->term_bytes.push_back(enc_bytes);
+    {
+      const size_t nb = sp->blocks.size() - first_block;
+      sp->term_probe.push_back(nb >= 8 && direct_blocks * 16 >= nb * 15 ? 1 : 0);   // >= 15/16 of the blocks
+    }
     sp->term_blk_begin.push_back(uint32_t(sp->blocks.size()));
   }
   sp->arena.resize(sp->arena.size() + 1024, 0);  // slack so 16-byte over-reads of the last block stay in bounds

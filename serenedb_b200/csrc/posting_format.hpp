@@ -144,6 +144,8 @@ struct StagedPostings {
   std::vector<MaxPair> blk_max;        // per block; blocks without a skip entry carry the term's root pair
   std::vector<MaxPair> term_max;       // per term root pair ({0,0} when !has_wand)
   std::vector<uint64_t> term_bytes;    // per term: encoded block bytes in the .doc stream (headers + payloads)
+  std::vector<uint8_t> term_probe;     // per term: 1 when (nearly) every full block is a bitset with random-access freqs
+                                       // (a doc can be looked up without decoding the block: driver-mode probes)
   uint64_t n_postings = 0;
   bool has_wand = false;
 };

@@ -52,6 +52,8 @@ struct sdbg_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;          // second lane for the top-k launch pair (driver-mode / plain chains)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
   uint64_t launches = 0;
@@ -79,6 +81,7 @@ struct sdbg_segment {
   void* d_blkmax = nullptr;
   std::vector<uint32_t> term_blk_begin, term_docs;
   std::vector<MaxPair> term_max;
+  std::vector<uint8_t> term_probe;
   std::vector<uint64_t> term_bytes;
   uint64_t arena_bytes = 0, n_blocks = 0, n_postings = 0;
   bool has_wand = false;
@@ -176,8 +179,11 @@ extern "C" int sdbg_init(int device, sdbg_ctx** out) {
   auto* c = new sdbg_ctx;
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
-  c->wand = std::max(0, std::min(2, env_int("SDBG_WAND", 1)));
+  c->wand = std::max(0, std::min(2, env_int("SDBG_WAND", 2)));
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
     delete c;
     return SDBG_ECUDA;
@@ -193,7 +199,10 @@ extern "C" void sdbg_destroy(sdbg_ctx* c) {
   for (auto& b : c->scratch) if (b.p) cudaFree(b.p);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->flush) cudaFree(c->flush);
+  cudaStreamSynchronize(c->stream2);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+  cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
+  cudaStreamDestroy(c->stream2);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -315,6 +324,7 @@ int upload_postings(sdbg_segment* s, const StagedPostings& sp) {
   s->term_blk_begin = sp.term_blk_begin;
   s->term_docs = sp.term_docs;
   s->term_max = sp.term_max;
+  s->term_probe = sp.term_probe;
   s->term_bytes = sp.term_bytes;
   s->arena_bytes = sp.arena.size();
   s->n_blocks = sp.blocks.size();
@@ -525,7 +535,9 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
     for (uint32_t i = 0; i < total_terms; ++i)
       if (terms[i].term < segs[si]->term_docs.size()) batch_postings += segs[si]->term_docs[terms[i].term];
   const uint64_t chain_target = std::max<uint64_t>(uint64_t(env_int("SDBG_TOPK_CHAIN_MIN", 65536)), batch_postings / (uint64_t(c->sm_count) * uint64_t(std::max(1, env_int("SDBG_TOPK_CHAIN_DIV", 4)))));
-  struct WorkItem { uint32_t q, g, chunk, list; uint64_t weight; };
+  struct WorkItem { uint32_t q, g, chunk, list; uint64_t weight; bool drive; };
+  const bool level2 = c->wand >= 2 && kind != SDBG_QUERY_AND && k1 != 0.f && b != 0.f;
+  std::vector<size_t> n_drive(n_segs, 0);
   std::vector<std::vector<WorkItem>> seg_work(n_segs);
   std::vector<uint32_t> list_off(nq + 1, 0);
   for (size_t q = 0; q < nq; ++q) {          // lists of one query are contiguous: [segment 0 chains | segment 1 chains | ...]
@@ -533,13 +545,22 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
     for (size_t si = 0; si < n_segs; ++si) {
       const sdbg_segment* s = segs[si];
       uint64_t postings = 0;
+      uint32_t largest = 0, largest_term = UINT32_MAX;
       for (uint32_t i = term_off[q]; i < term_off[q + 1]; ++i)
-        if (terms[i].term < s->term_docs.size()) postings += s->term_docs[terms[i].term];
+        if (terms[i].term < s->term_docs.size()) {
+          postings += s->term_docs[terms[i].term];
+          if (s->term_docs[terms[i].term] >= largest) { largest = s->term_docs[terms[i].term]; largest_term = terms[i].term; }
+        }
+      // Driver mode (pruning level 2) pays only when the largest list can be probed without decoding blocks; the
+      // other queries run the plain kernel, which is lighter (fewer registers, no probe buffers, level-1 planner).
+      const bool drive_q = level2 && s->has_wand && term_off[q + 1] - term_off[q] >= 2 && largest_term < s->term_probe.size() &&
+                           s->term_probe[largest_term] != 0;
       uint32_t g = uint32_t(std::max<uint64_t>(pl.G, (postings + chain_target - 1) / chain_target));
       g = std::min(g, max_chains);
       g = std::min(g, std::max(1u, s->n_docs / 4096u));
       const uint32_t chunk = (s->n_docs + g - 1) / g;
-      for (uint32_t j = 0; j < g; ++j) seg_work[si].push_back({uint32_t(q), j, chunk, list_off[q] + lists + j, postings / g});
+      for (uint32_t j = 0; j < g; ++j) seg_work[si].push_back({uint32_t(q), j, chunk, list_off[q] + lists + j, postings / g, drive_q});
+      if (drive_q) n_drive[si] += g;
       lists += g;
     }
     list_off[q + 1] = list_off[q] + lists;
@@ -547,11 +568,12 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
   const uint32_t total_lists = list_off[nq];
   size_t total_work = 0;
   for (auto& w : seg_work) {
-    std::stable_sort(w.begin(), w.end(), [](const WorkItem& x, const WorkItem& y) { return x.weight > y.weight; });
+    std::stable_sort(w.begin(), w.end(), [](const WorkItem& x, const WorkItem& y) { return x.drive != y.drive ? x.drive : x.weight > y.weight; });
     total_work += w.size();
   }
-  pl.smem = size_t(entries) * 8 + (kind == SDBG_QUERY_AND ? entries : 0) + size_t(pl.cap) * 8 + (c->wand >= 2 ? size_t(entries) * 2 : 0);
-  if (pl.smem > 200 * 1024) return fail(c, SDBG_EUNSUPPORTED, "hash window + candidate buffer exceed shared memory");
+  pl.smem = size_t(entries) * 8 + (kind == SDBG_QUERY_AND ? entries : 0) + size_t(pl.cap) * 8;
+  const size_t smem_drive = pl.smem + size_t(entries) * 4;   // probe list | decode-fallback list
+  if (smem_drive > 200 * 1024) return fail(c, SDBG_EUNSUPPORTED, "hash window + candidate buffer exceed shared memory");
 
   // host-side query descriptors, per segment, sorted by ascending docs_count (conjunction.hpp:520-523)
   const size_t qt_bytes = size_t(total_terms) * sizeof(QTermDev) * n_segs;
@@ -584,7 +606,8 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
         if (k1 == 0.f) d.c0 = 0.f;                                            // BM1: Bm1Score without a filter boost scores 0 (bm25.cpp:118-126)
         else if (b == 0.f) d.norm_length = std::numeric_limits<float>::quiet_NaN();   // BM15 form (device-side marker, see bm25())
         d.docs_count = s->term_docs[t.term];
-        d.root_freq = s->term_max[t.term].freq; d.root_norm = s->term_max[t.term].norm;
+        d.root_freq = s->term_max[t.term].freq & 0x7FFFFFFFu; d.root_norm = s->term_max[t.term].norm;
+        if (t.term < s->term_probe.size() && s->term_probe[t.term]) d.root_freq |= 0x80000000u;   // probe-friendly list (driver mode)
       }
       std::stable_sort(dst + t_begin, dst + t_end, [](const QTermDev& x, const QTermDev& y) { return x.docs_count < y.docs_count; });
     }
@@ -616,30 +639,52 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
   }
   uint32_t base = 0;
   size_t work_done = 0;
-  for (size_t si = 0; si < n_segs; ++si) {
-    sdbg_segment* s = segs[si];
-    TopkParams P;
-    P.seg = postings_view(s, base);
-    if ((rc = filter_view(s, filt, &P.filt))) return rc;
-    P.qterms = static_cast<const QTermDev*>(b_qt.p) + si * total_terms;
-    P.qterm_off = reinterpret_cast<const uint32_t*>(static_cast<const char*>(b_qt.p) + qt_bytes);
-    P.theta = d_theta; P.total = d_total;
-    P.cand = static_cast<unsigned long long*>(b_cand.p);
-    P.cand_n = static_cast<uint32_t*>(b_candn.p);
-    P.work = reinterpret_cast<const uint4*>(static_cast<const char*>(b_qt.p) + qt_pad) + work_done;
-    work_done += seg_work[si].size();
-    P.k = k; P.cap = pl.cap; P.conjunction = kind == SDBG_QUERY_AND ? 1 : 0;
-    P.wand = (c->wand && s->has_wand && k1 != 0.f && b != 0.f) ? c->wand : 0;   // the staged block-max pairs are BM25's
-    { ProfScope ps_(c, kProfTopk);
-      const dim3 grid(unsigned(seg_work[si].size()));
-      const bool drive = c->wand >= 2 && kind != SDBG_QUERY_AND;
-      if (pl.budget == 16) { if (drive) bm25_topk_kernel<16, true><<<grid, kTopkThreads, pl.smem, c->stream>>>(P);
-                             else bm25_topk_kernel<16, false><<<grid, kTopkThreads, pl.smem, c->stream>>>(P); }
-      else { if (drive) bm25_topk_kernel<32, true><<<grid, kTopkThreads, pl.smem, c->stream>>>(P);
-             else bm25_topk_kernel<32, false><<<grid, kTopkThreads, pl.smem, c->stream>>>(P); } }
-    ++c->launches;
-    CU(c, cudaGetLastError());
-    base += s->n_docs;
+  bool any_drive = false, any_plain = false;
+  for (size_t si = 0; si < n_segs; ++si) { any_drive |= n_drive[si] != 0; any_plain |= n_drive[si] != seg_work[si].size(); }
+  // Driver-mode chains and plain chains are two kernels; with both present they run side by side on two streams
+  // (forked from and joined back into the context's stream) so that neither waits for the other's tail.
+  const bool two_lanes = any_drive && any_plain;
+  {
+    ProfScope ps_(c, kProfTopk);   // one span for all top-k launches of the call
+    if (two_lanes) {
+      CU(c, cudaEventRecord(c->ev_fork, c->stream));
+      CU(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+    }
+    for (size_t si = 0; si < n_segs; ++si) {
+      sdbg_segment* s = segs[si];
+      TopkParams P;
+      P.seg = postings_view(s, base);
+      if ((rc = filter_view(s, filt, &P.filt))) return rc;
+      P.qterms = static_cast<const QTermDev*>(b_qt.p) + si * total_terms;
+      P.qterm_off = reinterpret_cast<const uint32_t*>(static_cast<const char*>(b_qt.p) + qt_bytes);
+      P.theta = d_theta; P.total = d_total;
+      P.cand = static_cast<unsigned long long*>(b_cand.p);
+      P.cand_n = static_cast<uint32_t*>(b_candn.p);
+      P.k = k; P.cap = pl.cap; P.conjunction = kind == SDBG_QUERY_AND ? 1 : 0;
+      const int wand = (c->wand && s->has_wand && k1 != 0.f && b != 0.f) ? c->wand : 0;   // the staged block-max pairs are BM25's
+      const uint4* work = reinterpret_cast<const uint4*>(static_cast<const char*>(b_qt.p) + qt_pad) + work_done;
+      const size_t nd = n_drive[si], np = seg_work[si].size() - nd;
+      work_done += seg_work[si].size();
+      if (nd) {
+        P.work = work; P.wand = wand;
+        if (pl.budget == 16) bm25_topk_kernel<16, true><<<unsigned(nd), kTopkThreads, smem_drive, c->stream>>>(P);
+        else bm25_topk_kernel<32, true><<<unsigned(nd), kTopkThreads, smem_drive, c->stream>>>(P);
+        ++c->launches;
+      }
+      if (np) {
+        P.work = work + nd; P.wand = std::min(wand, 1);
+        cudaStream_t st = two_lanes ? c->stream2 : c->stream;
+        if (pl.budget == 16) bm25_topk_kernel<16, false><<<unsigned(np), kTopkThreads, pl.smem, st>>>(P);
+        else bm25_topk_kernel<32, false><<<unsigned(np), kTopkThreads, pl.smem, st>>>(P);
+        ++c->launches;
+      }
+      CU(c, cudaGetLastError());
+      base += s->n_docs;
+    }
+    if (two_lanes) {
+      CU(c, cudaEventRecord(c->ev_join, c->stream2));
+      CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    }
   }
   MergeParams M;
   M.cand = static_cast<const unsigned long long*>(b_cand.p);
