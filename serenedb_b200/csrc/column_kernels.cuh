@@ -707,56 +707,6 @@ groupby_pack_kernel(const GroupSlot* __restrict__ table, const unsigned long lon
   }
 }
 
-// Compact non-empty groups (ascending key) into rows {key, count, sum_i128, sum_f64, cnt_f64}.
-// wide: total = hi * 2^32 + lo (each limb sum exact in int64 for < 2^31 rows per group).
-struct GroupRowDev { long long key; unsigned long long count; unsigned long long sum_lo; long long sum_hi; double sum_f; unsigned long long cnt_f; };
-__global__ void __launch_bounds__(256)
-groupby_compact_kernel(const long long* __restrict__ d_i64, const double* __restrict__ d_f64, uint64_t span,
-                       long long key_min, int wide_int, GroupRowDev* __restrict__ out,
-                       unsigned long long* __restrict__ n_out, uint64_t cap) {
-  // Ordered compaction: one CTA walks the span in tiles and keeps a running offset (span is small:
-  // the dense path is only taken for bounded key ranges).
-  __shared__ unsigned long long s_base;
-  __shared__ uint32_t s_warp[8];
-  if (threadIdx.x == 0) s_base = 0;
-  __syncthreads();
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  for (uint64_t t0 = 0; t0 < span; t0 += blockDim.x) {
-    const uint64_t i = t0 + threadIdx.x;
-    const bool live = i < span && d_i64[i] != 0;
-    const uint32_t bal = __ballot_sync(kFull, live);
-    if (lane == 0) s_warp[warp] = __popc(bal);
-    __syncthreads();
-    uint32_t before = 0, total = 0;
-    for (uint32_t w = 0; w < blockDim.x / 32u; ++w) { if (w < warp) before += s_warp[w]; total += s_warp[w]; }
-    if (live) {
-      const unsigned long long pos = s_base + before + __popc(bal & ((1u << lane) - 1u));
-      if (pos < cap) {
-        GroupRowDev r;
-        r.key = key_min + static_cast<long long>(i);
-        r.count = static_cast<unsigned long long>(d_i64[i]);
-        const long long lo = d_i64[span + i], hi = d_i64[2 * span + i];
-        if (wide_int) {
-          // total = hi * 2^32 + lo as a 128-bit two's-complement value
-          unsigned long long rlo = static_cast<unsigned long long>(hi) << 32;
-          long long rhi = hi >> 32;
-          add128u(rlo, rhi, static_cast<unsigned long long>(lo), lo < 0 ? -1ll : 0ll);
-          r.sum_lo = rlo; r.sum_hi = rhi;
-        } else {
-          r.sum_lo = static_cast<unsigned long long>(lo); r.sum_hi = lo < 0 ? -1ll : 0ll;
-        }
-        r.sum_f = d_f64[i];
-        r.cnt_f = static_cast<unsigned long long>(d_i64[3 * span + i]);
-        out[pos] = r;
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) s_base += total;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *n_out = s_base;
-}
-
 // min/max of an integer column (statistics gathered at staging: the reference keeps them per
 // column block in ColumnBlockMeta::statistics, column_reader.hpp:90-96).
 __global__ void __launch_bounds__(256)
