@@ -172,6 +172,33 @@ def test_reference_goldens_on_gpu():
     assert np.format_float_positional(hits["score"][0], unique=True, trim="-") == r["expected"]
 
 
+def test_sequential_order_goldens_on_gpu():
+    """bm25_test.cpp:163,214 (rank order of a ByRange disjunction under BM25 with norms) through the GPU path,
+    at every pruning level, bit-exact against the oracle that test_oracle_goldens pins to the same golden."""
+    g = G["sequential_order"]
+    n = len(g["docs"])
+    dl = np.array([len(d["field"]) for d in g["docs"]], np.uint32)
+    oseg = orc.Segment(n, has_wand=True)
+    oseg.set_norms(dl)
+    for t in range(10):
+        docs = [i + 1 for i, d in enumerate(g["docs"]) if str(t) in d["field"]]
+        oseg.add_term(np.array(docs, np.uint32), np.array([g["docs"][i - 1]["field"].count(str(t)) for i in docs], np.uint32))
+    gseg = to_gpu(oseg)
+    reader = sdb.IndexReader([gseg], n, int(dl.sum()), [oseg.term_meta(t).docs_count for t in range(10)])
+    scorer = sdb.BM25(g["k"], g["b"])
+    try:
+        for level in (0, 1, 2):
+            ctx().set_wand(level)
+            for c in g["cases"]:
+                tis = [int(t) for t in c["terms"]]
+                hits, total = sdb.ExecuteTopK(reader, tis, sdb.OR, scorer, 8)
+                assert [g["docs"][d - 1]["seq"] for d in hits["doc"]] == c["expected_seq_order"], (level, c["range"])
+                oh, _, _ = orc.bm25_topk([oseg], "OR", oracle_terms(reader, scorer, tis), 8, k1=g["k"], b=g["b"], mode=1)
+                assert_hits_equal(hits, oh)
+    finally:
+        ctx().set_wand(0)
+
+
 def test_collector_worst_case_increasing_scores():
     """Scores increasing with doc id defeat every threshold: the candidate buffer must keep compacting."""
     n = 200_000

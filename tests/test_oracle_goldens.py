@@ -103,3 +103,38 @@ def test_scan_10k_goldens():
     assert (cnt, s) == (100, 1204950)
     # conjunction of pushed filters: x >= 8000 AND n IS NOT NULL  (x % 2 = 0 is an expression filter, out of scope)
     assert orc.filter_count_sum(segs, [P(1, "GE", 8000), P(3, "IS_NOT_NULL")], 1)[0] == 16000
+
+
+def _sequential_order_segment():
+    """Index the 8 docs of simple_sequential_order.json: term id = the token's digit, norm = token count."""
+    g = G["sequential_order"]
+    n = len(g["docs"])
+    dl = np.array([len(d["field"]) for d in g["docs"]], np.uint32)
+    seg = orc.Segment(n, has_wand=True)
+    seg.set_norms(dl)
+    docs_count = []
+    for t in range(10):
+        docs = [i + 1 for i, d in enumerate(g["docs"]) if str(t) in d["field"]]
+        freqs = [g["docs"][i - 1]["field"].count(str(t)) for i in docs]
+        seg.add_term(np.array(docs, np.uint32), np.array(freqs, np.uint32))
+        docs_count.append(len(docs))
+    assert int(dl.sum()) == 52 and n == 8                       # the statistics in the test's comment
+    return g, seg, dl, docs_count
+
+
+def test_sequential_order_goldens():
+    """bm25_test.cpp:163,214: rank order of a multi-term disjunction (ByRange) under BM25 with norms."""
+    g, seg, dl, docs_count = _sequential_order_segment()
+    for c in g["cases"]:
+        terms = []
+        for tok in c["terms"]:
+            t = int(tok)
+            st = orc.bm25_stats(len(dl), int(dl.sum()), docs_count[t], g["k"], g["b"])
+            q = orc.BM25Term()
+            q.idf, q.norm_const, q.norm_length, q.boost, q.term = st.idf, st.norm_const, st.norm_length, 1.0, t
+            terms.append(q)
+        for mode in (0, 1, 2):
+            hits, total, _ = orc.bm25_topk([seg], "OR", terms, 8, k1=g["k"], b=g["b"], mode=mode)
+            seqs = [g["docs"][d - 1]["seq"] for d in hits["doc"]]
+            assert seqs == c["expected_seq_order"], (c["range"], mode, seqs)
+            assert total == len(c["expected_seq_order"])
