@@ -33,6 +33,42 @@ def merge_groupby_partials(dist, part_i64, part_f64):
     return part_i64, part_f64
 
 
+def combine_group_rows(rows):
+    """Merge finalized group rows (engine.GROUP_DTYPE) that may repeat a key: COUNT / cnt add, SUM(double) adds,
+    SUM(int) adds as a 128-bit two's-complement value carried in (sum_lo unsigned, sum_hi signed).
+    Returns rows sorted by key, one per distinct key."""
+    rows = np.asarray(rows)
+    if len(rows) == 0:
+        return rows.copy()
+    r = rows[np.argsort(rows["key"], kind="stable")]
+    keys, start = np.unique(r["key"], return_index=True)
+    out = np.zeros(len(keys), rows.dtype)
+    out["key"] = keys
+    out["count"] = np.add.reduceat(r["count"], start)
+    out["cnt_f64"] = np.add.reduceat(r["cnt_f64"], start)
+    out["sum_f64"] = np.add.reduceat(r["sum_f64"], start)
+    lo = r["sum_lo"].view(np.uint64)
+    m32 = np.uint64(0xFFFFFFFF)
+    lo_l = np.add.reduceat(lo & m32, start)                 # 32-bit halves: exact in uint64 below 2^32 rows per key
+    lo_h = np.add.reduceat(lo >> np.uint64(32), start)
+    lo_h = lo_h + (lo_l >> np.uint64(32))
+    carry = lo_h >> np.uint64(32)
+    out["sum_lo"] = (((lo_h & m32) << np.uint64(32)) | (lo_l & m32)).view(np.int64)
+    out["sum_hi"] = np.add.reduceat(r["sum_hi"], start) + carry.astype(np.int64)
+    return out
+
+
+def merge_group_rows(dist, rows):
+    """Cross-rank merge for the hash-table GROUP BY (key ranges too wide for a dense partial, so there is
+    nothing flat to all-reduce): every rank contributes the group rows of its shard, one all-gather of the
+    (small, variable-length) results, and the same key-wise merge on every rank."""
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        gathered = [None] * dist.get_world_size()
+        dist.all_gather_object(gathered, np.asarray(rows))
+        rows = np.concatenate(gathered)
+    return combine_group_rows(rows)
+
+
 def gather_topk_keys(dist, keys, out=None):
     """All-gather of every rank's k best sortable keys per query ([Q*k] int64 each) -> [world, Q*k]."""
     import torch

@@ -50,6 +50,22 @@ def _partials(groups):
     return i64, f64
 
 
+def _wide_table(shard):
+    """Sparse int64 keys shared between shards, values that need the full 128-bit SUM, doubles of mixed sign."""
+    import orc
+    rng = np.random.default_rng(100 + shard)
+    rows = 30_000 + 17 * shard
+    pool = np.random.default_rng(5).integers(-2**62, 2**62, size=400)          # same key pool on every shard
+    key = pool[rng.integers(0, len(pool), size=rows)].astype(np.int64)
+    v = rng.integers(-2**62, 2**62, size=rows).astype(np.int64)
+    a = rng.integers(0, 100, size=rows).astype(np.int64)
+    w = rng.standard_normal(rows)
+    seg = orc.Segment(rows, has_wand=False)
+    for f, vals in {1: key, 2: v, 3: a, 4: w}.items():
+        seg.add_column(f, vals)
+    return seg, rows
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -85,6 +101,10 @@ def _worker(rank, world, port, q):
             keys[qi * TOPK + i] = np.uint64(sd.rebase_key(sd.make_key(h["score"], h["doc"]), rank)).view(np.int64)
     gathered = sd.gather_topk_keys(dist, torch.from_numpy(keys))
     res["topk"] = sd.select_topk_host(gathered.numpy(), world, len(queries), TOPK)
+    # ---- hash-table GROUP BY (wide keys): group rows per shard, one object all-gather, key-wise merge ----
+    wseg, _ = _wide_table(rank)
+    wrows = orc.filter_groupby([wseg], [orc.make_pred(3, "LT", 70)], 1, 2, 4, cap=5000)
+    res["wide"] = sd.merge_group_rows(dist, wrows)
     if rank == 0:
         q.put(res)
     dist.barrier()
@@ -144,3 +164,14 @@ def test_topk_sharded_equals_unsharded(two_rank_result):
         for (score, rank, ordinal), h in zip(got, hits):
             assert np.float32(score) == h["score"]
             assert rank * per + ordinal == h["doc"]     # shards are doc ranges: global doc = rank*per + local
+
+
+def test_hash_groupby_rows_merge(two_rank_result):
+    """Sparse-key GROUP BY: per-shard group rows merged across ranks == one GROUP BY over both shards."""
+    import orc
+    segs = [_wide_table(r)[0] for r in range(2)]
+    full = orc.filter_groupby(segs, [orc.make_pred(3, "LT", 70)], 1, 2, 4, cap=5000)
+    got = two_rank_result["wide"]
+    for f in ("key", "count", "sum_lo", "sum_hi", "cnt_f64"):
+        assert np.array_equal(got[f], full[f]), f
+    assert np.allclose(got["sum_f64"], full["sum_f64"], rtol=1e-9, atol=1e-9)
