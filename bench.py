@@ -112,16 +112,26 @@ def ncu_traffic(kernel, units):
         return None
 
 
-def make_queries(nq):
-    """Two-term disjunctions, pairs drawn from the 256 synthetic terms; query 0 is the named
+_M64 = (1 << 64) - 1
+
+
+def synth_hash(stream, index):
+    """splitmix64 finaliser over seed ^ (stream << 48) ^ index -- the generator both the product and the
+    oracle use; restated here so that the query list depends on neither library."""
+    z = ((0x5EDB2026 ^ ((stream << 48) & _M64) ^ index) + 0x9E3779B97F4A7C15) & _M64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+    return z ^ (z >> 31)
+
+
+def make_queries(nq, n_terms=N_TERMS, stream=7):
+    """Two-term disjunctions, pairs drawn from the synthetic terms; query 0 is the named
     case p = (0.10, 0.01) => terms 5 and 59."""
-    import serenedb_b200._native as N
-    h = N.lib().sdbg_synth_hash
     qs = [[5, 59]]
     i = 0
     while len(qs) < nq:
-        a = h(7, 2 * i) % N_TERMS
-        b = h(7, 2 * i + 1) % N_TERMS
+        a = synth_hash(stream, 2 * i) % n_terms
+        b = synth_hash(stream, 2 * i + 1) % n_terms
         i += 1
         if a != b:
             qs.append([int(a), int(b)])

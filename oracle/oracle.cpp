@@ -393,6 +393,9 @@ struct Column {
   uint64_t rows = 0;
   std::vector<uint8_t> data;
   std::vector<uint64_t> validity;  // empty => all valid
+  // integer min / max over the valid rows, kept with the column like the reference keeps ColumnBlockMeta::statistics
+  // (irs/formats/column/column_reader.hpp:90-96): computed when the column is added, never at query time
+  bool has_stats = false; int64_t mn = 0, mx = 0;
   bool valid(uint64_t r) const { return validity.empty() || ((validity[r >> 6] >> (r & 63)) & 1); }
   int64_t i64(uint64_t r) const {
     if (type == 2) { int32_t v; std::memcpy(&v, data.data() + 4 * r, 4); return v; }
@@ -1010,6 +1013,12 @@ int orc_segment_add_column(orc_segment* s, uint64_t field, int type, const void*
   const size_t w = type == 2 ? 4 : 8;
   c.data.assign(static_cast<const uint8_t*>(values), static_cast<const uint8_t*>(values) + rows * w);
   if (validity) c.validity.assign(validity, validity + (rows + 63) / 64);
+  if (type != 1 && rows) {
+    int64_t mn = std::numeric_limits<int64_t>::max(), mx = std::numeric_limits<int64_t>::min();
+    bool any = false;
+    for (uint64_t r = 0; r < rows; ++r) if (c.valid(r)) { const int64_t v = c.i64(r); mn = std::min(mn, v); mx = std::max(mx, v); any = true; }
+    if (any) { c.has_stats = true; c.mn = mn; c.mx = mx; }
+  }
   s->cols[field] = std::move(c);
   return 0;
 }
@@ -1139,23 +1148,76 @@ int orc_filter_count_sum(orc_segment* const* segs, size_t n_segs, const orc_pred
   return 0;
 }
 
+}  // extern "C"
+
+// Vectorised in the way the reference's engine executes this plan (DuckDB: 2048-row vectors, one selection vector
+// per chunk, predicates evaluated column-at-a-time with the type switch outside the row loop, thread-local aggregate
+// states merged at the end): restated, since the DuckDB fork is not vendored.
+namespace {
+constexpr uint64_t kVec = 2048;            // STANDARD_VECTOR_SIZE
+constexpr uint64_t kRowGroup = 60 * kVec;  // DuckDB row group = 122880 rows: the unit a worker claims
+
+template <class V, class P>
+inline uint32_t select_typed(const V* v, uint64_t base, const uint16_t* in, uint32_t n_in, bool dense_in, uint16_t* out, P pass) {
+  uint32_t n = 0;
+  if (dense_in) { for (uint32_t i = 0; i < n_in; ++i) { out[n] = uint16_t(i); n += pass(v[base + i]) ? 1u : 0u; } }
+  else { for (uint32_t i = 0; i < n_in; ++i) { const uint16_t r = in[i]; out[n] = r; n += pass(v[base + r]) ? 1u : 0u; } }
+  return n;
+}
+template <class V>
+inline uint32_t select_op(const V* v, uint64_t base, const uint16_t* in, uint32_t n_in, bool dense_in, uint16_t* out, int op, V lo, V hi) {
+  switch (op) {
+    case ORC_OP_LT: return select_typed(v, base, in, n_in, dense_in, out, [=](V x) { return x < lo; });
+    case ORC_OP_LE: return select_typed(v, base, in, n_in, dense_in, out, [=](V x) { return x <= lo; });
+    case ORC_OP_GT: return select_typed(v, base, in, n_in, dense_in, out, [=](V x) { return x > lo; });
+    case ORC_OP_GE: return select_typed(v, base, in, n_in, dense_in, out, [=](V x) { return x >= lo; });
+    case ORC_OP_EQ: return select_typed(v, base, in, n_in, dense_in, out, [=](V x) { return x == lo; });
+    case ORC_OP_NE: return select_typed(v, base, in, n_in, dense_in, out, [=](V x) { return x != lo; });
+    default: return select_typed(v, base, in, n_in, dense_in, out, [=](V x) { return x >= lo && x <= hi; });
+  }
+}
+// One predicate over one vector: narrows the selection. Nullable columns and the NULL tests take the row-wise path.
+inline uint32_t select_pred(const BoundPred& b, uint64_t base, const uint16_t* in, uint32_t n_in, bool dense_in, uint16_t* out) {
+  const Column& c = *b.c;
+  if (!c.validity.empty() || b.p.op == ORC_OP_IS_NULL || b.p.op == ORC_OP_IS_NOT_NULL) {
+    uint32_t n = 0;
+    for (uint32_t i = 0; i < n_in; ++i) { const uint16_t r = dense_in ? uint16_t(i) : in[i]; if (pred_row(c, b.p, base + r)) out[n++] = r; }
+    return n;
+  }
+  if (c.type == 1) return select_op<double>(reinterpret_cast<const double*>(c.data.data()), base, in, n_in, dense_in, out, b.p.op, b.p.lo_f, b.p.hi_f);
+  if (c.type == 2) {
+    const int64_t lo = std::max<int64_t>(std::min<int64_t>(b.p.lo_i, INT32_MAX), INT32_MIN), hi = std::max<int64_t>(std::min<int64_t>(b.p.hi_i, INT32_MAX), INT32_MIN);
+    if (lo != b.p.lo_i || hi != b.p.hi_i) {   // bound outside int32: keep the exact 64-bit comparison
+      uint32_t n = 0;
+      for (uint32_t i = 0; i < n_in; ++i) { const uint16_t r = dense_in ? uint16_t(i) : in[i]; if (pred_row(c, b.p, base + r)) out[n++] = r; }
+      return n;
+    }
+    return select_op<int32_t>(reinterpret_cast<const int32_t*>(c.data.data()), base, in, n_in, dense_in, out, b.p.op, int32_t(lo), int32_t(hi));
+  }
+  return select_op<int64_t>(reinterpret_cast<const int64_t*>(c.data.data()), base, in, n_in, dense_in, out, b.p.op, b.p.lo_i, b.p.hi_i);
+}
+struct DenseAgg { __int128 sum_i = 0; double sum_f = 0; uint64_t count = 0; uint64_t cnt_f = 0; };
+}  // namespace
+
+extern "C" {
+
 int orc_filter_groupby(orc_segment* const* segs, size_t n_segs, const orc_pred* preds, size_t n_preds,
                        uint64_t key_field, uint64_t sum_int_field, uint64_t avg_f64_field, int threads,
                        orc_group_row* out, uint64_t cap, uint64_t* n_out) {
   threads = std::max(threads, 1);
-  // Key range from column statistics (the reference keeps per-block min/max: ColumnBlockMeta,
-  // irs/formats/column/column_reader.hpp:90-96); a small range selects the dense ("perfect hash") path.
+  // Key range from the column statistics (ColumnBlockMeta, irs/formats/column/column_reader.hpp:90-96); a small
+  // range selects the dense ("perfect hash") aggregate.
   int64_t kmin = std::numeric_limits<int64_t>::max(), kmax = std::numeric_limits<int64_t>::min();
   for (size_t si = 0; si < n_segs; ++si) {
     const Column* kc = find_col(*segs[si], key_field);
-    if (!kc || !kc->validity.empty()) return -1;  // GROUP BY key must be NOT NULL here
-    for (uint64_t r = 0; r < kc->rows; ++r) { const int64_t v = kc->i64(r); kmin = std::min(kmin, v); kmax = std::max(kmax, v); }
+    if (!kc || !kc->validity.empty() || kc->type == 1) return -1;  // GROUP BY key must be a NOT NULL integer here
+    if (kc->has_stats) { kmin = std::min(kmin, kc->mn); kmax = std::max(kmax, kc->mx); }
   }
   if (kmin > kmax) { *n_out = 0; return 0; }
   const bool dense = (unsigned __int128)((__int128)kmax - kmin) < ((unsigned __int128)1 << 24);
   const uint64_t span = dense ? uint64_t(kmax - kmin) + 1 : 0;
-  std::vector<std::vector<Agg>> dpart(dense ? size_t(threads) : 0);
-  std::vector<std::unordered_map<int64_t, Agg>> hpart(dense ? 0 : size_t(threads));
+  std::vector<std::vector<DenseAgg>> dpart(dense ? size_t(threads) : 0);
+  std::vector<std::unordered_map<int64_t, DenseAgg>> hpart(dense ? 0 : size_t(threads));
   for (size_t si = 0; si < n_segs; ++si) {
     const orc_segment& s = *segs[si];
     std::vector<BoundPred> bp;
@@ -1163,37 +1225,74 @@ int orc_filter_groupby(orc_segment* const* segs, size_t n_segs, const orc_pred* 
     const Column* kc = find_col(s, key_field);
     const Column* ic = find_col(s, sum_int_field);
     const Column* fc = find_col(s, avg_f64_field);
-    parallel_chunks(kc->rows, threads, uint64_t(1) << 20, [&](int t, uint64_t b, uint64_t e) {
+    parallel_chunks(kc->rows, threads, kRowGroup, [&](int t, uint64_t b, uint64_t e) {
       if (dense && dpart[size_t(t)].empty()) dpart[size_t(t)].resize(span);
-      for (uint64_t r = b; r < e; ++r) {
-        if (!row_passes(bp, r)) continue;
-        const int64_t key = kc->i64(r);
-        Agg& a = dense ? dpart[size_t(t)][uint64_t(key - kmin)] : hpart[size_t(t)][key];
-        ++a.count;
-        if (ic && ic->valid(r)) a.sum_i += ic->i64(r);
-        if (fc && fc->valid(r)) { a.sum_f += fc->f64(r); ++a.cnt_f; }
+      uint16_t sel_a[kVec], sel_b[kVec];
+      for (uint64_t base = b; base < e; base += kVec) {
+        uint32_t n = uint32_t(std::min<uint64_t>(kVec, e - base));
+        const uint16_t* sel = nullptr;   // nullptr = every row of the vector
+        uint16_t* bufs[2] = {sel_a, sel_b};
+        int which = 0;
+        for (const BoundPred& p : bp) {
+          n = select_pred(p, base, sel, n, sel == nullptr, bufs[which]);
+          sel = bufs[which]; which ^= 1;
+          if (!n) break;
+        }
+        for (uint32_t i = 0; i < n; ++i) {
+          const uint64_t r = base + (sel ? sel[i] : i);
+          const int64_t key = kc->i64(r);
+          DenseAgg& a = dense ? dpart[size_t(t)][uint64_t(key - kmin)] : hpart[size_t(t)][key];
+          ++a.count;
+          if (ic && ic->valid(r)) a.sum_i += ic->i64(r);
+          if (fc && fc->valid(r)) { a.sum_f += fc->f64(r); ++a.cnt_f; }
+        }
       }
     });
   }
-  std::map<int64_t, Agg> merged;
+  auto emit_row = [](orc_group_row& g, int64_t key, const DenseAgg& a) {
+    g.key = key; g.count = a.count;
+    g.sum_i128[0] = int64_t(uint64_t(a.sum_i)); g.sum_i128[1] = int64_t(a.sum_i >> 64);
+    g.sum_f64 = a.sum_f; g.cnt_f64 = a.cnt_f;
+  };
   if (dense) {
-    for (uint64_t i = 0; i < span; ++i) {
-      Agg tot;
-      for (auto& p : dpart) if (!p.empty()) { const Agg& a = p[i]; tot.count += a.count; tot.sum_i += a.sum_i; tot.sum_f += a.sum_f; tot.cnt_f += a.cnt_f; }
-      if (tot.count) merged[kmin + int64_t(i)] = tot;
-    }
-  } else {
-    for (auto& p : hpart) for (auto& kv : p) { Agg& d = merged[kv.first]; d.count += kv.second.count; d.sum_i += kv.second.sum_i; d.sum_f += kv.second.sum_f; d.cnt_f += kv.second.cnt_f; }
+    // merge by key range, one range per thread (thread-local states are combined in thread order, so the floating-
+    // point sum of a group does not depend on the merge's own parallelism); output in key order
+    std::vector<DenseAgg> merged(span);
+    const uint64_t parts = uint64_t(std::min<uint64_t>(uint64_t(threads), std::max<uint64_t>(1, span / 1024)));
+    std::vector<uint64_t> part_groups(parts + 1, 0);
+    parallel_chunks(parts, threads, 1, [&](int, uint64_t pb, uint64_t pe) {
+      for (uint64_t pi = pb; pi < pe; ++pi) {
+        const uint64_t lo = span * pi / parts, hi = span * (pi + 1) / parts;
+        uint64_t groups = 0;
+        for (uint64_t i = lo; i < hi; ++i) {
+          DenseAgg tot;
+          for (auto& p : dpart) if (!p.empty()) { const DenseAgg& a = p[i]; tot.count += a.count; tot.sum_i += a.sum_i; tot.sum_f += a.sum_f; tot.cnt_f += a.cnt_f; }
+          merged[i] = tot;
+          groups += tot.count ? 1 : 0;
+        }
+        part_groups[pi + 1] = groups;
+      }
+    });
+    for (uint64_t pi = 0; pi < parts; ++pi) part_groups[pi + 1] += part_groups[pi];
+    *n_out = part_groups[parts];
+    if (*n_out > cap) return -2;
+    parallel_chunks(parts, threads, 1, [&](int, uint64_t pb, uint64_t pe) {
+      for (uint64_t pi = pb; pi < pe; ++pi) {
+        uint64_t o = part_groups[pi];
+        for (uint64_t i = span * pi / parts; i < span * (pi + 1) / parts; ++i)
+          if (merged[i].count) emit_row(out[o++], kmin + int64_t(i), merged[i]);
+      }
+    });
+    return 0;
   }
-  *n_out = merged.size();
-  uint64_t i = 0;
-  for (auto& kv : merged) {
-    if (i >= cap) return -2;
-    orc_group_row& g = out[i++];
-    g.key = kv.first; g.count = kv.second.count;
-    g.sum_i128[0] = int64_t(uint64_t(kv.second.sum_i)); g.sum_i128[1] = int64_t(kv.second.sum_i >> 64);
-    g.sum_f64 = kv.second.sum_f; g.cnt_f64 = kv.second.cnt_f;
-  }
+  std::unordered_map<int64_t, DenseAgg> all;
+  for (auto& p : hpart) for (auto& kv : p) { DenseAgg& d = all[kv.first]; d.count += kv.second.count; d.sum_i += kv.second.sum_i; d.sum_f += kv.second.sum_f; d.cnt_f += kv.second.cnt_f; }
+  std::vector<int64_t> keys; keys.reserve(all.size());
+  for (auto& kv : all) keys.push_back(kv.first);
+  std::sort(keys.begin(), keys.end());
+  *n_out = keys.size();
+  if (keys.size() > cap) return -2;
+  for (size_t i = 0; i < keys.size(); ++i) emit_row(out[i], keys[i], all[keys[i]]);
   return 0;
 }
 

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <cfloat>
 #include <cmath>
@@ -19,6 +20,7 @@
 
 #include "../../include/sdbg.h"
 #include "bm25_kernels.cuh"
+#include "bm25_stream.cuh"
 #include "column_kernels.cuh"
 #include "posting_format.hpp"
 
@@ -315,7 +317,16 @@ int upload_postings(sdbg_segment* s, const StagedPostings& sp) {
   CU(c, cudaSetDevice(c->device));
   free_postings(s);
   CU(c, cudaMalloc(&s->d_arena, std::max<size_t>(sp.arena.size(), 16)));
-  CU(c, cudaMalloc(&s->d_blocks, std::max<size_t>(sp.blocks.size() * sizeof(BlockDesc), 16)));
+  // one sentinel descriptor behind the last block: off16 = end of the payloads, so that "next offset - own offset" is
+  // the payload size of every block (the stream kernel's prefetch size)
+  CU(c, cudaMalloc(&s->d_blocks, (sp.blocks.size() + 1) * sizeof(BlockDesc)));
+  {
+    BlockDesc sentinel;
+    sentinel.off16 = uint32_t((sp.arena.size() >= 1024 ? sp.arena.size() - 1024 : 0) / 16);
+    sentinel.last_doc = 0xFFFFFFFFu; sentinel.prev_last = 0xFFFFFFFFu; sentinel.packed = 0;
+    CU(c, cudaMemcpyAsync(static_cast<BlockDesc*>(s->d_blocks) + sp.blocks.size(), &sentinel, sizeof sentinel, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+  }
   CU(c, cudaMalloc(&s->d_blkmax, std::max<size_t>(sp.blk_max.size() * sizeof(MaxPair), 16)));
   CU(c, cudaMemcpyAsync(s->d_arena, sp.arena.data(), sp.arena.size(), cudaMemcpyHostToDevice, c->stream));
   CU(c, cudaMemcpyAsync(s->d_blocks, sp.blocks.data(), sp.blocks.size() * sizeof(BlockDesc), cudaMemcpyHostToDevice, c->stream));
@@ -535,9 +546,16 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
     for (uint32_t i = 0; i < total_terms; ++i)
       if (terms[i].term < segs[si]->term_docs.size()) batch_postings += segs[si]->term_docs[terms[i].term];
   const uint64_t chain_target = std::max<uint64_t>(uint64_t(env_int("SDBG_TOPK_CHAIN_MIN", 65536)), batch_postings / (uint64_t(c->sm_count) * uint64_t(std::max(1, env_int("SDBG_TOPK_CHAIN_DIV", 4)))));
-  struct WorkItem { uint32_t q, g, chunk, list; uint64_t weight; bool drive; };
+  // Work classes: 0 = legacy kernel in driver mode, 1 = legacy kernel, 2 + (T-1) = warp-autonomous stream kernel for a
+  // disjunction of T = 1..4 terms (bm25_stream.cuh). The stream kernel covers plain BM25 disjunctions without a column
+  // filter or deleted-doc mask; everything else (AND, hybrid, BM15 / BM1 forms, > 4 terms) stays on the legacy kernel.
+  struct WorkItem { uint32_t q, g, chunk, list; uint64_t weight; uint32_t cls; };
+  constexpr uint32_t kClasses = 2 + kStreamMaxTerms;
   const bool level2 = c->wand >= 2 && kind != SDBG_QUERY_AND && k1 != 0.f && b != 0.f;
-  std::vector<size_t> n_drive(n_segs, 0);
+  const bool stream_ok = env_int("SDBG_STREAM", 1) != 0 && kind != SDBG_QUERY_AND && !filt && k1 != 0.f && b != 0.f &&
+                         size_t(pl.cap) * 8 + size_t(kStreamMaxTerms) * (kLutFreqs * 1024 + kTopkWarps * kStreamTermBytes) <= 200 * 1024;
+  std::vector<std::array<size_t, kClasses>> n_cls(n_segs);
+  for (auto& a : n_cls) a.fill(0);
   std::vector<std::vector<WorkItem>> seg_work(n_segs);
   std::vector<uint32_t> list_off(nq + 1, 0);
   for (size_t q = 0; q < nq; ++q) {          // lists of one query are contiguous: [segment 0 chains | segment 1 chains | ...]
@@ -551,16 +569,19 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
           postings += s->term_docs[terms[i].term];
           if (s->term_docs[terms[i].term] >= largest) { largest = s->term_docs[terms[i].term]; largest_term = terms[i].term; }
         }
+      const uint32_t nt = term_off[q + 1] - term_off[q];
       // Driver mode (pruning level 2) pays only when the largest list can be probed without decoding blocks; the
       // other queries run the plain kernel, which is lighter (fewer registers, no probe buffers, level-1 planner).
-      const bool drive_q = level2 && s->has_wand && term_off[q + 1] - term_off[q] >= 2 && largest_term < s->term_probe.size() &&
+      const bool drive_q = level2 && s->has_wand && nt >= 2 && largest_term < s->term_probe.size() &&
                            s->term_probe[largest_term] != 0;
+      uint32_t cls = drive_q ? 0u : 1u;
+      if (stream_ok && nt <= kStreamMaxTerms && !s->d_deleted) cls = 2u + (nt - 1u);
       uint32_t g = uint32_t(std::max<uint64_t>(pl.G, (postings + chain_target - 1) / chain_target));
       g = std::min(g, max_chains);
       g = std::min(g, std::max(1u, s->n_docs / 4096u));
       const uint32_t chunk = (s->n_docs + g - 1) / g;
-      for (uint32_t j = 0; j < g; ++j) seg_work[si].push_back({uint32_t(q), j, chunk, list_off[q] + lists + j, postings / g, drive_q});
-      if (drive_q) n_drive[si] += g;
+      for (uint32_t j = 0; j < g; ++j) seg_work[si].push_back({uint32_t(q), j, chunk, list_off[q] + lists + j, postings / g, cls});
+      n_cls[si][cls] += g;
       lists += g;
     }
     list_off[q + 1] = list_off[q] + lists;
@@ -568,7 +589,7 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
   const uint32_t total_lists = list_off[nq];
   size_t total_work = 0;
   for (auto& w : seg_work) {
-    std::stable_sort(w.begin(), w.end(), [](const WorkItem& x, const WorkItem& y) { return x.drive != y.drive ? x.drive : x.weight > y.weight; });
+    std::stable_sort(w.begin(), w.end(), [](const WorkItem& x, const WorkItem& y) { return x.cls != y.cls ? x.cls < y.cls : x.weight > y.weight; });
     total_work += w.size();
   }
   pl.smem = size_t(entries) * 8 + (kind == SDBG_QUERY_AND ? entries : 0) + size_t(pl.cap) * 8;
@@ -629,27 +650,37 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
   ++c->launches;
   CU(c, cudaMemsetAsync(d_total, 0, nq * 8, c->stream));
 
+  // shared memory of the stream kernel: candidates | score table | per warp (live blocks + prefetch slots)
+  bool use_lut[n_segs ? n_segs : 1];
+  for (size_t si = 0; si < n_segs; ++si) use_lut[si] = segs[si]->norm_width == 1 && env_int("SDBG_STREAM_LUT", 1) != 0;
+  auto stream_smem = [&](uint32_t T, bool lut) { return size_t(pl.cap) * 8 + (lut ? size_t(T) * kLutFreqs * 1024 : 0) + size_t(kTopkWarps) * T * kStreamTermBytes; };
   if (!c->topk_attr_set) {
     CU(c, cudaFuncSetAttribute(bm25_topk_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(c, cudaFuncSetAttribute(bm25_topk_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(c, cudaFuncSetAttribute(bm25_topk_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(c, cudaFuncSetAttribute(bm25_topk_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+#define SDBG_STREAM_ATTR(TT) \
+    CU(c, cudaFuncSetAttribute(bm25_stream_kernel<TT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+    CU(c, cudaFuncSetAttribute(bm25_stream_kernel<TT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))
+    SDBG_STREAM_ATTR(1); SDBG_STREAM_ATTR(2); SDBG_STREAM_ATTR(3); SDBG_STREAM_ATTR(4);
+#undef SDBG_STREAM_ATTR
     CU(c, cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     c->topk_attr_set = true;
   }
   uint32_t base = 0;
   size_t work_done = 0;
-  bool any_drive = false, any_plain = false;
-  for (size_t si = 0; si < n_segs; ++si) { any_drive |= n_drive[si] != 0; any_plain |= n_drive[si] != seg_work[si].size(); }
-  // Driver-mode chains and plain chains are two kernels; with both present they run side by side on two streams
-  // (forked from and joined back into the context's stream) so that neither waits for the other's tail.
-  const bool two_lanes = any_drive && any_plain;
+  // Work classes are separate launches; with more than one present they alternate between two streams (forked from
+  // and joined back into the context's stream) so that no class waits for another's tail.
+  uint32_t classes_present = 0;
+  for (size_t si = 0; si < n_segs; ++si) for (uint32_t k2 = 0; k2 < kClasses; ++k2) if (n_cls[si][k2]) classes_present |= 1u << k2;
+  const bool two_lanes = (classes_present & (classes_present - 1u)) != 0u;
   {
     ProfScope ps_(c, kProfTopk);   // one span for all top-k launches of the call
     if (two_lanes) {
       CU(c, cudaEventRecord(c->ev_fork, c->stream));
       CU(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
     }
+    uint32_t lane_no = 0;
     for (size_t si = 0; si < n_segs; ++si) {
       sdbg_segment* s = segs[si];
       TopkParams P;
@@ -663,19 +694,37 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
       P.k = k; P.cap = pl.cap; P.conjunction = kind == SDBG_QUERY_AND ? 1 : 0;
       const int wand = (c->wand && s->has_wand && k1 != 0.f && b != 0.f) ? c->wand : 0;   // the staged block-max pairs are BM25's
       const uint4* work = reinterpret_cast<const uint4*>(static_cast<const char*>(b_qt.p) + qt_pad) + work_done;
-      const size_t nd = n_drive[si], np = seg_work[si].size() - nd;
       work_done += seg_work[si].size();
-      if (nd) {
-        P.work = work; P.wand = wand;
-        if (pl.budget == 16) bm25_topk_kernel<16, true><<<unsigned(nd), kTopkThreads, smem_drive, c->stream>>>(P);
-        else bm25_topk_kernel<32, true><<<unsigned(nd), kTopkThreads, smem_drive, c->stream>>>(P);
-        ++c->launches;
-      }
-      if (np) {
-        P.work = work + nd; P.wand = std::min(wand, 1);
-        cudaStream_t st = two_lanes ? c->stream2 : c->stream;
-        if (pl.budget == 16) bm25_topk_kernel<16, false><<<unsigned(np), kTopkThreads, pl.smem, st>>>(P);
-        else bm25_topk_kernel<32, false><<<unsigned(np), kTopkThreads, pl.smem, st>>>(P);
+      for (uint32_t cls = 0; cls < kClasses; ++cls) {
+        const size_t n = n_cls[si][cls];
+        if (!n) continue;
+        cudaStream_t st = (two_lanes && (lane_no++ & 1u)) ? c->stream2 : c->stream;
+        P.work = work;
+        work += n;
+        if (cls == 0) {
+          P.wand = wand;
+          if (pl.budget == 16) bm25_topk_kernel<16, true><<<unsigned(n), kTopkThreads, smem_drive, st>>>(P);
+          else bm25_topk_kernel<32, true><<<unsigned(n), kTopkThreads, smem_drive, st>>>(P);
+        } else if (cls == 1) {
+          P.wand = std::min(wand, 1);
+          if (pl.budget == 16) bm25_topk_kernel<16, false><<<unsigned(n), kTopkThreads, pl.smem, st>>>(P);
+          else bm25_topk_kernel<32, false><<<unsigned(n), kTopkThreads, pl.smem, st>>>(P);
+        } else {
+          const uint32_t T = cls - 1u;
+          const bool lut = use_lut[si];
+          const size_t sm = stream_smem(T, lut);
+          P.wand = wand;
+#define SDBG_STREAM_LAUNCH(TT) \
+          if (lut) bm25_stream_kernel<TT, true><<<unsigned(n), kTopkThreads, sm, st>>>(P); \
+          else bm25_stream_kernel<TT, false><<<unsigned(n), kTopkThreads, sm, st>>>(P)
+          switch (T) {
+            case 1: SDBG_STREAM_LAUNCH(1); break;
+            case 2: SDBG_STREAM_LAUNCH(2); break;
+            case 3: SDBG_STREAM_LAUNCH(3); break;
+            default: SDBG_STREAM_LAUNCH(4); break;
+          }
+#undef SDBG_STREAM_LAUNCH
+        }
         ++c->launches;
       }
       CU(c, cudaGetLastError());
