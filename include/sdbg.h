@@ -101,6 +101,10 @@ int sdbg_stage_postings(sdbg_segment*, const uint8_t* doc_file, size_t n, const 
  * scored, collected nor counted by the BM25 calls, like SegmentReaderImpl::mask wrapping the query iterator
  * (segment_reader_impl.cpp:95-157,318-326; duckdb_search_full_scan.cpp:1898). n == 0 clears the mask. */
 int sdbg_stage_docs_mask(sdbg_segment*, const uint32_t* deleted_docs, size_t n);
+/* The b of the BM25 scorer the segment's block-max (wand) entries were written for (wand_writer.hpp:142-175; default
+   0.75). Block-max pruning is used only for queries whose scorer has the same b -- the check Scorer::equals makes in
+   PostingsReaderImpl::WandIterator (formats/posting/reader.hpp:457-501); any other scorer is evaluated exhaustively. */
+int sdbg_segment_set_wand_b(sdbg_segment*, float wand_b);
 typedef struct { uint8_t byte_size; uint32_t row_count; uint64_t file_offset; } sdbg_norm_rg; /* norm_writer.hpp:41-48 */
 /* Row groups of fixed-width (1/2/4 B) little-endian field lengths; row = doc - 1. */
 int sdbg_stage_norms(sdbg_segment*, const uint8_t* bytes, size_t n, const sdbg_norm_rg* rgs, size_t n_rg);

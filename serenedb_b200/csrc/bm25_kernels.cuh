@@ -26,6 +26,7 @@ struct PostingsDev {
   const uint4* arena;     // block payloads, 16-byte units
   const uint4* blocks;    // BlockDesc {off16, last_doc, prev_last, packed}
   const uint2* blk_max;   // {freq, norm} per block (block-max pairs), may be null
+  const uint4* anchors;   // per block: doc ids of postings 31, 63, 95 (probe acceleration, see posting_format.hpp)
   const uint8_t* norms;   // fixed-width field lengths, row = doc-1; null => norm = 1
   const uint32_t* deleted; // DocumentMask as a bitmap, bit `doc` set = deleted (SegmentReaderImpl::mask, segment_reader_impl.cpp:318-326); null = none
   uint32_t norm_width;    // 1, 2 or 4

@@ -50,14 +50,9 @@ struct StreamCtl {   // CTA-wide control block (shared memory)
   uint32_t hist[258];
 };
 
-// A block is prefetched into its slot unless it is a StreamVByte tail (decoded from the arena by the scalar-ish svb
-// path) or larger than a slot. Its size is exact: payloads are contiguous in the arena in block order, so
-// units = off16 of the next block - off16 of this one (the block table ends with a sentinel).
-__device__ __forceinline__ bool block_is_svb(uint32_t packed) {
-  const uint32_t de = desc_doc_enc(packed);
-  return de == 5u || de == 7u || desc_freq_enc(packed) == 4u;
-}
-
+// A block is prefetched into its slot unless it is larger than a slot. Its size is exact: payloads are contiguous in
+// the arena in block order, so units = off16 of the next block - off16 of this one (the block table ends with a
+// sentinel).
 __device__ __forceinline__ void unpack4s(const uint4* p, uint32_t b, uint32_t lane, uint32_t v[4]) {
   const uint32_t bit = lane * b;
   const uint32_t w = bit >> 5, sh = bit & 31u;
@@ -70,10 +65,34 @@ __device__ __forceinline__ void unpack4s(const uint4* p, uint32_t b, uint32_t la
   v[3] = __funnelshift_r(lo.w, hi.w, sh) & mask;
 }
 
-// Doc ids and frequencies of one prefetched block; `pd` / `pf` point at the doc / freq payload in SHARED memory.
-// `stage` = 128 u32 of per-warp shared scratch (bitset rank scatter). Lane l gets postings 4l .. 4l+3.
-__device__ __forceinline__ void decode_block_smem(const uint4* pd, const uint4* pf, const uint4& d, uint32_t lane,
-                                                  uint32_t* stage, uint32_t doc[4], uint32_t f[4]) {
+// StreamVByte 1234 from shared memory (tails only): control byte `lane` describes this lane's four values.
+__device__ __noinline__ void svb4s(const uint4* p, uint32_t len, uint32_t lane, uint32_t* v_out /* shared: 128 u32 */) {
+  const uint8_t* bytes = reinterpret_cast<const uint8_t*>(p);
+  const uint32_t nctl = (len + 3u) >> 2;
+  const uint32_t ctl = lane < nctl ? uint32_t(bytes[lane]) : 0u;
+  uint32_t n[4], mine = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    n[j] = (4u * lane + j < len) ? ((ctl >> (2 * j)) & 3u) + 1u : 0u;
+    mine += n[j];
+  }
+  uint32_t pos = nctl + warp_incl_scan(mine, lane) - mine;
+  uint32_t v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t x = 0;
+    for (uint32_t k = 0; k < n[j]; ++k) x |= uint32_t(bytes[pos + k]) << (8 * k);
+    pos += n[j];
+    v[j] = x;
+  }
+  __syncwarp();
+  reinterpret_cast<uint4*>(v_out)[lane] = make_uint4(v[0], v[1], v[2], v[3]);
+  __syncwarp();
+}
+
+// Doc ids of one prefetched block; `pd` points at the doc payload in SHARED memory. `stage` = 128 u32 of per-warp
+// shared scratch (bitset rank scatter, svb). Lane l gets postings 4l .. 4l+3.
+__device__ __forceinline__ void decode_docs_smem(const uint4* pd, const uint4& d, uint32_t lane, uint32_t* stage, uint32_t doc[4]) {
   const uint32_t enc = desc_doc_enc(d.w), len = desc_len(d.w), prev = d.z;
   if (enc >= 8u) {                                  // de_delta_bitpack_b, b = enc - 6
     unpack4s(pd, enc - 6u, lane, doc);
@@ -108,21 +127,34 @@ __device__ __forceinline__ void decode_block_smem(const uint4* pd, const uint4* 
     const uint32_t g = enc == 1u ? (raw & 0xFFu) : enc == 2u ? (raw & 0xFFFFu) : raw;
 #pragma unroll
     for (int j = 0; j < 4; ++j) doc[j] = prev + g * (4u * lane + j + 1u);
-  } else {                                          // de_values
+  } else if (enc == 0u) {                           // de_values
     uint4 x = make_uint4(0, 0, 0, 0);
     if (4u * lane < len) x = pd[lane];
     doc[0] = x.x; doc[1] = x.y; doc[2] = x.z; doc[3] = x.w;
+  } else {                                          // 5 de_streamvbyte1234, 7 de_delta_streamvbyte1234 (tails)
+    svb4s(pd, len, lane, stage);
+    const uint4 o = reinterpret_cast<const uint4*>(stage)[lane];
+    doc[0] = o.x; doc[1] = o.y; doc[2] = o.z; doc[3] = o.w;
+    __syncwarp();
+    if (enc == 7u) prefix_from_gaps(prev, lane, doc);
   }
-  const uint32_t fenc = desc_freq_enc(d.w);
+}
+__device__ __forceinline__ void decode_freqs_smem(const uint4* pf, const uint4& d, uint32_t lane, uint32_t* stage, uint32_t f[4]) {
+  const uint32_t fenc = desc_freq_enc(d.w), len = desc_len(d.w);
   if (fenc >= 5u) {
     unpack4s(pf, fenc - 4u, lane, f);
   } else if (fenc >= 1u && fenc <= 3u) {
     const uint32_t raw = *reinterpret_cast<const uint32_t*>(pf);
     f[0] = f[1] = f[2] = f[3] = fenc == 1u ? (raw & 0xFFu) : fenc == 2u ? (raw & 0xFFFFu) : raw;
-  } else {
+  } else if (fenc == 0u) {
     uint4 x = make_uint4(0, 0, 0, 0);
     if (4u * lane < len) x = pf[lane];
     f[0] = x.x; f[1] = x.y; f[2] = x.z; f[3] = x.w;
+  } else {
+    svb4s(pf, len, lane, stage);
+    const uint4 o = reinterpret_cast<const uint4*>(stage)[lane];
+    f[0] = o.x; f[1] = o.y; f[2] = o.z; f[3] = o.w;
+    __syncwarp();
   }
 }
 
@@ -157,6 +189,99 @@ __device__ __forceinline__ uint32_t warp_first_block(const uint4* B, uint32_t n,
   return m ? lo + uint32_t(__ffs(m) - 1) : lo + n;
 }
 
+// ------------------------------------------------------------------------------------------
+// Probes: "does list u contain doc d, and with which frequency?" answered by ONE lane without decoding the block
+// for the whole warp -- 32 candidates are looked up at once. This is what the reference does with
+// it.seek(doc) on a non-essential iterator (ProcessNonEssentialFromCandidates, search/max_score_iterator.hpp:406-429)
+// and on the non-lead iterators of a conjunction (Conjunction::converge / LazySeek, search/conjunction.hpp:248-340,
+// PostingIteratorBase::seek, formats/posting/iterator_doc.hpp:233-306): skip-list to the block, search inside it.
+// Here: gallop + binary search over the block table's last_doc column, then inside the block
+//   bit-packed gaps  the staged anchors (doc ids of postings 31 / 63 / 95) pick a quarter, <= 32 gaps are summed
+//   bitset           one bit test, rank by popcount
+//   all-same / raw   arithmetic / binary search
+//   StreamVByte      scalar walk (tail blocks only)
+// followed by a random-access read of the frequency.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t svb_value_at(const uint8_t* bytes, uint32_t len, uint32_t idx_or_doc, bool by_doc, bool delta,
+                                                 uint32_t prev, uint32_t* idx_out) {
+  // by_doc: walks the doc stream until the running id reaches idx_or_doc (returns the id found or 0xFFFFFFFF);
+  // else returns value number idx_or_doc.
+  const uint32_t nctl = (len + 3u) >> 2;
+  uint32_t pos = nctl, acc = prev;
+  for (uint32_t i = 0; i < len; ++i) {
+    const uint32_t c = (uint32_t(__ldg(bytes + (i >> 2))) >> (2u * (i & 3u))) & 3u;
+    uint32_t x = 0;
+    for (uint32_t k = 0; k <= c; ++k) x |= uint32_t(__ldg(bytes + pos + k)) << (8u * k);
+    pos += c + 1u;
+    if (by_doc) {
+      acc = delta ? acc + x : x;
+      if (acc >= idx_or_doc) { *idx_out = i; return acc; }
+    } else if (i == idx_or_doc) {
+      return x;
+    }
+  }
+  return 0xFFFFFFFFu;
+}
+
+// Position of doc `d` inside block `desc` (prev_last < d <= last_doc), or false when the block does not hold it.
+__device__ __forceinline__ bool block_find_doc(const PostingsDev& S, const uint4& desc, uint32_t gblk, uint32_t d, uint32_t& idx) {
+  const uint4* p = S.arena + desc.x;
+  const uint32_t enc = desc_doc_enc(desc.w), len = desc_len(desc.w), prev = desc.z;
+  if (enc >= 8u) {                                   // bit-packed gaps: row r = postings 4r .. 4r+3
+    const uint32_t b = enc - 6u;
+    const uint4 an = __ldg(S.anchors + gblk);
+    const uint32_t qd = (d > an.x ? 1u : 0u) + (d > an.y ? 1u : 0u) + (d > an.z ? 1u : 0u);
+    uint32_t acc = qd == 0u ? prev : qd == 1u ? an.x : qd == 2u ? an.y : an.z;
+    const uint32_t mask = (1u << b) - 1u;
+    for (uint32_t r = 8u * qd; r < 8u * qd + 8u; ++r) {
+      const uint32_t bit = r * b, w = bit >> 5, sh = bit & 31u;
+      const uint4 lo = __ldg(p + w), hi = __ldg(p + min(w + 1u, b - 1u));
+      acc += __funnelshift_r(lo.x, hi.x, sh) & mask; if (acc >= d) { idx = 4u * r; return acc == d; }
+      acc += __funnelshift_r(lo.y, hi.y, sh) & mask; if (acc >= d) { idx = 4u * r + 1u; return acc == d; }
+      acc += __funnelshift_r(lo.z, hi.z, sh) & mask; if (acc >= d) { idx = 4u * r + 2u; return acc == d; }
+      acc += __funnelshift_r(lo.w, hi.w, sh) & mask; if (acc >= d) { idx = 4u * r + 3u; return acc == d; }
+    }
+    return false;
+  }
+  if (enc == 4u) return bitset_rank(S.arena, desc, d, idx);
+  if (enc >= 1u && enc <= 3u) {                       // constant gap g: ids prev + g, prev + 2g, ...
+    const uint32_t g = same_value(p, enc);
+    const uint32_t off = d - prev;
+    if (g == 0u || off % g != 0u) return false;
+    idx = off / g - 1u;
+    return idx < len;
+  }
+  if (enc == 0u) {                                    // raw ids
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(p);
+    uint32_t l = 0, r = len;
+    while (l < r) { const uint32_t m = (l + r) >> 1; if (__ldg(a + m) < d) l = m + 1u; else r = m; }
+    idx = l;
+    return l < len && __ldg(a + l) == d;
+  }
+  return svb_value_at(reinterpret_cast<const uint8_t*>(p), len, d, true, enc == 7u, prev, &idx) == d;
+}
+
+// One lane: score of doc d in the posting list of `qt`, or false when the list does not contain d. `hint` = a block
+// of the list (index within the term) that is not behind d's block; on return the block that was searched.
+__device__ __forceinline__ bool probe_term(const PostingsDev& S, const QTermDev& qt, uint32_t d, uint32_t hint, uint32_t& found_blk,
+                                           float& score) {
+  const uint4* B = S.blocks + qt.blk_begin;
+  const uint32_t n = qt.nblk;
+  if (n == 0u) { found_blk = 0u; return false; }
+  const uint32_t l = find_block_from(B, 0u, n, min(hint, n - 1u), d);   // first block whose last doc is >= d, searched outwards from the hint
+  found_blk = min(l, n - 1u);
+  if (l >= n) return false;
+  const uint4 desc = __ldg(B + l);
+  if (d <= desc.z) return false;                       // d lies between two blocks
+  uint32_t idx = 0, f = 0;
+  if (!block_find_doc(S, desc, qt.blk_begin + l, d, idx)) return false;
+  if (!freq_at(S.arena, desc, idx, f)) {               // StreamVByte frequencies: scalar walk
+    f = svb_value_at(reinterpret_cast<const uint8_t*>(S.arena + desc.x + desc_fdelta(desc.w)), desc_len(desc.w), idx, false, false, 0u, &idx);
+  }
+  score = bm25(f, load_norm(S.norms, S.norm_width, d), qt.c0, qt.norm_const, qt.norm_length);
+  return true;
+}
+
 // Candidate buffer full: exact radix select keeps the best k and raises the thresholds. Called by every thread of the
 // CTA between two barriers of the rendezvous.
 __device__ __noinline__ void stream_compact(StreamCtl* ctl, unsigned long long* cand, uint32_t cap, uint32_t k,
@@ -189,10 +314,14 @@ __device__ __noinline__ bool stream_rendezvous(StreamCtl* ctl, unsigned long lon
 
 // Dynamic shared memory: cand[cap] u64 | lut[T][kLutFreqs][256] f32 (kLut) | per warp: T x kStreamTermBytes.
 // Terms are in ascending-cost order (the host sorts them); T-1 is the "top" term.
-template <uint32_t T, bool kLut>
-__global__ void __launch_bounds__(kTopkThreads, 3)
+// kAnd: conjunction -- term 0 (the shortest list) is streamed, every other list is probed per candidate and must
+// contain it (T = 1 live term, any number of probed terms). Disjunctions stream all T terms until the running
+// threshold exceeds the summed block-max bounds of a suffix of them (MaxScore's non-essential lists, P.wand != 0).
+template <uint32_t T, bool kLut, int kMinBlocks, bool kAnd>
+__global__ void __launch_bounds__(kTopkThreads, kMinBlocks)
 bm25_stream_kernel(const TopkParams P) {
-  static_assert(T >= 1 && T <= kStreamMaxTerms, "1..4 terms");
+  static_assert(T >= 1 && T <= kStreamMaxTerms, "1..4 live terms");
+  static_assert(!kAnd || T == 1, "a conjunction streams its lead list only");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* cand = reinterpret_cast<unsigned long long*>(smem_raw);
   float* lut = reinterpret_cast<float*>(cand + P.cap);
@@ -200,10 +329,13 @@ bm25_stream_kernel(const TopkParams P) {
 
   __shared__ __align__(16) StreamCtl ctl;
   __shared__ uint64_t s_bar[kTopkWarps][kStreamMaxTerms][2];
-  __shared__ QTermDev s_qt[kStreamMaxTerms];
+  __shared__ QTermDev s_qt[kMaxQueryTerms];
+  __shared__ float s_sfx[kMaxQueryTerms + 1];          // s_sfx[e] = sum of the list-wide block-max bounds of terms e .. (inf when unknown)
+  __shared__ uint32_t s_hint[kTopkWarps][kMaxQueryTerms];   // per warp and probed term: block where the last probe ended
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  unsigned char* mine = warp_area + warp * (T * kStreamTermBytes);
+  constexpr uint32_t kWarpBytes = T * kStreamTermBytes + (kAnd ? 1024u : 0u);
+  unsigned char* mine = warp_area + warp * kWarpBytes;
   auto live_docs = [&](uint32_t t) { return reinterpret_cast<uint32_t*>(mine + t * kStreamTermBytes); };
   auto live_scores = [&](uint32_t t) { return reinterpret_cast<float*>(mine + t * kStreamTermBytes + 512u); };
   auto slot_of = [&](uint32_t t, uint32_t s) { return reinterpret_cast<uint4*>(mine + t * kStreamTermBytes + 1024u + s * 512u); };
@@ -212,6 +344,7 @@ bm25_stream_kernel(const TopkParams P) {
   const uint4 work = P.work[blockIdx.x];
   const uint32_t q = work.x, g = work.y, chunk = work.z;
   const uint32_t t0 = P.qterm_off[q];
+  const uint32_t n_terms = kAnd ? min(P.qterm_off[q + 1] - t0, kMaxQueryTerms) : T;   // live + probed
   const unsigned long long first64 = 1ull + static_cast<unsigned long long>(g) * chunk;
   const bool chain_empty = first64 > P.seg.n_docs;
   const uint32_t chain_lo = chain_empty ? 1u : uint32_t(first64);
@@ -223,7 +356,7 @@ bm25_stream_kernel(const TopkParams P) {
   const uint32_t hi_w = warp_empty ? 0u : min(chain_hi, lo_w + sub - 1u);
 
   for (uint32_t i = tid; i < P.cap; i += blockDim.x) cand[i] = 0ull;
-  if (tid < T) s_qt[tid] = P.qterms[t0 + tid];
+  if (tid < n_terms) s_qt[tid] = P.qterms[t0 + tid];
   if (tid == 0) { ctl.ncand = 0u; ctl.matched = 0u; ctl.full = 0u; ctl.active = kTopkWarps; ctl.theta = 0ull; }
   if (lane == 0) {
 #pragma unroll
@@ -240,17 +373,33 @@ bm25_stream_kernel(const TopkParams P) {
     }
     __syncthreads();
   }
+  if (tid == 0) {
+    // suffix sums of the list-wide upper bounds (root block-max pair scored with the query's statistics)
+    float acc = 0.f;
+    s_sfx[n_terms] = 0.f;
+    for (uint32_t t = n_terms; t-- > 0;) {
+      const uint32_t rf = s_qt[t].root_freq & 0x7FFFFFFFu;
+      const float ub = (P.wand && P.seg.blk_max != nullptr && rf != 0u) ? bm25(rf, s_qt[t].root_norm, s_qt[t].c0, s_qt[t].norm_const, s_qt[t].norm_length)
+                                                                       : __int_as_float(0x7f800000);
+      acc = __fadd_rn(acc, ub);
+      s_sfx[t] = acc;
+    }
+  }
+  __syncthreads();
   unsigned long long* const theta_global = P.theta + q;
+  const bool doc_checks = P.filt.values != nullptr || P.seg.deleted != nullptr;   // hybrid filter / DocumentMask on final docs
   const uint8_t* const norms_m1 = P.seg.norms ? P.seg.norms - 1 : nullptr;   // row = doc - 1 (1-byte norms: kLut)
 
   if (!warp_empty) {
     // ---- per-term stream state: registers (every loop over t is unrolled) ----
     uint32_t cur[T] = {};     // next block to load (index within the term)
-    uint32_t wb[T] = {};      // first block of the descriptor window
-    uint32_t start[T] = {};   // first block of this warp (slot / parity bookkeeping)
+    uint32_t widx[T] = {};    // its position in the descriptor window
+    uint32_t rr[T] = {};      // blocks consumed so far, mod 4: prefetch slot = rr & 1, barrier parity = rr >> 1
     uint32_t fr[T] = {};      // last doc of the live block (kNoDoc: list exhausted for this warp)
-    uint32_t a0[T] = {};      // first pending entry of the live block (lower terms)
+    uint32_t a0[T] = {};      // first pending entry of the live block
+    uint32_t nxt[T] = {};     // its doc id (kNoDoc: none) -- lower terms only
     uint32_t matched = 0;     // per lane; summed at the end
+    uint32_t skip0 = 0u;      // term 0, bit i: window block i cannot reach the threshold (judged when the window was loaded)
     unsigned long long theta = 0ull;
     uint32_t theta_hi = 0u;
 
@@ -271,84 +420,220 @@ bm25_stream_kernel(const TopkParams P) {
       }
     };
 
-    // Issues the bulk copy of block b of term t into its slot (b - start) & 1; every block gets exactly one arrival
-    // on its slot's barrier, in block order (a block that is not prefetched arrives with 0 bytes). The window holds
-    // the descriptors of b and b + 1 (refilled before it runs out), b + 1 possibly being the table's sentinel.
-    auto prefetch = [&](const uint32_t t, uint32_t b) {
-      if (b >= s_qt[t].nblk) return;
-      if (lane == 0) {
-        const uint4* w = desc_win(t);
-        const uint4 d = w[b - wb[t]];
-        uint32_t units = w[b - wb[t] + 1u].x - d.x;
-        if (units > kSlotUnits || block_is_svb(d.w)) units = 0u;
-        const uint32_t r = b - start[t];
-        uint64_t* bar = &s_bar[warp][t][r & 1u];
-        mbar_arrive_expect_tx(bar, units * 16u);
-        if (units) bulk_g2s(slot_of(t, r & 1u), P.seg.arena + d.x, units * 16u, bar);
+    // ---- candidates that still have lists to visit (probed terms) wait in a per-warp ring of 128 (doc, partial score);
+    // a round looks 32 of them up at once, one per lane ----
+    uint32_t E = kAnd ? 1u : T;          // live terms 0 .. E-1 are streamed; terms E .. n_terms-1 are probed
+    uint32_t qhead = 0u, qcount = 0u;
+    uint32_t* const qd = kAnd ? reinterpret_cast<uint32_t*>(mine + T * kStreamTermBytes) : live_docs(T - 1u);   // OR: the ring
+    float* const qs = kAnd ? reinterpret_cast<float*>(mine + T * kStreamTermBytes + 512u) : live_scores(T - 1u);  // reuses the dropped top list's arrays
+
+    auto doc_ok = [&](uint32_t d) {
+      if (P.seg.deleted != nullptr && ((__ldg(P.seg.deleted + (d >> 5)) >> (d & 31u)) & 1u)) return false;   // MaskDocIterator
+      return filter_pass(P.filt, d);
+    };
+    auto test_and_append = [&](bool alive, uint32_t dv, float sv) {
+      bool want = alive && __float_as_uint(sv) >= theta_hi;
+      if (__any_sync(kFull, want)) {
+        unsigned long long key = 0ull;
+        if (want) { key = make_key(sv, P.seg.ordinal_base + dv); want = key > theta; }
+        append(want, key);
       }
     };
-    // Window = descriptors [wb, wb + 32) of the term (zeros past the sentinel).
+    auto probe_round = [&]() {
+      const uint32_t n = min(32u, qcount);
+      bool alive = lane < n;
+      const uint32_t d = alive ? qd[(qhead + lane) & 127u] : kNoDoc;
+      float s = alive ? qs[(qhead + lane) & 127u] : 0.f;
+      qhead = (qhead + n) & 127u; qcount -= n;
+      const float theta_score = __uint_as_float(theta_hi);
+      for (uint32_t u = E; u < n_terms; ++u) {
+        if (!__any_sync(kFull, alive)) break;
+        uint32_t fb = 0u;
+        float su = 0.f;
+        bool found = false;
+        if (alive) found = probe_term(P.seg, s_qt[u], d, s_hint[warp][u], fb, su);
+        const uint32_t who = __ballot_sync(kFull, alive);
+        fb = __shfl_sync(kFull, fb, __ffs(who) - 1);
+        __syncwarp();
+        if (lane == 0) s_hint[warp][u] = fb;
+        __syncwarp();
+        if (kAnd) {
+          alive = alive && found;
+          if (found) s = __fadd_rn(s, su);
+        } else {
+          if (found) s = __fadd_rn(s, su);                       // ascending-cost order: probed lists come last
+          // even with the best the remaining lists can add this doc stays below the threshold
+          if (alive && __fmul_rn(__fadd_rn(s, s_sfx[u + 1u]), 1.000001f) < theta_score) alive = false;
+        }
+      }
+      if (kAnd) {
+        if (doc_checks && alive) alive = doc_ok(d);
+        matched += alive ? 1u : 0u;
+      }
+      test_and_append(alive, d, s);
+    };
+    // Entries that no live list absorbs any more.
+    auto finalize_entries = [&](bool alive, uint32_t dv, float sv) {
+      if (!kAnd) {
+        if (doc_checks && alive) alive = doc_ok(dv);
+        matched += alive ? 1u : 0u;
+        if (E == T) { test_and_append(alive, dv, sv); return; }
+        // MaxScore: a doc that cannot reach the threshold even with every probed list's bound is dropped unprobed
+        alive = alive && !(__fmul_rn(__fadd_rn(sv, s_sfx[E]), 1.000001f) < __uint_as_float(theta_hi));
+      }
+      const uint32_t bal = __ballot_sync(kFull, alive);
+      if (bal) {
+        if (alive) {
+          const uint32_t pos = (qhead + qcount + __popc(bal & ((1u << lane) - 1u))) & 127u;
+          qd[pos] = dv; qs[pos] = sv;
+        }
+        qcount += __popc(bal);
+        __syncwarp();
+        while (qcount >= 32u) probe_round();
+      }
+    };
+
+    // Top live term: entries [a0, ...) with doc <= limit of its live block, lane l holding entries 4l .. 4l+3.
+    auto finalize_top = [&](const uint32_t t, uint32_t limit) {
+      const uint4 dd = reinterpret_cast<const uint4*>(live_docs(t))[lane];
+      const float4 ss = reinterpret_cast<const float4*>(live_scores(t))[lane];
+      const uint32_t dv[4] = {dd.x, dd.y, dd.z, dd.w};
+      const float sv[4] = {ss.x, ss.y, ss.z, ss.w};
+      bool alive[4];
+      bool want_any = false;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        alive[j] = dv[j] <= limit && 4u * lane + j >= a0[t];       // pads are kNoDoc > limit
+        want_any |= alive[j] && __float_as_uint(sv[j]) >= theta_hi;
+      }
+      if (!kAnd && E == T && !doc_checks) {
+        // common case: nothing to probe, nothing to check -- count, and touch the append path only when some score
+        // reaches the threshold
+#pragma unroll
+        for (int j = 0; j < 4; ++j) matched += alive[j] ? 1u : 0u;
+        if (__any_sync(kFull, want_any)) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) test_and_append(alive[j], dv[j], sv[j]);
+        }
+      } else {
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t d1 = j == 0 ? dv[0] : j == 1 ? dv[1] : j == 2 ? dv[2] : dv[3];
+          const float s1 = j == 0 ? sv[0] : j == 1 ? sv[1] : j == 2 ? sv[2] : sv[3];
+          const bool al = j == 0 ? alive[0] : j == 1 ? alive[1] : j == 2 ? alive[2] : alive[3];
+          finalize_entries(al, d1, s1);
+        }
+      }
+    };
+
+    // Issues the bulk copy of the block at window position wi of term t into slot `sl`; every block gets exactly one
+    // arrival on its slot's barrier, in block order (a block larger than a slot arrives with 0 bytes and is decoded
+    // from the arena). The window holds the block's descriptor and its successor's (possibly the table's sentinel).
+    auto prefetch = [&](const uint32_t t, uint32_t wi, uint32_t sl) {
+      if (lane == 0) {
+        const uint4* w = desc_win(t) + wi;
+        const uint32_t off = w[0].x;
+        uint32_t units = w[1].x - off;
+        if (units > kSlotUnits || (t == 0u && ((skip0 >> wi) & 1u))) units = 0u;
+        uint64_t* bar = &s_bar[warp][t][sl];
+        mbar_arrive_expect_tx(bar, units * 16u);
+        if (units) bulk_g2s(slot_of(t, sl), P.seg.arena + off, units * 16u, bar);
+      }
+    };
+    // Window = descriptors [first, first + 32) of the term (zeros past the sentinel).
     auto load_window = [&](const uint32_t t, uint32_t first) {
       __syncwarp();
-      wb[t] = first;
       desc_win(t)[lane] = (first + lane <= s_qt[t].nblk) ? __ldg(P.seg.blocks + s_qt[t].blk_begin + first + lane) : make_uint4(0, 0, 0, 0);
+      if (t == 0u) {
+        // Single live list (one term, or MaxScore has demoted the others): a block whose block-max bound plus the
+        // probed lists' bounds stays below the threshold is never decoded -- SingleWandIterator's block skip
+        // (formats/posting/iterator_score.hpp:218-233, 513-632). The threshold only rises, so a verdict stays valid.
+        bool skip = false;
+        if (!kAnd && P.wand && E == 1u && first + lane < s_qt[0].nblk) {
+          const uint2 fn = __ldg(P.seg.blk_max + s_qt[0].blk_begin + first + lane);
+          if (fn.x != 0u) {
+            const float bound = bm25(fn.x, fn.y, s_qt[0].c0, s_qt[0].norm_const, s_qt[0].norm_length);
+            skip = __fmul_rn(__fadd_rn(bound, s_sfx[1]), 1.000001f) < __uint_as_float(theta_hi);
+          }
+        }
+        skip0 = __ballot_sync(kFull, skip);
+      }
       __syncwarp();
     };
 
     // Makes block cur[t] the live block of term t: wait for its payload, decode, gather norms, score, publish.
-    auto advance = [&](const uint32_t t, uint32_t plo) {
+    auto advance = [&](const uint32_t t, uint32_t plo, bool first_block) {
       uint32_t* ld = live_docs(t);
       float* ls = live_scores(t);
-      bool have = cur[t] < s_qt[t].nblk;
+      const uint32_t nblk = s_qt[t].nblk;
+      bool have = cur[t] < nblk;
       uint4 d = make_uint4(0, 0, 0, 0);
       if (have) {
-        if (cur[t] - wb[t] >= 28u) load_window(t, cur[t]);         // keeps cur .. cur + 3 inside the window
-        d = desc_win(t)[cur[t] - wb[t]];
+        if (widx[t] >= 28u) { load_window(t, cur[t]); widx[t] = 0u; }   // keeps positions widx .. widx + 3 inside the window
+        d = desc_win(t)[widx[t]];
         have = d.z < hi_w;                                         // first doc of the block (prev_last + 1) inside the sub-range
       }
       if (!have) {
         reinterpret_cast<uint4*>(ld)[lane] = make_uint4(kNoDoc, kNoDoc, kNoDoc, kNoDoc);
-        fr[t] = kNoDoc; a0[t] = 0u;
+        fr[t] = kNoDoc; a0[t] = 128u; nxt[t] = kNoDoc;
         return;
       }
-      const uint32_t r = cur[t] - start[t];
-      mbar_wait(&s_bar[warp][t][r & 1u], (r >> 1) & 1u);
-      uint32_t doc[4], f[4];
-      const uint32_t units = desc_win(t)[cur[t] - wb[t] + 1u].x - d.x;
-      if (units <= kSlotUnits && !block_is_svb(d.w)) {
-        const uint4* p = slot_of(t, r & 1u);
-        decode_block_smem(p, p + desc_fdelta(d.w), d, lane, ld, doc, f);
+      const uint32_t units = desc_win(t)[widx[t] + 1u].x - d.x;
+      const uint32_t sl = rr[t] & 1u;
+      mbar_wait(&s_bar[warp][t][sl], (rr[t] >> 1) & 1u);
+      if (t == 0u && ((skip0 >> widx[0]) & 1u)) {
+        // block-max says no doc of this block can qualify: consume it without decoding
+        __syncwarp();
+        if (cur[t] + 2u < nblk) prefetch(t, widx[t] + 2u, sl);
+        reinterpret_cast<uint4*>(ld)[lane] = make_uint4(kNoDoc, kNoDoc, kNoDoc, kNoDoc);
+        fr[t] = d.y; a0[t] = 128u; nxt[t] = kNoDoc;
+        ++cur[t]; ++widx[t]; rr[t] = (rr[t] + 1u) & 3u;
+        return;
+      }
+      const uint32_t len = desc_len(d.w);
+      uint32_t doc[4], f[4], nrm[4];
+      const uint4* p = slot_of(t, sl);
+      if (units <= kSlotUnits) {
+        decode_docs_smem(p, d, lane, ld, doc);
       } else {
         decode_block_global(P.seg.arena, d, lane, ld, reinterpret_cast<uint32_t*>(ls));
         const uint4 x = reinterpret_cast<const uint4*>(ld)[lane], y = reinterpret_cast<const uint4*>(ls)[lane];
         doc[0] = x.x; doc[1] = x.y; doc[2] = x.z; doc[3] = x.w;
         f[0] = y.x; f[1] = y.y; f[2] = y.z; f[3] = y.w;
       }
-      __syncwarp();                                                // every lane is done with the slot
-      prefetch(t, cur[t] + 2u);
-      const uint32_t len = desc_len(d.w);
-      uint32_t nrm[4];
+      // norm gathers go out before the rest of the decode: their L2 latency overlaps the frequency unpack + prefetch
+      if (len == 128u) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const bool valid = 4u * lane + j < len;
-        if (!valid) { doc[j] = kNoDoc; f[j] = 1u; }
-        if constexpr (kLut) nrm[j] = (valid && norms_m1) ? __ldg(norms_m1 + doc[j]) : 1u;
-        else nrm[j] = valid ? load_norm(P.seg.norms, P.seg.norm_width, doc[j]) : 1u;
+        for (int j = 0; j < 4; ++j) {
+          if constexpr (kLut) nrm[j] = norms_m1 ? uint32_t(__ldg(norms_m1 + doc[j])) : 1u;
+          else nrm[j] = load_norm(P.seg.norms, P.seg.norm_width, doc[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool valid = 4u * lane + j < len;
+          if (!valid) doc[j] = kNoDoc;
+          if constexpr (kLut) nrm[j] = (valid && norms_m1) ? uint32_t(__ldg(norms_m1 + doc[j])) : 1u;
+          else nrm[j] = valid ? load_norm(P.seg.norms, P.seg.norm_width, doc[j]) : 1u;
+        }
+      }
+      if (units <= kSlotUnits) decode_freqs_smem(p + desc_fdelta(d.w), d, lane, reinterpret_cast<uint32_t*>(ls), f);
+      __syncwarp();                                                // every lane is done with the slot
+      if (cur[t] + 2u < nblk) prefetch(t, widx[t] + 2u, sl);
+      if (len != 128u) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (4u * lane + j >= len) f[j] = 1u;
       }
       float s[4];
       if constexpr (kLut) {
-        bool slow = false;
         const float* lt = lut + t * kLutFreqs * 256u;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          slow |= f[j] > kLutFreqs;
-          s[j] = lt[min(f[j] - 1u, kLutFreqs - 1u) * 256u + nrm[j]];
-        }
-        if (__any_sync(kFull, slow)) {
+        for (int j = 0; j < 4; ++j) s[j] = lt[min(f[j] - 1u, kLutFreqs - 1u) * 256u + nrm[j]];
+        if (__any_sync(kFull, max(max(f[0], f[1]), max(f[2], f[3])) > kLutFreqs)) {
           const float c0 = s_qt[t].c0, nc = s_qt[t].norm_const, nl = s_qt[t].norm_length;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (f[j] > kLutFreqs) s[j] = bm25(f[j], nrm[j], c0, nc, nl);
+            if (__any_sync(kFull, f[j] > kLutFreqs)) { if (f[j] > kLutFreqs) s[j] = bm25(f[j], nrm[j], c0, nc, nl); }
         }
       } else {
         const float c0 = s_qt[t].c0, nc = s_qt[t].norm_const, nl = s_qt[t].norm_length;
@@ -358,42 +643,43 @@ bm25_stream_kernel(const TopkParams P) {
       reinterpret_cast<uint4*>(ld)[lane] = make_uint4(doc[0], doc[1], doc[2], doc[3]);
       reinterpret_cast<float4*>(ls)[lane] = make_float4(s[0], s[1], s[2], s[3]);
       a0[t] = 0u;
-      if (cur[t] == start[t]) {
+      if (first_block) {
         // the first block of a warp may hold docs below its sub-range: they are not pending
         a0[t] = __popc(__ballot_sync(kFull, doc[0] <= plo)) + __popc(__ballot_sync(kFull, doc[1] <= plo)) +
                 __popc(__ballot_sync(kFull, doc[2] <= plo)) + __popc(__ballot_sync(kFull, doc[3] <= plo));
       }
-      fr[t] = d.y;
-      ++cur[t];
-    };
-
-    // Final entries (nobody absorbs them any more): count, threshold test, append.
-    auto emit = [&](bool alive, uint32_t dv, float sv) {
-      matched += alive ? 1u : 0u;
-      bool want = alive && __float_as_uint(sv) >= theta_hi;
-      if (__any_sync(kFull, want)) {
-        unsigned long long key = 0ull;
-        if (want) { key = make_key(sv, P.seg.ordinal_base + dv); want = key > theta; }
-        append(want, key);
+      if (t + 1u < T) {
+        __syncwarp();
+        nxt[t] = a0[t] < 128u ? ld[a0[t]] : kNoDoc;
       }
+      fr[t] = d.y;
+      ++cur[t]; ++widx[t]; rr[t] = (rr[t] + 1u) & 3u;
     };
 
 #pragma unroll
     for (uint32_t t = 0; t < T; ++t) {
       const uint32_t st = warp_first_block(P.seg.blocks + s_qt[t].blk_begin, s_qt[t].nblk, lo_w, lane);
-      start[t] = st; cur[t] = st;
+      cur[t] = st; widx[t] = 0u; rr[t] = 0u;
       load_window(t, st);
+      if (st < s_qt[t].nblk) prefetch(t, 0u, 0u);
+      if (st + 1u < s_qt[t].nblk) prefetch(t, 1u, 1u);
       fr[t] = lo_w - 1u;
     }
-#pragma unroll
-    for (uint32_t t = 0; t < T; ++t) { prefetch(t, start[t]); prefetch(t, start[t] + 1u); }
+
+    if (kAnd) {
+      for (uint32_t u = 1u; u < n_terms; ++u) {
+        const uint32_t hb = warp_first_block(P.seg.blocks + s_qt[u].blk_begin, s_qt[u].nblk, lo_w, lane);
+        if (lane == 0) s_hint[warp][u] = hb;
+      }
+      __syncwarp();
+    }
 
     uint32_t plo = lo_w - 1u;   // docs <= plo are final
     for (uint32_t step = 0;; ++step) {
       // ---- replace the live blocks that ended at plo (first step: every term) ----
 #pragma unroll
       for (uint32_t t = 0; t < T; ++t)
-        if (fr[t] == plo) advance(t, plo);
+        if (fr[t] == plo) advance(t, plo, step == 0u);
       __syncwarp();
 
       uint32_t phi = hi_w;
@@ -406,82 +692,77 @@ bm25_stream_kernel(const TopkParams P) {
       }
       theta_hi = uint32_t(theta >> 32);
 
-      // ---- lower terms: pending entries [a0, a1) with doc <= phi, 32 at a time, one entry per lane ----
+      // ---- MaxScore: lists whose summed bounds stay below the threshold stop being streamed (they are probed for the
+      // candidates the remaining lists produce). Strict, with a margin for the rounding of the canonical sum. ----
+      if (!kAnd && T > 1u && P.wand) {
+        while (E > 1u && __fmul_rn(s_sfx[E - 1u], 1.000001f) < __uint_as_float(theta_hi)) {
 #pragma unroll
-      for (uint32_t t = 0; t + 1u < T; ++t) {
-        const uint32_t* ld = live_docs(t);
-        const float* ls = live_scores(t);
-        const uint4 dd = reinterpret_cast<const uint4*>(ld)[lane];
-        const uint32_t a1 = __popc(__ballot_sync(kFull, dd.x <= phi)) + __popc(__ballot_sync(kFull, dd.y <= phi)) +
-                            __popc(__ballot_sync(kFull, dd.z <= phi)) + __popc(__ballot_sync(kFull, dd.w <= phi));
-        for (uint32_t e0 = a0[t]; e0 < a1; e0 += 32u) {
-          const uint32_t e = e0 + lane;
-          bool alive = e < a1;
-          const uint32_t dv = alive ? ld[e] : kNoDoc;
-          const float sv = alive ? ls[e] : 0.f;
-#pragma unroll
-          for (uint32_t u = t + 1u; u < T; ++u) {
-            // absorbed by a later term's live block? (a pending doc can only sit in live blocks: everything a list
-            // holds before its live block is <= plo)
-            if (fr[u] == kNoDoc) continue;                         // uniform: nothing live in term u
-            const uint32_t* a = live_docs(u);
-            uint32_t pos = 0;
-#pragma unroll
-            for (uint32_t stp = 64u; stp; stp >>= 1) pos += (a[pos + stp - 1u] < dv) ? stp : 0u;
-            if (alive && a[pos] == dv) {
-              float* as = live_scores(u);
-              as[pos] = __fadd_rn(sv, as[pos]);                    // unique writer: docs are unique within term t
-              alive = false;
+          for (uint32_t t = 1; t < T; ++t)
+            if (t + 1u == E) {
+              // entries of the departing top list up to plo are complete (they may carry scores folded in from the
+              // lower lists): finalise them before its live block is abandoned
+              finalize_top(t, plo);
+              __syncwarp();
+              if (lane == 0) s_hint[warp][t] = cur[t] ? cur[t] - 1u : 0u;
+              fr[t] = kNoDoc; nxt[t] = kNoDoc; a0[t] = 128u;
             }
-          }
-          emit(alive, dv, sv);                                     // whatever is still alive is final
+          --E;
+          __syncwarp();
         }
-        a0[t] = a1;
-        __syncwarp();   // folds into later terms are visible before those terms are read
       }
-      // ---- top term: its block is finalised as a whole when it retires (every lower term has been folded in up to
-      // its last doc by then); lane l holds entries 4l .. 4l+3 ----
-      if (fr[T - 1u] <= phi || phi >= hi_w) {
-        const uint4 dd = reinterpret_cast<const uint4*>(live_docs(T - 1u))[lane];
-        const float4 ss = reinterpret_cast<const float4*>(live_scores(T - 1u))[lane];
-        const uint32_t dv[4] = {dd.x, dd.y, dd.z, dd.w};
-        const float sv[4] = {ss.x, ss.y, ss.z, ss.w};
-        const uint32_t first = 4u * lane;
-        bool want_any = false;
-        bool alive[4];
+
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          alive[j] = first + j >= a0[T - 1u] && dv[j] <= phi;      // pads are kNoDoc > phi
-          matched += alive[j] ? 1u : 0u;
-          want_any |= alive[j] && __float_as_uint(sv[j]) >= theta_hi;
-        }
-        if (__any_sync(kFull, want_any)) {
-#pragma unroll 1
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t d1 = j == 0 ? dv[0] : j == 1 ? dv[1] : j == 2 ? dv[2] : dv[3];
-            const float s1 = j == 0 ? sv[0] : j == 1 ? sv[1] : j == 2 ? sv[2] : sv[3];
-            const bool al = j == 0 ? alive[0] : j == 1 ? alive[1] : j == 2 ? alive[2] : alive[3];
-            bool want = al && __float_as_uint(s1) >= theta_hi;
-            unsigned long long key = 0ull;
-            if (want) { key = make_key(s1, P.seg.ordinal_base + d1); want = key > theta; }
-            append(want, key);
+      for (uint32_t t = 0; t < T; ++t) {
+        if (t + 1u < E) {
+          // ---- lower live terms: pending entries [a0, a1) with doc <= phi, 32 at a time, one entry per lane ----
+          if (nxt[t] > phi) continue;                              // uniform: nothing of this term is due
+          const uint32_t* ld = live_docs(t);
+          const float* ls = live_scores(t);
+          const uint4 dd = reinterpret_cast<const uint4*>(ld)[lane];
+          const uint32_t a1 = __popc(__ballot_sync(kFull, dd.x <= phi)) + __popc(__ballot_sync(kFull, dd.y <= phi)) +
+                              __popc(__ballot_sync(kFull, dd.z <= phi)) + __popc(__ballot_sync(kFull, dd.w <= phi));
+          for (uint32_t e0 = a0[t]; e0 < a1; e0 += 32u) {
+            const uint32_t e = e0 + lane;
+            bool alive = e < a1;
+            const uint32_t dv = alive ? ld[e] : kNoDoc;
+            const float sv = alive ? ls[e] : 0.f;
+#pragma unroll
+            for (uint32_t u = t + 1u; u < T; ++u) {
+              // absorbed by a later live term's block? (a pending doc can only sit in live blocks: everything a list
+              // holds before its live block is <= plo)
+              if (fr[u] == kNoDoc) continue;                       // uniform: nothing live in term u (exhausted / probed)
+              const uint32_t* a = live_docs(u);
+              uint32_t pos = 0;
+#pragma unroll
+              for (uint32_t stp = 64u; stp; stp >>= 1) pos += (a[pos + stp - 1u] < dv) ? stp : 0u;
+              if (alive && a[pos] == dv) {
+                float* as = live_scores(u);
+                as[pos] = __fadd_rn(sv, as[pos]);                  // unique writer: docs are unique within term t
+                alive = false;
+              }
+            }
+            finalize_entries(alive, dv, sv);                       // whatever is still alive is final
           }
+          a0[t] = a1;
+          __syncwarp();   // folds into later terms are visible before those terms are read
+          nxt[t] = a1 < 128u ? ld[a1] : kNoDoc;
+        } else if (t + 1u == E) {
+          // ---- top live term: its block is finalised as a whole when it retires (every lower term has been folded in
+          // up to its last doc by then); lane l holds entries 4l .. 4l+3 ----
+          if (fr[t] == phi || phi >= hi_w) { finalize_top(t, phi); a0[t] = 128u; }   // nothing of this block is pending any more
         }
-        // on the last step of a warp (phi == hi_w) the block may still hold docs beyond the sub-range: they belong
-        // to the next warp; a0 keeps what has been emitted if the same block is looked at again
-        a0[T - 1u] = 128u;
       }
       plo = phi;
       if (phi >= hi_w) break;
       if (*reinterpret_cast<volatile uint32_t*>(&ctl.full)) stream_rendezvous(&ctl, cand, P.cap, P.k, theta_global);
     }
-    // drain bulk copies that were issued but never consumed (they must not outlive the CTA's shared memory)
+    while (qcount) probe_round();
+    // drain bulk copies that were issued but never consumed (they must not outlive the CTA's shared memory):
+    // blocks cur and cur + 1 of every term
 #pragma unroll
     for (uint32_t t = 0; t < T; ++t) {
-      for (uint32_t b = cur[t]; b < min(s_qt[t].nblk, cur[t] + 2u); ++b) {   // issued: every block below cur + 2
-        const uint32_t r = b - start[t];
-        mbar_wait(&s_bar[warp][t][r & 1u], (r >> 1) & 1u);
-      }
+      for (uint32_t i = 0; i < 2u; ++i)
+        if (cur[t] + i < s_qt[t].nblk) { const uint32_t r = (rr[t] + i) & 3u; mbar_wait(&s_bar[warp][t][r & 1u], (r >> 1) & 1u); }
     }
     matched = warp_sum(matched);
     if (lane == 0 && matched) atomicAdd(&ctl.matched, matched);

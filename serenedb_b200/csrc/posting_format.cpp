@@ -360,7 +360,7 @@ bool read_pair(const uint8_t*& p, const uint8_t* end, MaxPair* m) {  // FreqNorm
 
 std::string stage_postings(const uint8_t* doc, size_t n, const TermMeta* terms, size_t n_terms, bool has_wand,
                            StagedPostings* sp) {
-  sp->arena.clear(); sp->blocks.clear(); sp->blk_max.clear(); sp->term_max.clear();
+  sp->arena.clear(); sp->blocks.clear(); sp->blk_max.clear(); sp->blk_anchor.clear(); sp->term_max.clear();
   sp->term_blk_begin.assign(1, 0); sp->term_docs.clear(); sp->term_bytes.clear(); sp->term_probe.clear();
   sp->n_postings = 0; sp->has_wand = has_wand;
   Arena arena{sp->arena};
@@ -386,6 +386,7 @@ std::string stage_postings(const uint8_t* doc, size_t n, const TermMeta* terms, 
       b.packed = pack_desc(kDeValues, kEValues, 1, 1, 0);
       sp->blocks.push_back(b);
       sp->blk_max.push_back(MaxPair{0, 0});  // unknown: resolved to "no bound" by the caller
+      for (uint32_t a = 0; a < 4; ++a) sp->blk_anchor.push_back(a == 3 ? 0u : 0xFFFFFFFFu);
     } else if (cnt > 1) {
       if (m.doc_start > n) return "term " + std::to_string(t) + ": doc_start beyond stream";
       const uint8_t* p = doc + m.doc_start;
@@ -425,6 +426,8 @@ std::string stage_postings(const uint8_t* doc, size_t n, const TermMeta* terms, 
         prev_last = b.last_doc;
         sp->blocks.push_back(b);
         sp->blk_max.push_back(MaxPair{0, 0});
+        for (uint32_t a = 0; a < 3; ++a) sp->blk_anchor.push_back(32u * a + 31u < len ? scratch[32u * a + 31u] : 0xFFFFFFFFu);
+        sp->blk_anchor.push_back(0u);
         if (denc == kDeBitset && fenc != kESvb) ++direct_blocks;
         p = fp + 1 + fsz;
         enc_bytes += 2 + dsz + fsz;

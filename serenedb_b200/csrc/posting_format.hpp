@@ -142,6 +142,9 @@ struct StagedPostings {
   std::vector<uint32_t> term_blk_begin;  // n_terms + 1
   std::vector<uint32_t> term_docs;     // docs_count per term
   std::vector<MaxPair> blk_max;        // per block; blocks without a skip entry carry the term's root pair
+  std::vector<uint32_t> blk_anchor;    // per block 4 x u32: doc ids of postings 31, 63, 95 (0xFFFFFFFF past the block's
+                                       // length) and 0 -- lets one GPU lane find a doc inside a bit-packed block by
+                                       // summing at most 32 gaps (probes of non-essential / conjunction lists)
   std::vector<MaxPair> term_max;       // per term root pair ({0,0} when !has_wand)
   std::vector<uint64_t> term_bytes;    // per term: encoded block bytes in the .doc stream (headers + payloads)
   std::vector<uint8_t> term_probe;     // per term: 1 when (nearly) every full block is a bitset with random-access freqs

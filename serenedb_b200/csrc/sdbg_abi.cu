@@ -80,6 +80,7 @@ struct sdbg_segment {
   // postings
   void* d_arena = nullptr;
   void* d_blocks = nullptr;
+  void* d_anchor = nullptr;
   void* d_blkmax = nullptr;
   std::vector<uint32_t> term_blk_begin, term_docs;
   std::vector<MaxPair> term_max;
@@ -87,6 +88,7 @@ struct sdbg_segment {
   std::vector<uint64_t> term_bytes;
   uint64_t arena_bytes = 0, n_blocks = 0, n_postings = 0;
   bool has_wand = false;
+  float wand_b = 0.75f;   // the b the block-max (freq, norm) pairs were chosen for (BM25 default unless told otherwise)
   // norms
   void* d_norms = nullptr;
   uint32_t norm_width = 0;
@@ -269,6 +271,8 @@ namespace {
 void free_postings(sdbg_segment* s) {
   if (s->d_arena) cudaFree(s->d_arena);
   if (s->d_blocks) cudaFree(s->d_blocks);
+  if (s->d_anchor) cudaFree(s->d_anchor);
+  s->d_anchor = nullptr;
   if (s->d_blkmax) cudaFree(s->d_blkmax);
   s->d_arena = s->d_blocks = s->d_blkmax = nullptr;
 }
@@ -288,6 +292,12 @@ extern "C" void sdbg_segment_destroy(sdbg_segment* s) {
   if (s->d_deleted) cudaFree(s->d_deleted);
   for (auto& kv : s->cols) free_column(kv.second);
   delete s;
+}
+
+extern "C" int sdbg_segment_set_wand_b(sdbg_segment* s, float wand_b) {
+  if (!s) return SDBG_EINVAL;
+  s->wand_b = wand_b;
+  return SDBG_OK;
 }
 
 extern "C" int sdbg_stage_docs_mask(sdbg_segment* s, const uint32_t* deleted_docs, size_t n) {
@@ -328,6 +338,8 @@ int upload_postings(sdbg_segment* s, const StagedPostings& sp) {
     CU(c, cudaStreamSynchronize(c->stream));
   }
   CU(c, cudaMalloc(&s->d_blkmax, std::max<size_t>(sp.blk_max.size() * sizeof(MaxPair), 16)));
+  CU(c, cudaMalloc(&s->d_anchor, std::max<size_t>(sp.blk_anchor.size() * 4, 16)));
+  CU(c, cudaMemcpyAsync(s->d_anchor, sp.blk_anchor.data(), sp.blk_anchor.size() * 4, cudaMemcpyHostToDevice, c->stream));
   CU(c, cudaMemcpyAsync(s->d_arena, sp.arena.data(), sp.arena.size(), cudaMemcpyHostToDevice, c->stream));
   CU(c, cudaMemcpyAsync(s->d_blocks, sp.blocks.data(), sp.blocks.size() * sizeof(BlockDesc), cudaMemcpyHostToDevice, c->stream));
   CU(c, cudaMemcpyAsync(s->d_blkmax, sp.blk_max.data(), sp.blk_max.size() * sizeof(MaxPair), cudaMemcpyHostToDevice, c->stream));
@@ -479,6 +491,7 @@ PostingsDev postings_view(const sdbg_segment* s, uint32_t ordinal_base) {
   p.arena = static_cast<const uint4*>(s->d_arena);
   p.blocks = static_cast<const uint4*>(s->d_blocks);
   p.blk_max = static_cast<const uint2*>(s->d_blkmax);
+  p.anchors = static_cast<const uint4*>(s->d_anchor);
   p.norms = static_cast<const uint8_t*>(s->d_norms);
   p.norm_width = s->norm_width;
   p.deleted = static_cast<const uint32_t*>(s->d_deleted);
@@ -550,9 +563,10 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
   // disjunction of T = 1..4 terms (bm25_stream.cuh). The stream kernel covers plain BM25 disjunctions without a column
   // filter or deleted-doc mask; everything else (AND, hybrid, BM15 / BM1 forms, > 4 terms) stays on the legacy kernel.
   struct WorkItem { uint32_t q, g, chunk, list; uint64_t weight; uint32_t cls; };
-  constexpr uint32_t kClasses = 2 + kStreamMaxTerms;
+  constexpr uint32_t kClasses = 3 + kStreamMaxTerms;     // last class: conjunctions on the stream kernel (lead list + probes)
+  constexpr uint32_t kClsAnd = 2 + kStreamMaxTerms;
   const bool level2 = c->wand >= 2 && kind != SDBG_QUERY_AND && k1 != 0.f && b != 0.f;
-  const bool stream_ok = env_int("SDBG_STREAM", 1) != 0 && kind != SDBG_QUERY_AND && !filt && k1 != 0.f && b != 0.f &&
+  const bool stream_ok = env_int("SDBG_STREAM", 1) != 0 && k1 != 0.f && b != 0.f &&
                          size_t(pl.cap) * 8 + size_t(kStreamMaxTerms) * (kLutFreqs * 1024 + kTopkWarps * kStreamTermBytes) <= 200 * 1024;
   std::vector<std::array<size_t, kClasses>> n_cls(n_segs);
   for (auto& a : n_cls) a.fill(0);
@@ -572,10 +586,11 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
       const uint32_t nt = term_off[q + 1] - term_off[q];
       // Driver mode (pruning level 2) pays only when the largest list can be probed without decoding blocks; the
       // other queries run the plain kernel, which is lighter (fewer registers, no probe buffers, level-1 planner).
-      const bool drive_q = level2 && s->has_wand && nt >= 2 && largest_term < s->term_probe.size() &&
+      const bool drive_q = level2 && s->has_wand && b == s->wand_b && nt >= 2 && largest_term < s->term_probe.size() &&
                            s->term_probe[largest_term] != 0;
       uint32_t cls = drive_q ? 0u : 1u;
-      if (stream_ok && nt <= kStreamMaxTerms && !s->d_deleted) cls = 2u + (nt - 1u);
+      if (stream_ok && kind == SDBG_QUERY_AND && env_int("SDBG_STREAM_AND", 1) != 0) cls = kClsAnd;
+      else if (stream_ok && kind != SDBG_QUERY_AND && nt <= kStreamMaxTerms) cls = 2u + (nt - 1u);
       uint32_t g = uint32_t(std::max<uint64_t>(pl.G, (postings + chain_target - 1) / chain_target));
       g = std::min(g, max_chains);
       g = std::min(g, std::max(1u, s->n_docs / 4096u));
@@ -653,17 +668,22 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
   // shared memory of the stream kernel: candidates | score table | per warp (live blocks + prefetch slots)
   bool use_lut[n_segs ? n_segs : 1];
   for (size_t si = 0; si < n_segs; ++si) use_lut[si] = segs[si]->norm_width == 1 && env_int("SDBG_STREAM_LUT", 1) != 0;
-  auto stream_smem = [&](uint32_t T, bool lut) { return size_t(pl.cap) * 8 + (lut ? size_t(T) * kLutFreqs * 1024 : 0) + size_t(kTopkWarps) * T * kStreamTermBytes; };
+  auto stream_smem = [&](uint32_t T, bool lut, bool conj) {
+    return size_t(pl.cap) * 8 + (lut ? size_t(T) * kLutFreqs * 1024 : 0) + size_t(kTopkWarps) * (T * kStreamTermBytes + (conj ? 1024 : 0));
+  };
   if (!c->topk_attr_set) {
     CU(c, cudaFuncSetAttribute(bm25_topk_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(c, cudaFuncSetAttribute(bm25_topk_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(c, cudaFuncSetAttribute(bm25_topk_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(c, cudaFuncSetAttribute(bm25_topk_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 #define SDBG_STREAM_ATTR(TT) \
-    CU(c, cudaFuncSetAttribute(bm25_stream_kernel<TT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-    CU(c, cudaFuncSetAttribute(bm25_stream_kernel<TT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))
+    CU(c, cudaFuncSetAttribute(bm25_stream_kernel<TT, false, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+    CU(c, cudaFuncSetAttribute(bm25_stream_kernel<TT, true, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+    CU(c, cudaFuncSetAttribute(bm25_stream_kernel<TT, true, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))
     SDBG_STREAM_ATTR(1); SDBG_STREAM_ATTR(2); SDBG_STREAM_ATTR(3); SDBG_STREAM_ATTR(4);
 #undef SDBG_STREAM_ATTR
+    CU(c, cudaFuncSetAttribute(bm25_stream_kernel<1, false, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(c, cudaFuncSetAttribute(bm25_stream_kernel<1, true, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(c, cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     c->topk_attr_set = true;
   }
@@ -692,7 +712,10 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
       P.cand = static_cast<unsigned long long*>(b_cand.p);
       P.cand_n = static_cast<uint32_t*>(b_candn.p);
       P.k = k; P.cap = pl.cap; P.conjunction = kind == SDBG_QUERY_AND ? 1 : 0;
-      const int wand = (c->wand && s->has_wand && k1 != 0.f && b != 0.f) ? c->wand : 0;   // the staged block-max pairs are BM25's
+      // The staged block-max pairs are maximisers for BM25 with the index-time b only (FreqNormProducer::CmpBm25,
+      // wand_writer.hpp:142-175; the order of two pairs does not depend on k); the reference enables WAND only when
+      // Scorer::equals matches (PostingsReaderImpl::WandIterator, reader.hpp:457-501). Any other b: exhaustive.
+      const int wand = (c->wand && s->has_wand && k1 != 0.f && b != 0.f && b == s->wand_b) ? c->wand : 0;
       const uint4* work = reinterpret_cast<const uint4*>(static_cast<const char*>(b_qt.p) + qt_pad) + work_done;
       work_done += seg_work[si].size();
       for (uint32_t cls = 0; cls < kClasses; ++cls) {
@@ -709,14 +732,22 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
           P.wand = std::min(wand, 1);
           if (pl.budget == 16) bm25_topk_kernel<16, false><<<unsigned(n), kTopkThreads, pl.smem, st>>>(P);
           else bm25_topk_kernel<32, false><<<unsigned(n), kTopkThreads, pl.smem, st>>>(P);
+        } else if (cls == kClsAnd) {
+          const bool lut = use_lut[si];
+          const size_t sm = stream_smem(1, lut, true);
+          P.wand = 0;                                  // conjunctions are exact: every candidate of the lead list is probed
+          if (lut) bm25_stream_kernel<1, true, 3, true><<<unsigned(n), kTopkThreads, sm, st>>>(P);
+          else bm25_stream_kernel<1, false, 3, true><<<unsigned(n), kTopkThreads, sm, st>>>(P);
         } else {
           const uint32_t T = cls - 1u;
           const bool lut = use_lut[si];
-          const size_t sm = stream_smem(T, lut);
+          const bool occ2 = env_int("SDBG_STREAM_OCC", 3) == 2;   // 2 CTAs / SM with up to 128 registers per thread
+          const size_t sm = stream_smem(T, lut, false);
           P.wand = wand;
 #define SDBG_STREAM_LAUNCH(TT) \
-          if (lut) bm25_stream_kernel<TT, true><<<unsigned(n), kTopkThreads, sm, st>>>(P); \
-          else bm25_stream_kernel<TT, false><<<unsigned(n), kTopkThreads, sm, st>>>(P)
+          if (lut && occ2) bm25_stream_kernel<TT, true, 2, false><<<unsigned(n), kTopkThreads, sm, st>>>(P); \
+          else if (lut) bm25_stream_kernel<TT, true, 3, false><<<unsigned(n), kTopkThreads, sm, st>>>(P); \
+          else bm25_stream_kernel<TT, false, 3, false><<<unsigned(n), kTopkThreads, sm, st>>>(P)
           switch (T) {
             case 1: SDBG_STREAM_LAUNCH(1); break;
             case 2: SDBG_STREAM_LAUNCH(2); break;

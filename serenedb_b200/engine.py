@@ -177,11 +177,12 @@ class Segment:
             pass
 
     # ---- staging ----
-    def stage_postings(self, doc_bytes, metas, has_wand=True):
+    def stage_postings(self, doc_bytes, metas, has_wand=True, wand_b=0.75):
         doc_bytes = np.ascontiguousarray(doc_bytes, dtype=np.uint8)
         metas = np.ascontiguousarray(metas, dtype=TERM_META_DTYPE)
         N.check(N.lib().sdbg_stage_postings(self._h, _ptr(doc_bytes), len(doc_bytes), _ptr(metas), len(metas),
                                             1 if has_wand else 0), self.ctx._h)
+        N.check(N.lib().sdbg_segment_set_wand_b(self._h, float(wand_b)), self.ctx._h)   # pruning only for scorers with this b
         self.term_docs = metas["docs_count"].astype(np.uint64)
 
     def stage_norms(self, norm_bytes, byte_width):

@@ -19,12 +19,12 @@ postings = sum(int(dc[t]) for q in queries for t in q)
 batch = sdb.PreparedBatch(reader, queries, sdb.OR, scorer, 1000)
 d_keys = torch.empty(len(queries) * 1000, dtype=torch.int64, device="cuda:0")
 ref = None
-configs = [({"SDBG_STREAM": "0"}, 0), ({"SDBG_STREAM": "1"}, 0), ({"SDBG_STREAM": "1", "SDBG_STREAM_LUT": "0"}, 0),
-           ({"SDBG_STREAM": "0"}, 2), ({"SDBG_STREAM": "1"}, 2)]
+configs = [({"SDBG_STREAM": "0"}, 0), ({"SDBG_STREAM": "1"}, 0), ({"SDBG_STREAM": "1", "SDBG_STREAM_OCC": "2"}, 0), ({"SDBG_STREAM": "1", "SDBG_STREAM_LUT": "0"}, 0),
+           ({"SDBG_STREAM": "0"}, 2)]
 if os.environ.get("PROBE_ONLY_STREAM"):
     configs = [({"SDBG_STREAM": "1"}, 0)]
 for env, wand in configs:
-    for k_ in ("SDBG_STREAM", "SDBG_STREAM_LUT"):
+    for k_ in ("SDBG_STREAM", "SDBG_STREAM_LUT", "SDBG_STREAM_OCC"):
         os.environ.pop(k_, None)
     os.environ.update(env)
     ctx.set_wand(wand)
