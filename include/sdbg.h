@@ -221,6 +221,21 @@ int sdbg_debug_stage_host(const uint8_t* doc_file, size_t n, const sdbg_term_met
                           uint32_t* prev_last, uint32_t* packed, uint32_t* max_freq, uint32_t* max_norm,
                           uint64_t* arena_bytes);
 
+/* ---- collectives over NVLink (NCCL, resolved at run time with dlopen: libsdbg.so does not link it) -------------
+   One communicator per context, everything enqueued on the context's stream. A C++ host needs nothing but these
+   calls: rank 0 creates the id, the host ships its 128 bytes to the other ranks by whatever channel it has
+   (the reference's own RPC, MPI, a file), every rank calls sdbg_dist_init. */
+#define SDBG_DIST_ID_BYTES 128
+int sdbg_dist_unique_id(uint8_t* id128);
+int sdbg_dist_init(sdbg_ctx*, const uint8_t* id128, int rank, int world);
+int sdbg_dist_destroy(sdbg_ctx*);
+int sdbg_dist_allreduce_i64(sdbg_ctx*, void* d_buf, size_t n);                          /* in place, SUM */
+int sdbg_dist_allgather(sdbg_ctx*, const void* d_send, void* d_recv, size_t bytes_per_rank);
+/* Dense GROUP BY partials (sdbg_filter_groupby_partial) of every rank -> global partials on every rank with ONE
+   ncclAllReduce: counts, SUM(int) limbs and SUM(double) as 120-bit fixed point share one int64 buffer (exact and
+   independent of the rank order). abs_bound >= |SUM(double column)| over all ranks, identical on every rank. */
+int sdbg_dist_groupby_merge(sdbg_ctx*, void* d_i64, void* d_f64, uint64_t span, double abs_bound);
+
 #ifdef __cplusplus
 }
 #endif

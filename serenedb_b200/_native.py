@@ -70,6 +70,12 @@ SIGNATURES = {
     "sdbg_bm25_collect": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_float, C.c_float, C.POINTER(BM25Term)]),
     "sdbg_stage_docs_mask": (C.c_int, [_vp, _vp, _sz]),
     "sdbg_segment_set_wand_b": (C.c_int, [_vp, C.c_float]),
+    "sdbg_dist_unique_id": (C.c_int, [_vp]),
+    "sdbg_dist_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "sdbg_dist_destroy": (C.c_int, [_vp]),
+    "sdbg_dist_allreduce_i64": (C.c_int, [_vp, _vp, _sz]),
+    "sdbg_dist_allgather": (C.c_int, [_vp, _vp, _vp, _sz]),
+    "sdbg_dist_groupby_merge": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_double]),
     "sdbg_bm25_topk": (C.c_int, [_vp, _sz, C.c_int, _vp, _sz, C.c_float, C.c_float, _vp, C.c_uint32, C.c_float, _vp, _u32p,
                                  _u64p, _f32p]),
     "sdbg_bm25_topk_batch": (C.c_int, [_vp, _sz, C.c_int, _vp, _vp, _sz, C.c_float, C.c_float, _vp, C.c_uint32, C.c_float,

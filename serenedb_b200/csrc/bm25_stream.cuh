@@ -387,6 +387,10 @@ bm25_stream_kernel(const TopkParams P) {
   }
   __syncthreads();
   unsigned long long* const theta_global = P.theta + q;
+  // The buffer is compacted when it holds k + max(k, 256) candidates (rounded up to the CTA size, at most its
+  // capacity): for small k the threshold then follows the running k-th best closely instead of waiting for 2048
+  // accepted candidates, which is what block-max skipping lives on.
+  const uint32_t lim = min(P.cap, (P.k + max(P.k, 256u) + kTopkThreads - 1u) / kTopkThreads * kTopkThreads);
   const bool doc_checks = P.filt.values != nullptr || P.seg.deleted != nullptr;   // hybrid filter / DocumentMask on final docs
   const uint8_t* const norms_m1 = P.seg.norms ? P.seg.norms - 1 : nullptr;   // row = doc - 1 (1-byte norms: kLut)
 
@@ -399,7 +403,8 @@ bm25_stream_kernel(const TopkParams P) {
     uint32_t a0[T] = {};      // first pending entry of the live block
     uint32_t nxt[T] = {};     // its doc id (kNoDoc: none) -- lower terms only
     uint32_t matched = 0;     // per lane; summed at the end
-    uint32_t skip0 = 0u;      // term 0, bit i: window block i cannot reach the threshold (judged when the window was loaded)
+    uint32_t skip0 = 0u;      // term 0, bit i: window block i cannot reach the threshold
+    uint32_t skip_theta = 0u; // threshold (score bits) the verdicts were made with
     unsigned long long theta = 0ull;
     uint32_t theta_hi = 0u;
 
@@ -412,10 +417,10 @@ bm25_stream_kernel(const TopkParams P) {
         if (lane == 0) base = atomicAdd(&ctl.ncand, uint32_t(__popc(wbal)));
         base = __shfl_sync(kFull, base, 0);
         const uint32_t pos = base + __popc(wbal & ((1u << lane) - 1u));
-        if (want && pos < P.cap) { cand[pos] = key; want = false; }
+        if (want && pos < lim) { cand[pos] = key; want = false; }
         if (!__any_sync(kFull, want)) break;
         if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&ctl.full) = 1u;
-        stream_rendezvous(&ctl, cand, P.cap, P.k, theta_global);
+        stream_rendezvous(&ctl, cand, lim, P.k, theta_global);
         want = want && key > *reinterpret_cast<volatile unsigned long long*>(&ctl.theta);
       }
     };
@@ -463,7 +468,7 @@ bm25_stream_kernel(const TopkParams P) {
         } else {
           if (found) s = __fadd_rn(s, su);                       // ascending-cost order: probed lists come last
           // even with the best the remaining lists can add this doc stays below the threshold
-          if (alive && __fmul_rn(__fadd_rn(s, s_sfx[u + 1u]), 1.000001f) < theta_score) alive = false;
+          if (!(P.wand & 64) && alive && __fmul_rn(__fadd_rn(s, s_sfx[u + 1u]), 1.000001f) < theta_score) alive = false;
         }
       }
       if (kAnd) {
@@ -479,7 +484,7 @@ bm25_stream_kernel(const TopkParams P) {
         matched += alive ? 1u : 0u;
         if (E == T) { test_and_append(alive, dv, sv); return; }
         // MaxScore: a doc that cannot reach the threshold even with every probed list's bound is dropped unprobed
-        alive = alive && !(__fmul_rn(__fadd_rn(sv, s_sfx[E]), 1.000001f) < __uint_as_float(theta_hi));
+        if (!(P.wand & 32)) alive = alive && !(__fmul_rn(__fadd_rn(sv, s_sfx[E]), 1.000001f) < __uint_as_float(theta_hi));
       }
       const uint32_t bal = __ballot_sync(kFull, alive);
       if (bal) {
@@ -540,24 +545,27 @@ bm25_stream_kernel(const TopkParams P) {
         if (units) bulk_g2s(slot_of(t, sl), P.seg.arena + off, units * 16u, bar);
       }
     };
+    // Single live list (one term, or MaxScore has demoted the others): a block whose block-max bound plus the probed
+    // lists' bounds stays below the threshold is never decoded -- SingleWandIterator's block skip
+    // (formats/posting/iterator_score.hpp:218-233, 513-632). Judged for the 32 blocks of term 0's descriptor window
+    // whenever the window moves or the threshold has risen; the threshold only rises, so a verdict stays valid.
+    auto judge_window = [&](uint32_t first) {
+      bool skip = false;
+      if (!kAnd && P.wand && !(P.wand & 16) && E == 1u && first + lane < s_qt[0].nblk) {
+        const uint2 fn = __ldg(P.seg.blk_max + s_qt[0].blk_begin + first + lane);
+        if (fn.x != 0u) {
+          const float bound = bm25(fn.x, fn.y, s_qt[0].c0, s_qt[0].norm_const, s_qt[0].norm_length);
+          skip = __fmul_rn(__fadd_rn(bound, s_sfx[1]), 1.000001f) < __uint_as_float(theta_hi);
+        }
+      }
+      skip0 = __ballot_sync(kFull, skip);
+      skip_theta = theta_hi;
+    };
     // Window = descriptors [first, first + 32) of the term (zeros past the sentinel).
     auto load_window = [&](const uint32_t t, uint32_t first) {
       __syncwarp();
       desc_win(t)[lane] = (first + lane <= s_qt[t].nblk) ? __ldg(P.seg.blocks + s_qt[t].blk_begin + first + lane) : make_uint4(0, 0, 0, 0);
-      if (t == 0u) {
-        // Single live list (one term, or MaxScore has demoted the others): a block whose block-max bound plus the
-        // probed lists' bounds stays below the threshold is never decoded -- SingleWandIterator's block skip
-        // (formats/posting/iterator_score.hpp:218-233, 513-632). The threshold only rises, so a verdict stays valid.
-        bool skip = false;
-        if (!kAnd && P.wand && E == 1u && first + lane < s_qt[0].nblk) {
-          const uint2 fn = __ldg(P.seg.blk_max + s_qt[0].blk_begin + first + lane);
-          if (fn.x != 0u) {
-            const float bound = bm25(fn.x, fn.y, s_qt[0].c0, s_qt[0].norm_const, s_qt[0].norm_length);
-            skip = __fmul_rn(__fadd_rn(bound, s_sfx[1]), 1.000001f) < __uint_as_float(theta_hi);
-          }
-        }
-        skip0 = __ballot_sync(kFull, skip);
-      }
+      if (t == 0u) judge_window(first);
       __syncwarp();
     };
 
@@ -695,13 +703,14 @@ bm25_stream_kernel(const TopkParams P) {
       // ---- MaxScore: lists whose summed bounds stay below the threshold stop being streamed (they are probed for the
       // candidates the remaining lists produce). Strict, with a margin for the rounding of the canonical sum. ----
       if (!kAnd && T > 1u && P.wand) {
-        while (E > 1u && __fmul_rn(s_sfx[E - 1u], 1.000001f) < __uint_as_float(theta_hi)) {
+        while (E > ((P.wand & 128) ? 2u : 1u) && __fmul_rn(s_sfx[E - 1u], 1.000001f) < __uint_as_float(theta_hi)) {
 #pragma unroll
           for (uint32_t t = 1; t < T; ++t)
             if (t + 1u == E) {
               // entries of the departing top list up to plo are complete (they may carry scores folded in from the
               // lower lists): finalise them before its live block is abandoned
               finalize_top(t, plo);
+              while (qcount) probe_round();   // ring entries are owed the lists E .. : empty it before E changes
               __syncwarp();
               if (lane == 0) s_hint[warp][t] = cur[t] ? cur[t] - 1u : 0u;
               fr[t] = kNoDoc; nxt[t] = kNoDoc; a0[t] = 128u;
@@ -710,6 +719,8 @@ bm25_stream_kernel(const TopkParams P) {
           __syncwarp();
         }
       }
+
+      if (!kAnd && P.wand && E == 1u && theta_hi != skip_theta) judge_window(cur[0] - widx[0]);
 
 #pragma unroll
       for (uint32_t t = 0; t < T; ++t) {
@@ -754,7 +765,7 @@ bm25_stream_kernel(const TopkParams P) {
       }
       plo = phi;
       if (phi >= hi_w) break;
-      if (*reinterpret_cast<volatile uint32_t*>(&ctl.full)) stream_rendezvous(&ctl, cand, P.cap, P.k, theta_global);
+      if (*reinterpret_cast<volatile uint32_t*>(&ctl.full)) stream_rendezvous(&ctl, cand, lim, P.k, theta_global);
     }
     while (qcount) probe_round();
     // drain bulk copies that were issued but never consumed (they must not outlive the CTA's shared memory):
@@ -770,10 +781,10 @@ bm25_stream_kernel(const TopkParams P) {
   __syncwarp();
   if (lane == 0) atomicSub(&ctl.active, 1u);
   // finished warps keep serving compactions until every warp of the CTA is done
-  while (!stream_rendezvous(&ctl, cand, P.cap, P.k, theta_global)) {}
+  while (!stream_rendezvous(&ctl, cand, lim, P.k, theta_global)) {}
 
   // ---- chain epilogue: best k, sorted descending ----
-  stream_compact(&ctl, cand, P.cap, P.k, theta_global);
+  stream_compact(&ctl, cand, lim, P.k, theta_global);
   const uint32_t n_out = min(ctl.ncand, P.k);
   uint32_t sort_n = 256u;
   while (sort_n < n_out) sort_n <<= 1;

@@ -2,6 +2,8 @@
 // preparation and kernel launches. Host code only orchestrates; all per-posting / per-row work is
 // in bm25_kernels.cuh and column_kernels.cuh. There is no CPU fallback anywhere in this file.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is resolved at run time (sdbg_dist_init)
 
 #include <algorithm>
 #include <array>
@@ -65,6 +67,10 @@ struct sdbg_ctx {
   void* flush = nullptr;
   size_t flush_bytes = 0;
   bool topk_attr_set = false;
+  void* nccl_comm = nullptr;   // ncclComm_t once sdbg_dist_init ran
+  unsigned long long* h_oor = nullptr;   // pinned: out-of-range key count of the last deferred GROUP BY partial
+  bool oor_pending = false;
+  int dist_rank = 0, dist_world = 1;
   bool merge_attr_set = false;
   // optional per-kernel timing: CUDA events recorded on `stream` around the hot kernels
   int wand = 1;       // block-max pruning level: 0 off (exact total_matches), 1 planner-level block/window skips, 2 + exact-partial-score skips of the largest term
@@ -196,14 +202,17 @@ extern "C" int sdbg_init(int device, sdbg_ctx** out) {
   return SDBG_OK;
 }
 
+extern "C" int sdbg_dist_destroy(sdbg_ctx* c);
 extern "C" void sdbg_destroy(sdbg_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (auto& b : c->scratch) if (b.p) cudaFree(b.p);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  if (c->h_oor) cudaFreeHost(c->h_oor);
   if (c->flush) cudaFree(c->flush);
   cudaStreamSynchronize(c->stream2);
+  sdbg_dist_destroy(c);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
   cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
   cudaStreamDestroy(c->stream2);
@@ -218,7 +227,14 @@ extern "C" int sdbg_timer_stop(sdbg_ctx* c, float* ms) {
   CU(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
   return SDBG_OK;
 }
-extern "C" int sdbg_sync(sdbg_ctx* c) { CU(c, cudaStreamSynchronize(c->stream)); return SDBG_OK; }
+extern "C" int sdbg_sync(sdbg_ctx* c) {
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (c->oor_pending) {
+    c->oor_pending = false;
+    if (*c->h_oor) return fail(c, SDBG_EINVAL, "GROUP BY key outside [key_min, key_min + span)");
+  }
+  return SDBG_OK;
+}
 extern "C" uint64_t sdbg_launch_count(const sdbg_ctx* c) { return c ? c->launches : 0; }
 extern "C" int sdbg_flush_l2(sdbg_ctx* c) {
   CU(c, cudaSetDevice(c->device));
@@ -743,7 +759,7 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
           const bool lut = use_lut[si];
           const bool occ2 = env_int("SDBG_STREAM_OCC", 3) == 2;   // 2 CTAs / SM with up to 128 registers per thread
           const size_t sm = stream_smem(T, lut, false);
-          P.wand = wand;
+          P.wand = wand ? (wand | (env_int("SDBG_STREAM_DBG", 0) & 0xF0)) : 0;   // debug bits 16/32/64/128 switch parts of the pruning off
 #define SDBG_STREAM_LAUNCH(TT) \
           if (lut && occ2) bm25_stream_kernel<TT, true, 2, false><<<unsigned(n), kTopkThreads, sm, st>>>(P); \
           else if (lut) bm25_stream_kernel<TT, true, 3, false><<<unsigned(n), kTopkThreads, sm, st>>>(P); \
@@ -1131,7 +1147,7 @@ constexpr int kGroupByTileRows = 512;   // tile of the default TMA shape; packed
 
 int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred* preds, size_t n_preds, uint64_t key_field,
                    int64_t key_min, uint64_t span, uint64_t sum_int_field, uint64_t avg_f64_field, void* d_i64, void* d_f64,
-                   GroupPlan* plan_out) {
+                   GroupPlan* plan_out, bool defer_check = false) {
   sdbg_ctx* c = segs[0]->ctx;
   int rc;
   // table | cnt_f | out_of_range
@@ -1362,10 +1378,18 @@ int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred
                                                                plan.pack_shift, plan.pack_tables, plan.pack_bias, plan.fix_limb, plan.fix_eunit);
   ++c->launches;
   CU(c, cudaGetLastError());
-  unsigned long long h_oor = 0;
-  CU(c, cudaMemcpyAsync(&h_oor, oor, 8, cudaMemcpyDeviceToHost, c->stream));
-  CU(c, cudaStreamSynchronize(c->stream));
-  if (h_oor) return fail(c, SDBG_EINVAL, "GROUP BY key outside [key_min, key_min + span)");
+  if (defer_check) {
+    // the partial path stays asynchronous (a collective usually follows on the same stream): the out-of-range count
+    // lands in pinned memory and is looked at by the next call that synchronises (finalize / sdbg_sync)
+    if (!c->h_oor) CU(c, cudaHostAlloc(reinterpret_cast<void**>(&c->h_oor), 8, cudaHostAllocDefault));
+    CU(c, cudaMemcpyAsync(c->h_oor, oor, 8, cudaMemcpyDeviceToHost, c->stream));
+    c->oor_pending = true;
+  } else {
+    unsigned long long h_oor = 0;
+    CU(c, cudaMemcpyAsync(&h_oor, oor, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (h_oor) return fail(c, SDBG_EINVAL, "GROUP BY key outside [key_min, key_min + span)");
+  }
   if (plan_out) *plan_out = plan;
   return SDBG_OK;
 }
@@ -1447,10 +1471,9 @@ extern "C" int sdbg_filter_groupby_partial(sdbg_segment* const* segs, size_t n_s
   if (!segs || !n_segs || !d_i64 || !d_f64 || !key_span || (!preds && n_preds)) return SDBG_EINVAL;
   CU(segs[0]->ctx, cudaSetDevice(segs[0]->ctx->device));
   GroupPlan plan;
-  const int rc = groupby_launch(segs, n_segs, preds, n_preds, key_field, key_min, key_span, sum_int_field, avg_f64_field, d_i64, d_f64, &plan);
-  if (rc) return rc;
-  // Narrow sums are re-expressed as limbs so that every rank's buffers add up the same way.
-  return SDBG_OK;
+  // asynchronous: nothing here waits for the GPU (SUM(int) leaves as two limbs, total = hi * 2^32 + lo; a narrow sum
+  // keeps the whole value in lo -- sdbg_dist_groupby_merge normalises the limbs before they are all-reduced)
+  return groupby_launch(segs, n_segs, preds, n_preds, key_field, key_min, key_span, sum_int_field, avg_f64_field, d_i64, d_f64, &plan, true);
 }
 
 extern "C" int sdbg_groupby_finalize(sdbg_ctx* c, int64_t key_min, uint64_t span, const void* d_i64, const void* d_f64,
@@ -1467,6 +1490,10 @@ extern "C" int sdbg_groupby_finalize(sdbg_ctx* c, int64_t key_min, uint64_t span
   CU(c, cudaMemcpyAsync(h_i, d_i64, span * 32, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaMemcpyAsync(h_f, d_f64, span * 8, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
+  if (c->oor_pending) {
+    c->oor_pending = false;
+    if (*c->h_oor) return fail(c, SDBG_EINVAL, "GROUP BY key outside [key_min, key_min + span)");
+  }
   uint64_t n = 0;
   for (uint64_t i = 0; i < span; ++i) {
     if (h_i[i] == 0) continue;
@@ -1517,6 +1544,155 @@ extern "C" int sdbg_filter_groupby(sdbg_segment* const* segs, size_t n_segs, con
   GroupPlan plan;
   if ((rc = groupby_launch(segs, n_segs, preds, n_preds, key_field, kmin, span, sum_int_field, avg_f64_field, d_i64, d_f64, &plan))) return rc;
   return sdbg_groupby_finalize(c, kmin, span, d_i64, d_f64, out, cap, n_out);
+}
+
+// ------------------------------------------------------------------------------------------
+// Collectives over NVLink for a C++ host (no torch): NCCL resolved lazily with dlopen, so libsdbg.so itself does not
+// link it and a process that already carries an NCCL (e.g. PyTorch's bundled one: same SONAME) shares that copy.
+// Everything below is enqueued on the context's stream: a partial aggregate or a top-k batch flows kernel ->
+// collective -> kernel without a host synchronisation in between.
+// ------------------------------------------------------------------------------------------
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok() const { return lib && GetUniqueId && CommInitRank && CommDestroy && AllReduce && AllGather && GetErrorString; }
+};
+NcclApi& nccl_api() {
+  static NcclApi api = [] {
+    NcclApi a;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+      a.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+      if (a.lib) break;
+    }
+    if (a.lib) {
+      a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(a.lib, "ncclGetUniqueId"));
+      a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(a.lib, "ncclCommInitRank"));
+      a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(a.lib, "ncclCommDestroy"));
+      a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(a.lib, "ncclAllReduce"));
+      a.AllGather = reinterpret_cast<decltype(a.AllGather)>(dlsym(a.lib, "ncclAllGather"));
+      a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(a.lib, "ncclGetErrorString"));
+    }
+    return a;
+  }();
+  return api;
+}
+#define NC(c, call)                                                                          \
+  do {                                                                                       \
+    const ncclResult_t r_ = (call);                                                          \
+    if (r_ != ncclSuccess) return fail((c), SDBG_ECUDA, std::string("NCCL: ") + nccl_api().GetErrorString(r_)); \
+  } while (0)
+
+// SUM(double) partials as fixed point: x / 2^eunit rounded to a 120-bit integer, two signed 60-bit limbs in int64 --
+// sums of up to 8 ranks cannot overflow a limb, the integer all-reduce is exact and independent of the rank order,
+// and the only rounding left is the final conversion back to double.
+__global__ void __launch_bounds__(256)
+dist_pack_kernel(const long long* __restrict__ part_i64, const double* __restrict__ part_f64, uint64_t span, int eunit,
+                 long long* __restrict__ wire /* [6 * span] */) {
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < span; i += uint64_t(gridDim.x) * blockDim.x) {
+    wire[i] = part_i64[i];
+    // SUM(int) limbs normalised so that lo is in [0, 2^32): the all-reduce of up to 2^31 ranks' lo limbs cannot wrap
+    const long long lo = part_i64[span + i], hi = part_i64[2 * span + i];
+    const long long carry = lo >> 32;                         // arithmetic shift: floor(lo / 2^32)
+    wire[span + i] = lo - (carry << 32);
+    wire[2 * span + i] = hi + carry;
+    wire[3 * span + i] = part_i64[3 * span + i];
+    long long l0, l1;
+    fix_limbs(part_f64[i], 60, eunit, l0, l1);
+    wire[4 * span + i] = l0;
+    wire[5 * span + i] = l1;
+  }
+}
+__global__ void __launch_bounds__(256)
+dist_unpack_kernel(const long long* __restrict__ wire, uint64_t span, int eunit, long long* __restrict__ part_i64,
+                   double* __restrict__ part_f64) {
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < span; i += uint64_t(gridDim.x) * blockDim.x) {
+    part_i64[i] = wire[i];
+    part_i64[span + i] = wire[span + i];
+    part_i64[2 * span + i] = wire[2 * span + i];
+    part_i64[3 * span + i] = wire[3 * span + i];
+    part_f64[i] = fix_total(wire[4 * span + i], wire[5 * span + i], 60, eunit);
+  }
+}
+}  // namespace
+
+extern "C" int sdbg_dist_unique_id(uint8_t* id128) {
+  if (!id128) return SDBG_EINVAL;
+  if (!nccl_api().ok()) return SDBG_EUNSUPPORTED;
+  ncclUniqueId id;
+  if (nccl_api().GetUniqueId(&id) != ncclSuccess) return SDBG_ECUDA;
+  std::memcpy(id128, id.internal, NCCL_UNIQUE_ID_BYTES);
+  return SDBG_OK;
+}
+
+extern "C" int sdbg_dist_init(sdbg_ctx* c, const uint8_t* id128, int rank, int world) {
+  if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return SDBG_EINVAL;
+  if (!nccl_api().ok()) return fail(c, SDBG_EUNSUPPORTED, "libnccl.so.2 not found");
+  if (c->nccl_comm) return fail(c, SDBG_EINVAL, "context already has a communicator");
+  CU(c, cudaSetDevice(c->device));
+  ncclUniqueId id;
+  std::memcpy(id.internal, id128, NCCL_UNIQUE_ID_BYTES);
+  ncclComm_t comm = nullptr;
+  NC(c, nccl_api().CommInitRank(&comm, world, id, rank));
+  c->nccl_comm = comm; c->dist_rank = rank; c->dist_world = world;
+  return SDBG_OK;
+}
+
+extern "C" int sdbg_dist_destroy(sdbg_ctx* c) {
+  if (!c) return SDBG_EINVAL;
+  if (c->nccl_comm) { nccl_api().CommDestroy(static_cast<ncclComm_t>(c->nccl_comm)); c->nccl_comm = nullptr; }
+  c->dist_rank = 0; c->dist_world = 1;
+  return SDBG_OK;
+}
+
+extern "C" int sdbg_dist_allreduce_i64(sdbg_ctx* c, void* d_buf, size_t n) {
+  if (!c || !d_buf) return SDBG_EINVAL;
+  if (!c->nccl_comm) return c->dist_world == 1 ? SDBG_OK : fail(c, SDBG_EINVAL, "sdbg_dist_init has not run");
+  NC(c, nccl_api().AllReduce(d_buf, d_buf, n, ncclInt64, ncclSum, static_cast<ncclComm_t>(c->nccl_comm), c->stream));
+  return SDBG_OK;
+}
+
+extern "C" int sdbg_dist_allgather(sdbg_ctx* c, const void* d_send, void* d_recv, size_t bytes_per_rank) {
+  if (!c || !d_send || !d_recv) return SDBG_EINVAL;
+  if (!c->nccl_comm) {
+    if (c->dist_world != 1) return fail(c, SDBG_EINVAL, "sdbg_dist_init has not run");
+    CU(c, cudaMemcpyAsync(d_recv, d_send, bytes_per_rank, cudaMemcpyDeviceToDevice, c->stream));
+    return SDBG_OK;
+  }
+  NC(c, nccl_api().AllGather(d_send, d_recv, bytes_per_rank, ncclInt8, static_cast<ncclComm_t>(c->nccl_comm), c->stream));
+  return SDBG_OK;
+}
+
+// Dense GROUP BY partials of every rank -> the global partials on every rank, in ONE all-reduce: counts, the SUM(int)
+// limbs and SUM(double) as fixed-point limbs travel in one int64 buffer. abs_bound >= |sum of the double column over
+// all ranks' passing rows| fixes the fixed-point unit (identical on every rank: derive it from the column statistics
+// and the total row count, which are known when the shards are built).
+extern "C" int sdbg_dist_groupby_merge(sdbg_ctx* c, void* d_i64, void* d_f64, uint64_t span, double abs_bound) {
+  if (!c || !d_i64 || !d_f64 || !span || !(abs_bound >= 0.0)) return SDBG_EINVAL;
+  if (!c->nccl_comm) return c->dist_world == 1 ? SDBG_OK : fail(c, SDBG_EINVAL, "sdbg_dist_init has not run");
+  if (c->dist_world > 8) return fail(c, SDBG_EUNSUPPORTED, "fixed-point limbs are sized for up to 8 ranks");
+  CU(c, cudaSetDevice(c->device));
+  int ex = 0;
+  std::frexp(abs_bound > 0.0 ? abs_bound : 1.0, &ex);        // abs_bound < 2^ex
+  const int eunit = ex + 1 - 117;                              // 120-bit fixed point with 3 bits of headroom for 8 ranks
+  DevBuf& wire = c->scratch[10];
+  int rc;
+  if ((rc = ensure(c, wire, span * 6 * sizeof(long long)))) return rc;
+  const unsigned grid = unsigned(std::min<uint64_t>((span + 255) / 256, uint64_t(c->sm_count) * 8));
+  dist_pack_kernel<<<grid, 256, 0, c->stream>>>(static_cast<const long long*>(d_i64), static_cast<const double*>(d_f64), span, eunit,
+                                               static_cast<long long*>(wire.p));
+  ++c->launches;
+  NC(c, nccl_api().AllReduce(wire.p, wire.p, span * 6, ncclInt64, ncclSum, static_cast<ncclComm_t>(c->nccl_comm), c->stream));
+  dist_unpack_kernel<<<grid, 256, 0, c->stream>>>(static_cast<const long long*>(wire.p), span, eunit, static_cast<long long*>(d_i64),
+                                                 static_cast<double*>(d_f64));
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  return SDBG_OK;
 }
 
 // ------------------------------------------------------------------------------------------

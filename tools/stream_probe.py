@@ -20,7 +20,7 @@ batch = sdb.PreparedBatch(reader, queries, sdb.OR, scorer, 1000)
 d_keys = torch.empty(len(queries) * 1000, dtype=torch.int64, device="cuda:0")
 ref = None
 configs = [({"SDBG_STREAM": "0"}, 0), ({"SDBG_STREAM": "1"}, 0), ({"SDBG_STREAM": "1", "SDBG_STREAM_OCC": "2"}, 0), ({"SDBG_STREAM": "1", "SDBG_STREAM_LUT": "0"}, 0),
-           ({"SDBG_STREAM": "0"}, 2)]
+           ({"SDBG_STREAM": "0"}, 2), ({"SDBG_STREAM": "1"}, 2)]
 if os.environ.get("PROBE_ONLY_STREAM"):
     configs = [({"SDBG_STREAM": "1"}, 0)]
 for env, wand in configs:
@@ -45,4 +45,22 @@ for env, wand in configs:
     for _ in range(3):
         batch.run_device(0, d_keys.data_ptr())
     ms = ctx.timer_stop() / 3
-    print(env, "wand", wand, "ms", round(ms, 3), "G postings/s", round(postings / ms / 1e6, 1), flush=True)
+    print(env, "wand", wand, "ms", round(ms, 3), "G postings/s", round(postings / ms / 1e6, 1), "seen %.0f%%" % (100.0 * float(tot.sum()) / float(ref[2].sum())), flush=True)
+# configs[3]: 5-term AND + range filter
+g.synth_column(9, 2, 6, 1, n)
+filt = sdb.pred(9, "BETWEEN", 250000, 749999)
+b4 = sdb.PreparedBatch(reader, [[0, 1, 2, 3, 4]] * 64, sdb.AND, scorer, 1000, filt=filt)
+p4 = sum(int(dc[t]) for t in range(5))
+r4 = None
+for env in ({"SDBG_STREAM": "0"}, {"SDBG_STREAM": "1"}):
+    os.environ.update(env)
+    ctx.set_wand(0)
+    h4, n4, t4 = b4.run_host()
+    if r4 is None:
+        r4 = (h4.copy(), n4.copy(), t4.copy())
+    else:
+        print("   AND hits identical:", bool(np.array_equal(h4["doc"], r4[0]["doc"]) and np.array_equal(h4["score"], r4[0]["score"])), "totals", int(t4[0]), int(r4[2][0]))
+    ctx.flush_l2(); ctx.sync(); ctx.timer_start()
+    h4, n4, t4 = b4.run_host()
+    ms4 = ctx.timer_stop()
+    print(env, "configs[3] 64x 5-term AND + filter: ms/query", round(ms4 / 64, 4), "G postings/s", round(64 * p4 / ms4 / 1e6, 1), flush=True)
