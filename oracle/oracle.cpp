@@ -621,10 +621,18 @@ enum ScoreForm { kFormBm25 = 0, kFormBm15 = 1, kFormBm1 = 2 };
 inline int score_form(float k, float b) { return k == 0.f ? kFormBm1 : b == 0.f ? kFormBm15 : kFormBm25; }
 // Bm25<MergeType,false> :90-107; Bm15<MergeType,false> :70-87 (c1 = norm_const = k, norms unused);
 // Bm1Score without a filter boost zero-fills (:118-126).
+// g_contract: the reference is built with clang (-ffp-contract=on is clang's default for C++) for haswell, which has FMA
+// (cmake/OptimizeForArchitecture.cmake:47,71-72), so its binary most plausibly evaluates bm25.cpp:105
+// `c1 = norm_const + norm_length * norm` as ONE fused multiply-add; nothing else in :105-106 has the a*b+c shape (the
+// product c0*c1 is divided before it is subtracted). The oracle is compiled -ffp-contract=off and restates the
+// unfused source order; orc_set_contract(1) switches c1 to the fused form so that tests can bound the difference
+// between the two possible reference binaries (tests/test_oracle_goldens.py: <= 2 ulp of the score, top-k equal up
+// to near-ties), both far inside north_star's 1e-5 relative bar for fp32 scores.
+int g_contract = 0;
 inline float bm25_one(uint32_t freq, uint32_t norm, float c0, float norm_const, float norm_length, int form = kFormBm25) {
   if (form == kFormBm1) return 0.f;
   if (form == kFormBm15) return c0 - c0 / (1.f + float(freq) / norm_const);
-  const float c1 = norm_const + norm_length * float(norm);
+  const float c1 = g_contract ? std::fmaf(norm_length, float(norm), norm_const) : norm_const + norm_length * float(norm);
   return c0 - c0 * c1 / (c1 + float(freq));
 }
 
@@ -1299,6 +1307,8 @@ int orc_filter_groupby(orc_segment* const* segs, size_t n_segs, const orc_pred* 
 // ==========================================================================================
 // Deterministic synthetic inputs. splitmix64 finaliser over seed ^ (stream<<48) ^ index.
 // ==========================================================================================
+void orc_set_contract(int on) { g_contract = on ? 1 : 0; }
+
 uint64_t orc_synth_hash(uint64_t stream, uint64_t index) {
   uint64_t z = (UINT64_C(0x5EDB2026) ^ (stream << 48) ^ index) + UINT64_C(0x9E3779B97F4A7C15);
   z = (z ^ (z >> 30)) * UINT64_C(0xBF58476D1CE4E5B9);

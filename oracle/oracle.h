@@ -157,6 +157,9 @@ int orc_filter_groupby(orc_segment* const* segs, size_t n_segs, const orc_pred* 
                        int threads, orc_group_row* out, uint64_t cap, uint64_t* n_out);
 
 /* ---------- deterministic synthetic inputs, seed 0x5EDB2026 ---------- */
+/* 1: evaluate c1 = norm_const + norm_length * norm of the BM25 form as one fused multiply-add (what a clang -mfma
+   build of bm25.cpp:105 does); 0 (default): the source order without contraction. Test-only switch. */
+void orc_set_contract(int on);
 uint64_t orc_synth_hash(uint64_t stream, uint64_t index);
 /* kind: 0 k=h%100000, 1 a=h%1e6, 2 b in [0,1), 3 v=(h%2001)-1000, 4 w in [0,1000), 5.. raw int64 */
 void orc_synth_column(uint64_t stream, int kind, uint64_t row0, uint64_t rows, void* out);

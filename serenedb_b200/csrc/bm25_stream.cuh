@@ -282,6 +282,43 @@ __device__ __forceinline__ bool probe_term(const PostingsDev& S, const QTermDev&
   return true;
 }
 
+// One probe round of a warp: lane i takes ring entry qhead + i (i < n) and visits the probed lists u0 .. n_terms-1 in
+// ascending-cost order. Outlined on purpose: the probe code is large and cold for exhaustive scans, and the scan loop
+// has to stay inside the instruction cache.
+struct ProbeResult { uint32_t d; float s; uint32_t alive; };
+template <bool kAnd>
+__device__ __noinline__ ProbeResult stream_probe_round(const PostingsDev* S, const QTermDev* qt, const float* sfx, uint32_t* hint,
+                                                      const uint32_t* qd, const float* qs, uint32_t qhead, uint32_t n, uint32_t u0,
+                                                      uint32_t n_terms, float theta_score, uint32_t flags) {
+  const uint32_t lane = threadIdx.x & 31u;
+  bool alive = lane < n;
+  const uint32_t d = alive ? qd[(qhead + lane) & 127u] : kNoDoc;
+  float s = alive ? qs[(qhead + lane) & 127u] : 0.f;
+  for (uint32_t u = u0; u < n_terms; ++u) {
+    if (!__any_sync(kFull, alive)) break;
+    uint32_t fb = 0u;
+    float su = 0.f;
+    bool found = false;
+    if (alive) found = probe_term(*S, qt[u], d, hint[u], fb, su);
+    const uint32_t who = __ballot_sync(kFull, alive);
+    fb = __shfl_sync(kFull, fb, __ffs(who) - 1);
+    __syncwarp();
+    if (lane == 0) hint[u] = fb;
+    __syncwarp();
+    if (kAnd) {
+      alive = alive && found;
+      if (found) s = __fadd_rn(s, su);
+    } else {
+      if (found) s = __fadd_rn(s, su);                       // ascending-cost order: probed lists come last
+      // even with the best the remaining lists can add this doc stays below the threshold
+      if (!(flags & 64u) && alive && __fmul_rn(__fadd_rn(s, sfx[u + 1u]), 1.000001f) < theta_score) alive = false;
+    }
+  }
+  ProbeResult r;
+  r.d = d; r.s = s; r.alive = alive ? 1u : 0u;
+  return r;
+}
+
 // Candidate buffer full: exact radix select keeps the best k and raises the thresholds. Called by every thread of the
 // CTA between two barriers of the rendezvous.
 __device__ __noinline__ void stream_compact(StreamCtl* ctl, unsigned long long* cand, uint32_t cap, uint32_t k,
@@ -319,7 +356,7 @@ __device__ __noinline__ bool stream_rendezvous(StreamCtl* ctl, unsigned long lon
 // threshold exceeds the summed block-max bounds of a suffix of them (MaxScore's non-essential lists, P.wand != 0).
 template <uint32_t T, bool kLut, int kMinBlocks, bool kAnd>
 __global__ void __launch_bounds__(kTopkThreads, kMinBlocks)
-bm25_stream_kernel(const TopkParams P) {
+bm25_stream_kernel(const __grid_constant__ TopkParams P) {
   static_assert(T >= 1 && T <= kStreamMaxTerms, "1..4 live terms");
   static_assert(!kAnd || T == 1, "a conjunction streams its lead list only");
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -446,36 +483,15 @@ bm25_stream_kernel(const TopkParams P) {
     };
     auto probe_round = [&]() {
       const uint32_t n = min(32u, qcount);
-      bool alive = lane < n;
-      const uint32_t d = alive ? qd[(qhead + lane) & 127u] : kNoDoc;
-      float s = alive ? qs[(qhead + lane) & 127u] : 0.f;
+      const ProbeResult r = stream_probe_round<kAnd>(&P.seg, s_qt, s_sfx, s_hint[warp], qd, qs, qhead, n, E, n_terms,
+                                                     __uint_as_float(theta_hi), uint32_t(P.wand));
       qhead = (qhead + n) & 127u; qcount -= n;
-      const float theta_score = __uint_as_float(theta_hi);
-      for (uint32_t u = E; u < n_terms; ++u) {
-        if (!__any_sync(kFull, alive)) break;
-        uint32_t fb = 0u;
-        float su = 0.f;
-        bool found = false;
-        if (alive) found = probe_term(P.seg, s_qt[u], d, s_hint[warp][u], fb, su);
-        const uint32_t who = __ballot_sync(kFull, alive);
-        fb = __shfl_sync(kFull, fb, __ffs(who) - 1);
-        __syncwarp();
-        if (lane == 0) s_hint[warp][u] = fb;
-        __syncwarp();
-        if (kAnd) {
-          alive = alive && found;
-          if (found) s = __fadd_rn(s, su);
-        } else {
-          if (found) s = __fadd_rn(s, su);                       // ascending-cost order: probed lists come last
-          // even with the best the remaining lists can add this doc stays below the threshold
-          if (!(P.wand & 64) && alive && __fmul_rn(__fadd_rn(s, s_sfx[u + 1u]), 1.000001f) < theta_score) alive = false;
-        }
-      }
+      bool alive = r.alive != 0u;
       if (kAnd) {
-        if (doc_checks && alive) alive = doc_ok(d);
+        if (doc_checks && alive) alive = doc_ok(r.d);
         matched += alive ? 1u : 0u;
       }
-      test_and_append(alive, d, s);
+      test_and_append(alive, r.d, r.s);
     };
     // Entries that no live list absorbs any more.
     auto finalize_entries = [&](bool alive, uint32_t dv, float sv) {
@@ -517,8 +533,13 @@ bm25_stream_kernel(const TopkParams P) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) matched += alive[j] ? 1u : 0u;
         if (__any_sync(kFull, want_any)) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) test_and_append(alive[j], dv[j], sv[j]);
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t d1 = j == 0 ? dv[0] : j == 1 ? dv[1] : j == 2 ? dv[2] : dv[3];
+            const float s1 = j == 0 ? sv[0] : j == 1 ? sv[1] : j == 2 ? sv[2] : sv[3];
+            const bool al = j == 0 ? alive[0] : j == 1 ? alive[1] : j == 2 ? alive[2] : alive[3];
+            test_and_append(al, d1, s1);
+          }
         }
       } else {
 #pragma unroll 1

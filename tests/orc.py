@@ -132,6 +132,8 @@ def lib():
                                        C.POINTER(C.c_double)]
     L.orc_filter_groupby.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64,
                                      C.c_int, vp, C.c_uint64, u64p]
+    L.orc_set_contract.argtypes = [C.c_int]
+    L.orc_set_contract.restype = None
     L.orc_synth_hash.argtypes = [C.c_uint64, C.c_uint64]
     L.orc_synth_hash.restype = C.c_uint64
     L.orc_synth_column.argtypes = [C.c_uint64, C.c_int, C.c_uint64, C.c_uint64, vp]
@@ -191,6 +193,11 @@ def bm25_stats(docs_with_field, total_term_freq, docs_with_term, k=1.2, b=0.75):
     st = BM25Stats()
     lib().orc_bm25_collect(docs_with_field, total_term_freq, docs_with_term, k, b, C.byref(st))
     return st
+
+
+def set_contract(on):
+    """1: c1 of the BM25 form as one fused multiply-add (a clang -mfma build of bm25.cpp:105); 0: source order."""
+    lib().orc_set_contract(1 if on else 0)
 
 
 def bm25_score(freq, norm, stats, k=1.2, boost=1.0):

@@ -138,3 +138,43 @@ def test_sequential_order_goldens():
             seqs = [g["docs"][d - 1]["seq"] for d in hits["doc"]]
             assert seqs == c["expected_seq_order"], (c["range"], mode, seqs)
             assert total == len(c["expected_seq_order"])
+
+
+def test_fma_contraction_of_the_reference_build_stays_inside_the_bar():
+    """The reference binary is a clang build for haswell: `c1 = norm_const + norm_length * norm` (bm25.cpp:105) is
+    most plausibly ONE fused multiply-add there, while the oracle and the GPU kernels evaluate the unfused source
+    order (bit-exact with each other). Both candidates for "the reference's scores" must agree far inside
+    north_star's 1e-5 relative bar, and top-k may differ only where scores are (nearly) tied at the cut."""
+    n = 200_000
+    oseg, dl, lists = orc.synth_segment(n, [3, 20, 45, 0])
+    total_dl = int(dl.sum())
+    worst = 0.0
+    for t, (docs, freqs) in enumerate(lists):
+        st = orc.bm25_stats(n, total_dl, len(docs))
+        norms = dl[docs - 1].astype(np.uint32)
+        orc.set_contract(0)
+        plain = orc.bm25_score(freqs, norms, st)
+        orc.set_contract(1)
+        fused = orc.bm25_score(freqs, norms, st)
+        orc.set_contract(0)
+        rel = np.abs(plain.astype(np.float64) - fused.astype(np.float64)) / plain.astype(np.float64)
+        worst = max(worst, float(rel.max()))
+        assert np.all(np.abs(plain.view(np.int32).astype(np.int64) - fused.view(np.int32).astype(np.int64)) <= 8)   # a few ulp (measured: <= 4)
+    assert 0.0 < worst <= 1e-6, worst      # the two forms do differ (~10-15 % of the postings, by <= 3e-7 relative): 30x inside the 1e-5 bar
+    for terms, k in (([0, 1], 100), ([1, 2, 3], 200), ([3], 50)):
+        qts = []
+        for t in terms:
+            st = orc.bm25_stats(n, total_dl, len(lists[t][0]))
+            q = orc.BM25Term(); q.idf, q.norm_const, q.norm_length, q.boost, q.term = st.idf, st.norm_const, st.norm_length, 1.0, t
+            qts.append(q)
+        orc.set_contract(0)
+        a, _, _ = orc.bm25_topk([oseg], "OR", qts, k, mode=1)
+        orc.set_contract(1)
+        b, _, _ = orc.bm25_topk([oseg], "OR", qts, k, mode=1)
+        orc.set_contract(0)
+        assert np.allclose(a["score"], b["score"], rtol=1e-5, atol=0)
+        kth = float(a["score"][-1])
+        only = set(a["doc"].tolist()) ^ set(b["doc"].tolist())
+        sc = {int(d): float(s) for d, s in zip(a["doc"], a["score"])}
+        sc.update({int(d): float(s) for d, s in zip(b["doc"], b["score"])})
+        assert all(abs(sc[d] - kth) <= 1e-5 * kth for d in only), (terms, sorted(only)[:5])   # membership differs only at the cut
