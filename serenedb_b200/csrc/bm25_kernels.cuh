@@ -285,10 +285,15 @@ struct TopkParams {
   unsigned long long* total;   // per query matched-doc count
   unsigned long long* cand;    // [lists][cap] candidate keys, sorted descending on exit
   uint32_t* cand_n;            // [lists]
-  // One CTA per work item {query, chain, docs per chain, candidate list}: a query is cut into as many
-  // chains (contiguous doc ranges) as its posting count warrants, and the items are ordered largest first
-  // so that the long chains do not end up running alone at the tail of the launch.
+  // One CTA per work item {query, first doc, docs, candidate list}: a query is cut into as many chains
+  // (contiguous doc ranges) as its posting count warrants, and the items are ordered largest first so that
+  // the long chains do not end up running alone at the tail of the launch.
   const uint4* work;
+  // Stream kernels only: one word per work item, or null. An item that can be run either as an exhaustive merge
+  // (bm25_merge_kernel) or as lead list + probes (bm25_stream_kernel in lead mode) is launched into BOTH; the
+  // first CTA to arrive looks at the query's threshold, decides, and records 1 = merge / 2 = lead here; the other
+  // one reads the verdict and exits.
+  uint32_t* claim;
   uint32_t k;
   uint32_t cap;                // candidate buffer capacity, power of two, > k
   int32_t conjunction;         // 0 OR, 1 AND
@@ -387,11 +392,11 @@ bm25_topk_kernel(const TopkParams P) {
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint4 work = P.work[blockIdx.x];
-  const uint32_t q = work.x, g = work.y, chunk = work.z;
+  const uint32_t q = work.x, chunk = work.z;   // work item = {query, first doc, docs, candidate list}
   const uint32_t t0 = P.qterm_off[q];
   const uint32_t T = min(P.qterm_off[q + 1] - t0, kMaxQueryTerms);
   const uint32_t m = max(1u, kBudget / T);                       // block budget per term
-  const unsigned long long first64 = 1ull + static_cast<unsigned long long>(g) * chunk;
+  const unsigned long long first64 = work.y;
   const bool chain_empty = first64 > P.seg.n_docs;
   const uint32_t chain_lo = chain_empty ? 1u : uint32_t(first64);
   const uint32_t chain_hi = chain_empty ? 0u : uint32_t(min(static_cast<unsigned long long>(P.seg.n_docs), first64 + chunk - 1ull));

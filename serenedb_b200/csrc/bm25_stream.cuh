@@ -354,11 +354,17 @@ __device__ __noinline__ bool stream_rendezvous(StreamCtl* ctl, unsigned long lon
 // kAnd: conjunction -- term 0 (the shortest list) is streamed, every other list is probed per candidate and must
 // contain it (T = 1 live term, any number of probed terms). Disjunctions stream all T terms until the running
 // threshold exceeds the summed block-max bounds of a suffix of them (MaxScore's non-essential lists, P.wand != 0).
-template <uint32_t T, bool kLut, int kMinBlocks, bool kAnd>
+// kMode: 0 = disjunction, all T lists live at first; 1 = conjunction (kAnd); 2 = disjunction in LEAD mode: only the
+// shortest list is live from the start and every other list is probed -- valid once the query's threshold exceeds the
+// summed bounds of those lists, which the CTA checks when it claims its work item (TopkParams::claim).
+constexpr int kModeOr = 0, kModeAnd = 1, kModeLead = 2;
+template <uint32_t T, bool kLut, int kMinBlocks, int kMode>
 __global__ void __launch_bounds__(kTopkThreads, kMinBlocks)
 bm25_stream_kernel(const __grid_constant__ TopkParams P) {
+  constexpr bool kAnd = kMode == kModeAnd;
+  constexpr bool kProbeRest = kMode != kModeOr;        // the query has more terms than live lists
   static_assert(T >= 1 && T <= kStreamMaxTerms, "1..4 live terms");
-  static_assert(!kAnd || T == 1, "a conjunction streams its lead list only");
+  static_assert(!kProbeRest || T == 1, "conjunctions and lead mode stream one list");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* cand = reinterpret_cast<unsigned long long*>(smem_raw);
   float* lut = reinterpret_cast<float*>(cand + P.cap);
@@ -371,7 +377,7 @@ bm25_stream_kernel(const __grid_constant__ TopkParams P) {
   __shared__ uint32_t s_hint[kTopkWarps][kMaxQueryTerms];   // per warp and probed term: block where the last probe ended
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  constexpr uint32_t kWarpBytes = T * kStreamTermBytes + (kAnd ? 1024u : 0u);
+  constexpr uint32_t kWarpBytes = T * kStreamTermBytes + (kProbeRest ? 1024u : 0u);
   unsigned char* mine = warp_area + warp * kWarpBytes;
   auto live_docs = [&](uint32_t t) { return reinterpret_cast<uint32_t*>(mine + t * kStreamTermBytes); };
   auto live_scores = [&](uint32_t t) { return reinterpret_cast<float*>(mine + t * kStreamTermBytes + 512u); };
@@ -379,10 +385,10 @@ bm25_stream_kernel(const __grid_constant__ TopkParams P) {
   auto desc_win = [&](uint32_t t) { return reinterpret_cast<uint4*>(mine + t * kStreamTermBytes + 2048u); };
 
   const uint4 work = P.work[blockIdx.x];
-  const uint32_t q = work.x, g = work.y, chunk = work.z;
+  const uint32_t q = work.x, chunk = work.z;   // work item = {query, first doc, docs, candidate list}
   const uint32_t t0 = P.qterm_off[q];
-  const uint32_t n_terms = kAnd ? min(P.qterm_off[q + 1] - t0, kMaxQueryTerms) : T;   // live + probed
-  const unsigned long long first64 = 1ull + static_cast<unsigned long long>(g) * chunk;
+  const uint32_t n_terms = kProbeRest ? min(P.qterm_off[q + 1] - t0, kMaxQueryTerms) : T;   // live + probed
+  const unsigned long long first64 = work.y;
   const bool chain_empty = first64 > P.seg.n_docs;
   const uint32_t chain_lo = chain_empty ? 1u : uint32_t(first64);
   const uint32_t chain_hi = chain_empty ? 0u : uint32_t(min(static_cast<unsigned long long>(P.seg.n_docs), first64 + chunk - 1ull));
@@ -424,6 +430,18 @@ bm25_stream_kernel(const __grid_constant__ TopkParams P) {
   }
   __syncthreads();
   unsigned long long* const theta_global = P.theta + q;
+  if (P.claim != nullptr) {
+    // Lead mode is valid only if a doc outside the lead list can no longer qualify: threshold above the summed bounds
+    // of all the other lists (strict, with the rounding margin). First arrival decides for both kernels.
+    if (tid == 0) {
+      const float th = __uint_as_float(uint32_t(*reinterpret_cast<volatile unsigned long long*>(theta_global) >> 32));
+      const uint32_t mine_mode = (__fmul_rn(s_sfx[1], 1.000001f) < th) ? 2u : 1u;
+      const uint32_t old = atomicCAS(P.claim + blockIdx.x, 0u, mine_mode);
+      ctl.full = (old ? old : mine_mode) == (kMode == kModeLead ? 2u : 1u) ? 0u : 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    if (ctl.full == 0xFFFFFFFFu) return;                 // the merge kernel owns this item
+  }
   // The buffer is compacted when it holds k + max(k, 256) candidates (rounded up to the CTA size, at most its
   // capacity): for small k the threshold then follows the running k-th best closely instead of waiting for 2048
   // accepted candidates, which is what block-max skipping lives on.
@@ -464,10 +482,10 @@ bm25_stream_kernel(const __grid_constant__ TopkParams P) {
 
     // ---- candidates that still have lists to visit (probed terms) wait in a per-warp ring of 128 (doc, partial score);
     // a round looks 32 of them up at once, one per lane ----
-    uint32_t E = kAnd ? 1u : T;          // live terms 0 .. E-1 are streamed; terms E .. n_terms-1 are probed
+    uint32_t E = T;                      // live terms 0 .. E-1 are streamed; terms E .. n_terms-1 are probed
     uint32_t qhead = 0u, qcount = 0u;
-    uint32_t* const qd = kAnd ? reinterpret_cast<uint32_t*>(mine + T * kStreamTermBytes) : live_docs(T - 1u);   // OR: the ring
-    float* const qs = kAnd ? reinterpret_cast<float*>(mine + T * kStreamTermBytes + 512u) : live_scores(T - 1u);  // reuses the dropped top list's arrays
+    uint32_t* const qd = kProbeRest ? reinterpret_cast<uint32_t*>(mine + T * kStreamTermBytes) : live_docs(T - 1u);   // plain OR: the ring
+    float* const qs = kProbeRest ? reinterpret_cast<float*>(mine + T * kStreamTermBytes + 512u) : live_scores(T - 1u);  // reuses the dropped top list's arrays
 
     auto doc_ok = [&](uint32_t d) {
       if (P.seg.deleted != nullptr && ((__ldg(P.seg.deleted + (d >> 5)) >> (d & 31u)) & 1u)) return false;   // MaskDocIterator
@@ -498,7 +516,7 @@ bm25_stream_kernel(const __grid_constant__ TopkParams P) {
       if (!kAnd) {
         if (doc_checks && alive) alive = doc_ok(dv);
         matched += alive ? 1u : 0u;
-        if (E == T) { test_and_append(alive, dv, sv); return; }
+        if (E == n_terms) { test_and_append(alive, dv, sv); return; }   // nothing left to probe
         // MaxScore: a doc that cannot reach the threshold even with every probed list's bound is dropped unprobed
         if (!(P.wand & 32)) alive = alive && !(__fmul_rn(__fadd_rn(sv, s_sfx[E]), 1.000001f) < __uint_as_float(theta_hi));
       }
@@ -527,7 +545,7 @@ bm25_stream_kernel(const __grid_constant__ TopkParams P) {
         alive[j] = dv[j] <= limit && 4u * lane + j >= a0[t];       // pads are kNoDoc > limit
         want_any |= alive[j] && __float_as_uint(sv[j]) >= theta_hi;
       }
-      if (!kAnd && E == T && !doc_checks) {
+      if (!kAnd && E == n_terms && !doc_checks) {
         // common case: nothing to probe, nothing to check -- count, and touch the append path only when some score
         // reaches the threshold
 #pragma unroll
@@ -695,7 +713,7 @@ bm25_stream_kernel(const __grid_constant__ TopkParams P) {
       fr[t] = lo_w - 1u;
     }
 
-    if (kAnd) {
+    if (kProbeRest) {
       for (uint32_t u = 1u; u < n_terms; ++u) {
         const uint32_t hb = warp_first_block(P.seg.blocks + s_qt[u].blk_begin, s_qt[u].nblk, lo_w, lane);
         if (lane == 0) s_hint[warp][u] = hb;

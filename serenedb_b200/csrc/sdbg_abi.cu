@@ -23,6 +23,7 @@
 #include "../../include/sdbg.h"
 #include "bm25_kernels.cuh"
 #include "bm25_stream.cuh"
+#include "bm25_merge.cuh"
 #include "column_kernels.cuh"
 #include "posting_format.hpp"
 
@@ -575,15 +576,27 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
     for (uint32_t i = 0; i < total_terms; ++i)
       if (terms[i].term < segs[si]->term_docs.size()) batch_postings += segs[si]->term_docs[terms[i].term];
   const uint64_t chain_target = std::max<uint64_t>(uint64_t(env_int("SDBG_TOPK_CHAIN_MIN", 65536)), batch_postings / (uint64_t(c->sm_count) * uint64_t(std::max(1, env_int("SDBG_TOPK_CHAIN_DIV", 4)))));
-  // Work classes: 0 = legacy kernel in driver mode, 1 = legacy kernel, 2 + (T-1) = warp-autonomous stream kernel for a
-  // disjunction of T = 1..4 terms (bm25_stream.cuh). The stream kernel covers plain BM25 disjunctions without a column
-  // filter or deleted-doc mask; everything else (AND, hybrid, BM15 / BM1 forms, > 4 terms) stays on the legacy kernel.
-  struct WorkItem { uint32_t q, g, chunk, list; uint64_t weight; uint32_t cls; };
-  constexpr uint32_t kClasses = 3 + kStreamMaxTerms;     // last class: conjunctions on the stream kernel (lead list + probes)
-  constexpr uint32_t kClsAnd = 2 + kStreamMaxTerms;
+  // Work classes (one launch each):
+  //   0 / 1        legacy window kernel (driver mode / plain): > 4-term disjunctions, BM15 / BM1 forms
+  //   2 + (T-1)    exhaustive warp-autonomous merge of T = 1..4 lists (bm25_merge.cuh): pruning off or not applicable
+  //   6 + (T-1)    stream kernel, disjunction with MaxScore demotion / single-list block-max skip (bm25_stream.cuh)
+  //   10           conjunctions: lead list + probes (stream kernel, kModeAnd), hybrid filter and deleted docs included
+  //   11           first slice of a two-term disjunction whose long list is worth probing instead of scanning: merged
+  //                exhaustively FIRST so that the query has a threshold when the rest of its range starts
+  //   12           the rest of such a query: launched into BOTH the merge kernel and the stream kernel in lead mode
+  //                (short list streamed, long list probed per candidate); the first CTA to arrive decides from the
+  //                threshold which of the two runs the item (TopkParams::claim)
+  struct WorkItem { uint32_t q, lo, len, list; uint64_t weight; uint32_t cls; };
+  constexpr uint32_t kClsMerge = 2, kClsStream = 2 + kStreamMaxTerms, kClsAnd = 2 + 2 * kStreamMaxTerms, kClsSlice = kClsAnd + 1,
+                     kClsLead = kClsAnd + 2, kClasses = kClsAnd + 3;
   const bool level2 = c->wand >= 2 && kind != SDBG_QUERY_AND && k1 != 0.f && b != 0.f;
   const bool stream_ok = env_int("SDBG_STREAM", 1) != 0 && k1 != 0.f && b != 0.f &&
                          size_t(pl.cap) * 8 + size_t(kStreamMaxTerms) * (kLutFreqs * 1024 + kTopkWarps * kStreamTermBytes) <= 200 * 1024;
+  const bool lead_ok = env_int("SDBG_STREAM_LEAD", 1) != 0;
+  // The staged block-max pairs are maximisers for BM25 with the index-time b only (FreqNormProducer::CmpBm25,
+  // wand_writer.hpp:142-175; the order of two pairs does not depend on k); the reference enables WAND only when
+  // Scorer::equals matches (PostingsReaderImpl::WandIterator, reader.hpp:457-501). Any other b: exhaustive.
+  auto seg_wand = [&](const sdbg_segment* s) { return (c->wand && s->has_wand && k1 != 0.f && b != 0.f && b == s->wand_b) ? c->wand : 0; };
   std::vector<std::array<size_t, kClasses>> n_cls(n_segs);
   for (auto& a : n_cls) a.fill(0);
   std::vector<std::vector<WorkItem>> seg_work(n_segs);
@@ -593,25 +606,63 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
     for (size_t si = 0; si < n_segs; ++si) {
       const sdbg_segment* s = segs[si];
       uint64_t postings = 0;
-      uint32_t largest = 0, largest_term = UINT32_MAX;
+      uint32_t largest = 0, largest_term = UINT32_MAX, smallest = UINT32_MAX;
       for (uint32_t i = term_off[q]; i < term_off[q + 1]; ++i)
         if (terms[i].term < s->term_docs.size()) {
-          postings += s->term_docs[terms[i].term];
-          if (s->term_docs[terms[i].term] >= largest) { largest = s->term_docs[terms[i].term]; largest_term = terms[i].term; }
+          const uint32_t dc = s->term_docs[terms[i].term];
+          postings += dc;
+          smallest = std::min(smallest, dc);
+          if (dc >= largest) { largest = dc; largest_term = terms[i].term; }
         }
       const uint32_t nt = term_off[q + 1] - term_off[q];
+      const int wand = seg_wand(s);
       // Driver mode (pruning level 2) pays only when the largest list can be probed without decoding blocks; the
       // other queries run the plain kernel, which is lighter (fewer registers, no probe buffers, level-1 planner).
-      const bool drive_q = level2 && s->has_wand && b == s->wand_b && nt >= 2 && largest_term < s->term_probe.size() &&
-                           s->term_probe[largest_term] != 0;
+      const bool drive_q = level2 && wand && nt >= 2 && largest_term < s->term_probe.size() && s->term_probe[largest_term] != 0;
       uint32_t cls = drive_q ? 0u : 1u;
+      uint32_t slice_docs = 0;    // > 0: lead candidate
       if (stream_ok && kind == SDBG_QUERY_AND && env_int("SDBG_STREAM_AND", 1) != 0) cls = kClsAnd;
-      else if (stream_ok && kind != SDBG_QUERY_AND && nt <= kStreamMaxTerms) cls = 2u + (nt - 1u);
-      uint32_t g = uint32_t(std::max<uint64_t>(pl.G, (postings + chain_target - 1) / chain_target));
+      else if (stream_ok && kind != SDBG_QUERY_AND && nt <= kStreamMaxTerms) {
+        const bool plain = !filt && !s->d_deleted;                  // the merge kernel has no per-doc checks
+        cls = (!plain || (wand && (nt != 2 || !lead_ok))) ? kClsStream + (nt - 1u) : kClsMerge + (nt - 1u);
+        if (wand && nt == 2 && lead_ok && plain && uint64_t(largest) >= 4ull * smallest && smallest >= 3u * k) {
+          // Lead mode needs the threshold above the long list's bound. That happens when a typical posting of the short
+          // list (freq 1, average length) already outscores the best posting of the long one; then about k docs of the
+          // short list, i.e. the first 1.5 k / |short| of the doc range, are enough to get there.
+          const sdbg_bm25_term* ta = &terms[term_off[q]];
+          const sdbg_bm25_term* tb = ta + 1;
+          if (s->term_docs[ta->term] > s->term_docs[tb->term]) std::swap(ta, tb);       // ta = short list
+          const MaxPair root = tb->term < s->term_max.size() ? s->term_max[tb->term] : MaxPair{0, 0};
+          if (root.freq != 0) {
+            const float c0b = tb->boost * (k1 + 1) * tb->idf, c1b = tb->norm_const + tb->norm_length * float(root.norm);
+            const float ub_b = c0b - c0b * c1b / (c1b + float(root.freq));
+            const float c0a = ta->boost * (k1 + 1) * ta->idf, c1a = ta->norm_const + ta->norm_length * (ta->norm_length > 0.f ? (k1 * b) / ta->norm_length : 1.f);
+            const float typ_a = c0a - c0a * c1a / (c1a + 1.f);                           // freq 1 at the average length
+            if (ub_b * 1.05f < typ_a) {
+              const double frac = 1.5 * double(k) / double(smallest);
+              slice_docs = uint32_t(std::min<double>(double(s->n_docs), std::max(4096.0, std::ceil(double(s->n_docs) * frac))));
+              if (slice_docs > s->n_docs / 2) slice_docs = 0;
+            }
+          }
+        }
+      }
+      const uint32_t first = slice_docs ? slice_docs + 1u : 1u;             // first doc of the chained range
+      const uint32_t rest_docs = s->n_docs - (first - 1u);
+      const uint64_t rest_postings = slice_docs ? uint64_t(double(postings) * double(rest_docs) / double(s->n_docs)) : postings;
+      if (slice_docs) {
+        seg_work[si].push_back({uint32_t(q), 1u, slice_docs, list_off[q] + lists, postings - rest_postings, kClsSlice});
+        ++n_cls[si][kClsSlice];
+        ++lists;
+        cls = kClsLead;
+      }
+      uint32_t g = uint32_t(std::max<uint64_t>(pl.G, (rest_postings + chain_target - 1) / chain_target));
+      // lead mode is latency-bound (dependent loads per probe), not throughput-bound: more, shorter chains
+      if (slice_docs) g = std::max(g, std::min<uint32_t>(uint32_t(env_int("SDBG_STREAM_LEAD_CHAINS", 16)), std::max(1u, smallest / 8192u)));
       g = std::min(g, max_chains);
-      g = std::min(g, std::max(1u, s->n_docs / 4096u));
-      const uint32_t chunk = (s->n_docs + g - 1) / g;
-      for (uint32_t j = 0; j < g; ++j) seg_work[si].push_back({uint32_t(q), j, chunk, list_off[q] + lists + j, postings / g, cls});
+      g = std::min(g, std::max(1u, rest_docs / 4096u));
+      const uint32_t chunk = (rest_docs + g - 1) / g;
+      for (uint32_t j = 0; j < g; ++j)
+        seg_work[si].push_back({uint32_t(q), first + j * chunk, chunk, list_off[q] + lists + j, rest_postings / g, cls});
       n_cls[si][cls] += g;
       lists += g;
     }
@@ -639,7 +690,7 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
   std::memcpy(h_off, term_off, off_bytes);
   {
     auto* h_work = reinterpret_cast<uint4*>(static_cast<char*>(c->h_pinned) + qt_pad);
-    for (auto& w : seg_work) for (const WorkItem& it : w) *h_work++ = make_uint4(it.q, it.g, it.chunk, it.list);
+    for (auto& w : seg_work) for (const WorkItem& it : w) *h_work++ = make_uint4(it.q, it.lo, it.len, it.list);
     std::memcpy(static_cast<char*>(c->h_pinned) + qt_pad + work_bytes, list_off.data(), off_bytes);
   }
   for (size_t si = 0; si < n_segs; ++si) {
@@ -693,29 +744,37 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
     CU(c, cudaFuncSetAttribute(bm25_topk_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(c, cudaFuncSetAttribute(bm25_topk_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 #define SDBG_STREAM_ATTR(TT) \
-    CU(c, cudaFuncSetAttribute(bm25_stream_kernel<TT, false, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-    CU(c, cudaFuncSetAttribute(bm25_stream_kernel<TT, true, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-    CU(c, cudaFuncSetAttribute(bm25_stream_kernel<TT, true, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))
+    CU(c, cudaFuncSetAttribute(bm25_merge_kernel<TT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+    CU(c, cudaFuncSetAttribute(bm25_merge_kernel<TT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+    CU(c, cudaFuncSetAttribute(bm25_stream_kernel<TT, false, 3, kModeOr>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+    CU(c, cudaFuncSetAttribute(bm25_stream_kernel<TT, true, 3, kModeOr>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))
     SDBG_STREAM_ATTR(1); SDBG_STREAM_ATTR(2); SDBG_STREAM_ATTR(3); SDBG_STREAM_ATTR(4);
 #undef SDBG_STREAM_ATTR
-    CU(c, cudaFuncSetAttribute(bm25_stream_kernel<1, false, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CU(c, cudaFuncSetAttribute(bm25_stream_kernel<1, true, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(c, cudaFuncSetAttribute(bm25_stream_kernel<1, false, 3, kModeAnd>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(c, cudaFuncSetAttribute(bm25_stream_kernel<1, true, 3, kModeAnd>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(c, cudaFuncSetAttribute(bm25_stream_kernel<1, false, 3, kModeLead>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(c, cudaFuncSetAttribute(bm25_stream_kernel<1, true, 3, kModeLead>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(c, cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     c->topk_attr_set = true;
   }
+  // one claim word per work item of class kClsLead (zeroed per call)
+  size_t n_lead_total = 0;
+  for (size_t si = 0; si < n_segs; ++si) n_lead_total += n_cls[si][kClsLead];
+  DevBuf& b_claim = c->scratch[11];
+  if (n_lead_total) {
+    if ((rc = ensure(c, b_claim, n_lead_total * 4))) return rc;
+    CU(c, cudaMemsetAsync(b_claim.p, 0, n_lead_total * 4, c->stream));
+  }
   uint32_t base = 0;
-  size_t work_done = 0;
+  size_t work_done = 0, lead_done = 0;
   // Work classes are separate launches; with more than one present they alternate between two streams (forked from
-  // and joined back into the context's stream) so that no class waits for another's tail.
+  // and joined back into the context's stream) so that no class waits for another's tail. First slices (class 11) go
+  // first, and everything that depends on their thresholds is ordered behind them.
   uint32_t classes_present = 0;
   for (size_t si = 0; si < n_segs; ++si) for (uint32_t k2 = 0; k2 < kClasses; ++k2) if (n_cls[si][k2]) classes_present |= 1u << k2;
   const bool two_lanes = (classes_present & (classes_present - 1u)) != 0u;
   {
     ProfScope ps_(c, kProfTopk);   // one span for all top-k launches of the call
-    if (two_lanes) {
-      CU(c, cudaEventRecord(c->ev_fork, c->stream));
-      CU(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-    }
     uint32_t lane_no = 0;
     for (size_t si = 0; si < n_segs; ++si) {
       sdbg_segment* s = segs[si];
@@ -728,42 +787,77 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
       P.cand = static_cast<unsigned long long*>(b_cand.p);
       P.cand_n = static_cast<uint32_t*>(b_candn.p);
       P.k = k; P.cap = pl.cap; P.conjunction = kind == SDBG_QUERY_AND ? 1 : 0;
-      // The staged block-max pairs are maximisers for BM25 with the index-time b only (FreqNormProducer::CmpBm25,
-      // wand_writer.hpp:142-175; the order of two pairs does not depend on k); the reference enables WAND only when
-      // Scorer::equals matches (PostingsReaderImpl::WandIterator, reader.hpp:457-501). Any other b: exhaustive.
-      const int wand = (c->wand && s->has_wand && k1 != 0.f && b != 0.f && b == s->wand_b) ? c->wand : 0;
-      const uint4* work = reinterpret_cast<const uint4*>(static_cast<const char*>(b_qt.p) + qt_pad) + work_done;
+      P.claim = nullptr;
+      const int wand = seg_wand(s);
+      const bool lut = use_lut[si];
+      const uint4* const work0 = reinterpret_cast<const uint4*>(static_cast<const char*>(b_qt.p) + qt_pad) + work_done;
       work_done += seg_work[si].size();
+      std::array<size_t, kClasses> cls_off{};
+      { size_t o = 0; for (uint32_t cls = 0; cls < kClasses; ++cls) { cls_off[cls] = o; o += n_cls[si][cls]; } }
+      auto launch_merge = [&](uint32_t T, size_t n, cudaStream_t st) {
+        const size_t sm = stream_smem(T, lut, false);
+#define SDBG_MERGE_LAUNCH(TT) \
+        if (lut) bm25_merge_kernel<TT, true><<<unsigned(n), kTopkThreads, sm, st>>>(P); \
+        else bm25_merge_kernel<TT, false><<<unsigned(n), kTopkThreads, sm, st>>>(P)
+        switch (T) {
+          case 1: SDBG_MERGE_LAUNCH(1); break;
+          case 2: SDBG_MERGE_LAUNCH(2); break;
+          case 3: SDBG_MERGE_LAUNCH(3); break;
+          default: SDBG_MERGE_LAUNCH(4); break;
+        }
+#undef SDBG_MERGE_LAUNCH
+        ++c->launches;
+      };
+      // first slices: before everything else of this segment, on the main stream
+      if (n_cls[si][kClsSlice]) {
+        P.work = work0 + cls_off[kClsSlice]; P.wand = 0;
+        launch_merge(2, n_cls[si][kClsSlice], c->stream);
+      }
+      if (two_lanes) {
+        CU(c, cudaEventRecord(c->ev_fork, c->stream));
+        CU(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+      }
       for (uint32_t cls = 0; cls < kClasses; ++cls) {
         const size_t n = n_cls[si][cls];
-        if (!n) continue;
+        if (!n || cls == kClsSlice) continue;
         cudaStream_t st = (two_lanes && (lane_no++ & 1u)) ? c->stream2 : c->stream;
-        P.work = work;
-        work += n;
+        P.work = work0 + cls_off[cls];
+        P.claim = nullptr;
         if (cls == 0) {
           P.wand = wand;
           if (pl.budget == 16) bm25_topk_kernel<16, true><<<unsigned(n), kTopkThreads, smem_drive, st>>>(P);
           else bm25_topk_kernel<32, true><<<unsigned(n), kTopkThreads, smem_drive, st>>>(P);
+          ++c->launches;
         } else if (cls == 1) {
           P.wand = std::min(wand, 1);
           if (pl.budget == 16) bm25_topk_kernel<16, false><<<unsigned(n), kTopkThreads, pl.smem, st>>>(P);
           else bm25_topk_kernel<32, false><<<unsigned(n), kTopkThreads, pl.smem, st>>>(P);
+          ++c->launches;
         } else if (cls == kClsAnd) {
-          const bool lut = use_lut[si];
           const size_t sm = stream_smem(1, lut, true);
           P.wand = 0;                                  // conjunctions are exact: every candidate of the lead list is probed
-          if (lut) bm25_stream_kernel<1, true, 3, true><<<unsigned(n), kTopkThreads, sm, st>>>(P);
-          else bm25_stream_kernel<1, false, 3, true><<<unsigned(n), kTopkThreads, sm, st>>>(P);
-        } else {
-          const uint32_t T = cls - 1u;
-          const bool lut = use_lut[si];
-          const bool occ2 = env_int("SDBG_STREAM_OCC", 3) == 2;   // 2 CTAs / SM with up to 128 registers per thread
+          if (lut) bm25_stream_kernel<1, true, 3, kModeAnd><<<unsigned(n), kTopkThreads, sm, st>>>(P);
+          else bm25_stream_kernel<1, false, 3, kModeAnd><<<unsigned(n), kTopkThreads, sm, st>>>(P);
+          ++c->launches;
+        } else if (cls == kClsLead) {
+          // both kernels over the same items; each item is run by exactly one of them (claim word)
+          P.claim = static_cast<uint32_t*>(b_claim.p) + lead_done;
+          lead_done += n;
+          P.wand = 0;
+          launch_merge(2, n, c->stream);
+          const size_t sm = stream_smem(1, lut, true);
+          P.wand = wand | (env_int("SDBG_STREAM_DBG", 0) & 0xF0);
+          cudaStream_t st2 = two_lanes ? c->stream2 : c->stream;
+          if (lut) bm25_stream_kernel<1, true, 3, kModeLead><<<unsigned(n), kTopkThreads, sm, st2>>>(P);
+          else bm25_stream_kernel<1, false, 3, kModeLead><<<unsigned(n), kTopkThreads, sm, st2>>>(P);
+          ++c->launches;
+        } else if (cls >= kClsStream) {
+          const uint32_t T = cls - kClsStream + 1u;
           const size_t sm = stream_smem(T, lut, false);
           P.wand = wand ? (wand | (env_int("SDBG_STREAM_DBG", 0) & 0xF0)) : 0;   // debug bits 16/32/64/128 switch parts of the pruning off
 #define SDBG_STREAM_LAUNCH(TT) \
-          if (lut && occ2) bm25_stream_kernel<TT, true, 2, false><<<unsigned(n), kTopkThreads, sm, st>>>(P); \
-          else if (lut) bm25_stream_kernel<TT, true, 3, false><<<unsigned(n), kTopkThreads, sm, st>>>(P); \
-          else bm25_stream_kernel<TT, false, 3, false><<<unsigned(n), kTopkThreads, sm, st>>>(P)
+          if (lut) bm25_stream_kernel<TT, true, 3, kModeOr><<<unsigned(n), kTopkThreads, sm, st>>>(P); \
+          else bm25_stream_kernel<TT, false, 3, kModeOr><<<unsigned(n), kTopkThreads, sm, st>>>(P)
           switch (T) {
             case 1: SDBG_STREAM_LAUNCH(1); break;
             case 2: SDBG_STREAM_LAUNCH(2); break;
@@ -771,15 +865,18 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
             default: SDBG_STREAM_LAUNCH(4); break;
           }
 #undef SDBG_STREAM_LAUNCH
+          ++c->launches;
+        } else {
+          P.wand = 0;
+          launch_merge(cls - kClsMerge + 1u, n, st);
         }
-        ++c->launches;
       }
       CU(c, cudaGetLastError());
       base += s->n_docs;
-    }
-    if (two_lanes) {
-      CU(c, cudaEventRecord(c->ev_join, c->stream2));
-      CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+      if (two_lanes) {
+        CU(c, cudaEventRecord(c->ev_join, c->stream2));
+        CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+      }
     }
   }
   MergeParams M;

@@ -22,7 +22,7 @@ ref = None
 configs = [({"SDBG_STREAM": "0"}, 0), ({"SDBG_STREAM": "1"}, 0), ({"SDBG_STREAM": "1", "SDBG_STREAM_OCC": "2"}, 0), ({"SDBG_STREAM": "1", "SDBG_STREAM_LUT": "0"}, 0),
            ({"SDBG_STREAM": "0"}, 2), ({"SDBG_STREAM": "1"}, 2)]
 if os.environ.get("PROBE_ONLY_STREAM"):
-    configs = [({"SDBG_STREAM": "1"}, 0)]
+    configs = [({"SDBG_STREAM": "1", "SDBG_STREAM_OCC": os.environ.get("PROBE_OCC", "3")}, int(os.environ.get("PROBE_WAND", "0")))]
 for env, wand in configs:
     for k_ in ("SDBG_STREAM", "SDBG_STREAM_LUT", "SDBG_STREAM_OCC"):
         os.environ.pop(k_, None)
@@ -31,6 +31,8 @@ for env, wand in configs:
     h, nout, tot = batch.run_host()
     if ref is None:
         ref = (h.copy(), nout.copy(), tot.copy())
+    elif os.environ.get("PROBE_ONLY_STREAM"):
+        pass
     else:
         ok = np.array_equal(nout, ref[1]) and np.array_equal(h["doc"], ref[0]["doc"]) and np.array_equal(h["score"], ref[0]["score"])
         print("   hits identical to legacy/wand0:", ok, " totals equal:", bool(np.array_equal(tot, ref[2])), flush=True)
@@ -46,6 +48,8 @@ for env, wand in configs:
         batch.run_device(0, d_keys.data_ptr())
     ms = ctx.timer_stop() / 3
     print(env, "wand", wand, "ms", round(ms, 3), "G postings/s", round(postings / ms / 1e6, 1), "seen %.0f%%" % (100.0 * float(tot.sum()) / float(ref[2].sum())), flush=True)
+if os.environ.get("PROBE_ONLY_STREAM"):
+    sys.exit(0)
 # configs[3]: 5-term AND + range filter
 g.synth_column(9, 2, 6, 1, n)
 filt = sdb.pred(9, "BETWEEN", 250000, 749999)
