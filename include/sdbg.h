@@ -211,6 +211,9 @@ int sdbg_writer_finish(sdbg_writer*, const uint8_t** doc_file, size_t* n, const 
  * dl<=255) and stages everything into `seg`. Returns per-term docs_count and the shard's sum of dl. */
 int sdbg_synth_corpus(sdbg_segment* seg, uint64_t doc0, uint32_t n_docs, uint32_t t0, uint32_t nt,
                       int threads, uint32_t* docs_count_out /* nt */, uint64_t* sum_dl_out);
+/* Same with a probability floor: p_t = max(p_floor, min(0.5, 0.6 / (t + 1))) (flat tail; an index far larger than L2). */
+int sdbg_synth_corpus_ex(sdbg_segment* seg, uint64_t doc0, uint32_t n_docs, uint32_t t0, uint32_t nt, int threads, double p_floor,
+                         uint32_t* docs_count_out /* nt */, uint64_t* sum_dl_out);
 /* Synthetic table column generated directly in HBM: kind as in SURVEY §8d (0 k,1 a,2 b,3 v,4 w,5+ raw),
  * or 6 = int32 n = h % 1000000 (hybrid INCLUDE column, stream 2). */
 int sdbg_synth_column(sdbg_segment* seg, uint64_t field, uint64_t stream, int kind, uint64_t row0, uint64_t rows);
@@ -235,6 +238,12 @@ int sdbg_dist_allgather(sdbg_ctx*, const void* d_send, void* d_recv, size_t byte
    ncclAllReduce: counts, SUM(int) limbs and SUM(double) as 120-bit fixed point share one int64 buffer (exact and
    independent of the rank order). abs_bound >= |SUM(double column)| over all ranks, identical on every rank. */
 int sdbg_dist_groupby_merge(sdbg_ctx*, void* d_i64, void* d_f64, uint64_t span, double abs_bound);
+/* BM25 top-k over the segments of ALL ranks: local scan -> one all-gather of the k best keys per query -> local
+   selection, back to back on the context's stream. hit.seg = rank, hit.doc = ordinal within the rank. out == NULL:
+   nothing is copied and nothing waits (results stay in HBM). */
+int sdbg_dist_bm25_topk_batch(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25_term* terms,
+                              const uint32_t* term_off, size_t n_queries, float k1, float b, const sdbg_col_pred* filt,
+                              uint32_t k, float threshold_in, sdbg_hit* out, uint32_t* n_out);
 
 #ifdef __cplusplus
 }

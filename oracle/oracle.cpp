@@ -1337,7 +1337,9 @@ void orc_synth_doc_lengths(uint64_t doc0, uint32_t n, uint32_t* out) {
 }
 
 uint32_t orc_synth_term(uint32_t t, uint64_t doc0, uint32_t n, const uint32_t* dl, uint32_t* docs, uint32_t* freqs) {
-  const double p = std::min(0.5, 0.6 / double(t + 1));
+  // terms 1000000 .. 1000004: BASELINE configs[3]'s conjunction terms, p = 0.50, 0.40, 0.30, 0.25, 0.20
+  static const double kCfg4P[5] = {0.50, 0.40, 0.30, 0.25, 0.20};
+  const double p = (t >= 1000000u && t < 1000005u) ? kCfg4P[t - 1000000u] : std::min(0.5, 0.6 / double(t + 1));
   const uint64_t thr = uint64_t(std::ldexp(p, 64));
   uint32_t c = 0;
   for (uint32_t i = 0; i < n; ++i) {

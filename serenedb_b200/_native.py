@@ -76,6 +76,7 @@ SIGNATURES = {
     "sdbg_dist_allreduce_i64": (C.c_int, [_vp, _vp, _sz]),
     "sdbg_dist_allgather": (C.c_int, [_vp, _vp, _vp, _sz]),
     "sdbg_dist_groupby_merge": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_double]),
+    "sdbg_dist_bm25_topk_batch": (C.c_int, [_vp, _sz, C.c_int, _vp, _vp, _sz, C.c_float, C.c_float, _vp, C.c_uint32, C.c_float, _vp, _vp]),
     "sdbg_bm25_topk": (C.c_int, [_vp, _sz, C.c_int, _vp, _sz, C.c_float, C.c_float, _vp, C.c_uint32, C.c_float, _vp, _u32p,
                                  _u64p, _f32p]),
     "sdbg_bm25_topk_batch": (C.c_int, [_vp, _sz, C.c_int, _vp, _vp, _sz, C.c_float, C.c_float, _vp, C.c_uint32, C.c_float,
@@ -97,6 +98,7 @@ SIGNATURES = {
     "sdbg_writer_add_term": (C.c_int, [_vp, _vp, _vp, C.c_uint32]),
     "sdbg_writer_finish": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_sz), C.POINTER(_vp), C.POINTER(_sz)]),
     "sdbg_synth_corpus": (C.c_int, [_vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, _vp, _u64p]),
+    "sdbg_synth_corpus_ex": (C.c_int, [_vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_double, _vp, _u64p]),
     "sdbg_synth_column": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, C.c_uint64]),
     "sdbg_synth_hash": (C.c_uint64, [C.c_uint64, C.c_uint64]),
     "sdbg_debug_stage_host": (C.c_int, [_vp, _sz, _vp, _sz, C.c_int, C.c_uint32, _u32p, _vp, _vp, _vp, _vp, _vp,

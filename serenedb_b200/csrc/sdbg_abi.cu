@@ -62,7 +62,7 @@ struct sdbg_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
   uint64_t launches = 0;
-  DevBuf scratch[12];
+  DevBuf scratch[16];
   void* h_pinned = nullptr;  // pinned host staging for small transfers
   size_t h_pinned_cap = 0;
   void* flush = nullptr;
@@ -990,9 +990,20 @@ __global__ void shift_keys_kernel(const unsigned long long* __restrict__ in, uns
 }
 }  // namespace
 
+namespace {
+int topk_batch_device_impl(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25_term* terms, const uint32_t* term_off,
+                           size_t nq, float k1, float b, const sdbg_col_pred* filt, uint32_t k, float threshold_in, uint32_t rank,
+                           void* d_keys, void* d_totals, bool sync);
+}
 extern "C" int sdbg_bm25_topk_batch_device(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25_term* terms,
                                            const uint32_t* term_off, size_t nq, float k1, float b, const sdbg_col_pred* filt,
                                            uint32_t k, float threshold_in, uint32_t rank, void* d_keys, void* d_totals) {
+  return topk_batch_device_impl(segs, n_segs, kind, terms, term_off, nq, k1, b, filt, k, threshold_in, rank, d_keys, d_totals, true);
+}
+namespace {
+int topk_batch_device_impl(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25_term* terms, const uint32_t* term_off,
+                           size_t nq, float k1, float b, const sdbg_col_pred* filt, uint32_t k, float threshold_in, uint32_t rank,
+                           void* d_keys, void* d_totals, bool sync) {
   if (!d_keys) return SDBG_EINVAL;
   TopkDevOut dev{};
   int rc = topk_run(segs, n_segs, kind, terms, term_off, nq, k1, b, filt, k, threshold_in, &dev);
@@ -1006,13 +1017,14 @@ extern "C" int sdbg_bm25_topk_batch_device(sdbg_segment* const* segs, size_t n_s
   ++c->launches;
   CU(c, cudaGetLastError());
   if (d_totals) CU(c, cudaMemcpyAsync(d_totals, dev.total, nq * 8, cudaMemcpyDeviceToDevice, c->stream));
-  CU(c, cudaStreamSynchronize(c->stream));
+  if (sync) CU(c, cudaStreamSynchronize(c->stream));
   return SDBG_OK;
 }
+}  // namespace
 
 extern "C" int sdbg_topk_merge_gathered(sdbg_ctx* c, const void* d_keys_all, uint32_t n_ranks, size_t nq, uint32_t k,
                                         sdbg_hit* out, uint32_t* n_out) {
-  if (!c || !d_keys_all || !n_ranks || !nq || !k || (out && !n_out)) return SDBG_EINVAL;
+  if (!c || !d_keys_all || !n_ranks || !nq || !k || (out && !n_out)) return SDBG_EINVAL;   // out == NULL: n_out != NULL asks for a sync
   CU(c, cudaSetDevice(c->device));
   // gathered layout [rank][query][k]; the merge kernel wants [query][list][stride] -> stride trick:
   // treat each rank's block as a list with a rank-major base pointer. Re-pack with a tiny kernel-free
@@ -1038,6 +1050,7 @@ extern "C" int sdbg_topk_merge_gathered(sdbg_ctx* c, const void* d_keys_all, uin
   topk_merge_kernel<<<unsigned(nq), kTopkThreads, size_t(cap) * 8, c->stream>>>(M);
   ++c->launches;
   CU(c, cudaGetLastError());
+  if (!out && !n_out) return SDBG_OK;                                       // enqueue only: results stay in HBM, nothing waits
   if (!out) { CU(c, cudaStreamSynchronize(c->stream)); return SDBG_OK; }   // results stay in HBM (scratch of this context)
   const size_t kb = nq * size_t(k) * 8, nb = nq * 4;
   if ((rc = ensure_pinned(c, kb + nb))) return rc;
@@ -1769,6 +1782,28 @@ extern "C" int sdbg_dist_allgather(sdbg_ctx* c, const void* d_send, void* d_recv
 // limbs and SUM(double) as fixed-point limbs travel in one int64 buffer. abs_bound >= |sum of the double column over
 // all ranks' passing rows| fixes the fixed-point unit (identical on every rank: derive it from the column statistics
 // and the total row count, which are known when the shards are built).
+// Distributed top-k in one call: local scan of this rank's segments, ONE all-gather of every rank's k best keys per query
+// over NVLink, local selection of the global top-k -- enqueued back to back on the context's stream, one host
+// synchronisation at the very end (none when out == NULL: the keys stay in HBM, see sdbg_topk_merge_gathered).
+extern "C" int sdbg_dist_bm25_topk_batch(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25_term* terms,
+                                         const uint32_t* term_off, size_t nq, float k1, float b, const sdbg_col_pred* filt, uint32_t k,
+                                         float threshold_in, sdbg_hit* out, uint32_t* n_out) {
+  if (!segs || !n_segs) return SDBG_EINVAL;
+  sdbg_ctx* c = segs[0]->ctx;
+  const uint32_t world = uint32_t(c->dist_world), rank = uint32_t(c->dist_rank);
+  if (world > 1 && !c->nccl_comm) return fail(c, SDBG_EINVAL, "sdbg_dist_init has not run");
+  DevBuf& mine = c->scratch[6 + 6];  // scratch[12..]: see DevBuf scratch[] size
+  DevBuf& all = c->scratch[6 + 7];
+  int rc;
+  const size_t bytes = nq * size_t(k) * 8;
+  if ((rc = ensure(c, mine, bytes))) return rc;
+  if ((rc = ensure(c, all, bytes * world))) return rc;
+  if ((rc = topk_batch_device_impl(segs, n_segs, kind, terms, term_off, nq, k1, b, filt, k, threshold_in, rank, mine.p, nullptr, false))) return rc;
+  if ((rc = sdbg_dist_allgather(c, mine.p, all.p, bytes))) return rc;
+  if (!out) return sdbg_topk_merge_gathered(c, all.p, world, nq, k, nullptr, nullptr);
+  return sdbg_topk_merge_gathered(c, all.p, world, nq, k, out, n_out);
+}
+
 extern "C" int sdbg_dist_groupby_merge(sdbg_ctx* c, void* d_i64, void* d_f64, uint64_t span, double abs_bound) {
   if (!c || !d_i64 || !d_f64 || !span || !(abs_bound >= 0.0)) return SDBG_EINVAL;
   if (!c->nccl_comm) return c->dist_world == 1 ? SDBG_OK : fail(c, SDBG_EINVAL, "sdbg_dist_init has not run");
@@ -1777,7 +1812,7 @@ extern "C" int sdbg_dist_groupby_merge(sdbg_ctx* c, void* d_i64, void* d_f64, ui
   int ex = 0;
   std::frexp(abs_bound > 0.0 ? abs_bound : 1.0, &ex);        // abs_bound < 2^ex
   const int eunit = ex + 1 - 117;                              // 120-bit fixed point with 3 bits of headroom for 8 ranks
-  DevBuf& wire = c->scratch[10];
+  DevBuf& wire = c->scratch[14];
   int rc;
   if ((rc = ensure(c, wire, span * 6 * sizeof(long long)))) return rc;
   const unsigned grid = unsigned(std::min<uint64_t>((span + 255) / 256, uint64_t(c->sm_count) * 8));
@@ -1823,9 +1858,17 @@ extern "C" int sdbg_writer_finish(sdbg_writer* w, const uint8_t** doc_file, size
 
 extern "C" uint64_t sdbg_synth_hash(uint64_t stream, uint64_t index) { return synth_hash(stream, index); }
 
+extern "C" int sdbg_synth_corpus_ex(sdbg_segment* seg, uint64_t doc0, uint32_t n_docs, uint32_t t0, uint32_t nt, int threads,
+                                    double p_floor, uint32_t* docs_count_out, uint64_t* sum_dl_out);
 extern "C" int sdbg_synth_corpus(sdbg_segment* seg, uint64_t doc0, uint32_t n_docs, uint32_t t0, uint32_t nt, int threads,
                                  uint32_t* docs_count_out, uint64_t* sum_dl_out) {
-  if (!seg || !n_docs || !nt || n_docs != seg->n_docs) return SDBG_EINVAL;
+  return sdbg_synth_corpus_ex(seg, doc0, n_docs, t0, nt, threads, 0.0, docs_count_out, sum_dl_out);
+}
+// p_floor > 0: inclusion probability max(p_floor, min(0.5, 0.6 / (t + 1))) -- a flat tail of equally sized lists, used to
+// build an index much larger than L2 (the HBM-resident bench workload).
+extern "C" int sdbg_synth_corpus_ex(sdbg_segment* seg, uint64_t doc0, uint32_t n_docs, uint32_t t0, uint32_t nt, int threads,
+                                    double p_floor, uint32_t* docs_count_out, uint64_t* sum_dl_out) {
+  if (!seg || !n_docs || !nt || n_docs != seg->n_docs || !(p_floor >= 0.0 && p_floor <= 0.5)) return SDBG_EINVAL;
   threads = std::max(1, threads);
   std::vector<uint32_t> dl(n_docs);
   uint64_t sum_dl = 0;
@@ -1841,7 +1884,9 @@ extern "C" int sdbg_synth_corpus(sdbg_segment* seg, uint64_t doc0, uint32_t n_do
       const uint32_t i = next.fetch_add(1);
       if (i >= nt) break;
       const uint32_t t = t0 + i;
-      const double p = std::min(0.5, 0.6 / double(t + 1));
+      // terms 1000000 .. 1000004: BASELINE configs[3]'s conjunction terms, p = 0.50, 0.40, 0.30, 0.25, 0.20
+      static const double kCfg4P[5] = {0.50, 0.40, 0.30, 0.25, 0.20};
+      const double p = (t >= 1000000u && t < 1000005u) ? kCfg4P[t - 1000000u] : std::max(p_floor, std::min(0.5, 0.6 / double(t + 1)));
       const uint64_t thr = uint64_t(std::ldexp(p, 64));
       docs.clear(); freqs.clear();
       for (uint32_t d = 0; d < n_docs; ++d) {

@@ -89,6 +89,27 @@ class Context:
     def profile(self, on=True):
         N.check(N.lib().sdbg_profile_enable(self._h, 1 if on else 0), self._h)
 
+    # ---- collectives (NCCL behind the C ABI; the host only has to ship the 128-byte id to every rank) ----
+    @staticmethod
+    def dist_unique_id():
+        buf = (C.c_uint8 * 128)()
+        N.check(N.lib().sdbg_dist_unique_id(buf))
+        return bytes(buf)
+
+    def dist_init(self, id128, rank, world):
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(id128))
+        N.check(N.lib().sdbg_dist_init(self._h, buf, int(rank), int(world)), self._h)
+
+    def dist_allreduce_i64(self, d_ptr, n):
+        N.check(N.lib().sdbg_dist_allreduce_i64(self._h, C.c_void_p(int(d_ptr)), int(n)), self._h)
+
+    def dist_allgather(self, d_send, d_recv, bytes_per_rank):
+        N.check(N.lib().sdbg_dist_allgather(self._h, C.c_void_p(int(d_send)), C.c_void_p(int(d_recv)), int(bytes_per_rank)), self._h)
+
+    def dist_groupby_merge(self, d_i64, d_f64, span, abs_bound):
+        """Dense GROUP BY partials of all ranks -> global partials on every rank: one ncclAllReduce on this context's stream."""
+        N.check(N.lib().sdbg_dist_groupby_merge(self._h, C.c_void_p(int(d_i64)), C.c_void_p(int(d_f64)), int(span), float(abs_bound)), self._h)
+
     def profile_read(self, kernel):
         """kernel: 'groupby' | 'topk' | 'merge' | 'count_sum' -> (total_ms, launches) since profile(True)."""
         kid = dict(groupby=0, topk=1, merge=2, count_sum=3)[kernel]
@@ -224,12 +245,13 @@ class Segment:
     def column_to_host(self, field, host_ptr, rows):
         N.check(N.lib().sdbg_column_to_host(self._h, int(field), C.c_void_p(int(host_ptr)), int(rows)), self.ctx._h)
 
-    def synth_corpus(self, doc0, t0, nt, threads=8):
-        """SURVEY §8d corpus shard: returns (docs_count per term, sum of doc lengths)."""
+    def synth_corpus(self, doc0, t0, nt, threads=8, p_floor=0.0):
+        """SURVEY §8d corpus shard: returns (docs_count per term, sum of doc lengths). p_floor > 0 gives every term at
+        least that inclusion probability (a flat tail: an index far larger than L2)."""
         dc = np.zeros(nt, np.uint32)
         sdl = C.c_uint64()
-        N.check(N.lib().sdbg_synth_corpus(self._h, int(doc0), self.n_docs, int(t0), int(nt), int(threads), _ptr(dc),
-                                          C.byref(sdl)), self.ctx._h)
+        N.check(N.lib().sdbg_synth_corpus_ex(self._h, int(doc0), self.n_docs, int(t0), int(nt), int(threads), float(p_floor),
+                                             _ptr(dc), C.byref(sdl)), self.ctx._h)
         self.term_docs = dc.astype(np.uint64)
         return dc, sdl.value
 
@@ -359,6 +381,22 @@ class PreparedBatch:
                                              _ptr(self.off), self.nq, self.scorer.k, self.scorer.b, fp, self.k, self.threshold,
                                              _ptr(self.hits), _ptr(self.n_out), _ptr(self.total)), r.segments[0].ctx._h)
         return self.hits, self.n_out, self.total
+
+    def run_dist(self, to_host=True):
+        """Distributed top-k (sdbg_dist_bm25_topk_batch): local scan, one all-gather, local selection -- all enqueued by
+        the library on its stream. to_host=False leaves the merged keys in HBM and returns without waiting."""
+        r = self.reader
+        fp = C.byref(self.filt) if self.filt is not None else None
+        if to_host:
+            hits = np.zeros((self.nq, self.k), HIT_DTYPE)
+            n_out = np.zeros(self.nq, np.uint32)
+            hp, npp = _ptr(hits), _ptr(n_out)
+        else:
+            hits = n_out = None
+            hp = npp = None
+        N.check(N.lib().sdbg_dist_bm25_topk_batch(_seg_array(r.segments), len(r.segments), self.kind, self.terms, _ptr(self.off), self.nq,
+                                                  self.scorer.k, self.scorer.b, fp, self.k, self.threshold, hp, npp), r.segments[0].ctx._h)
+        return hits, n_out
 
     def run_device(self, rank, d_keys_ptr, d_totals_ptr=None):
         """Results stay in HBM as sortable keys (for the multi-GPU gather + merge)."""
