@@ -15,6 +15,7 @@
 #include <cstring>
 #include <limits>
 #include <map>
+#include <mutex>
 #include <memory>
 #include <thread>
 #include <unordered_map>
@@ -1204,7 +1205,7 @@ inline uint32_t select_pred(const BoundPred& b, uint64_t base, const uint16_t* i
   }
   return select_op<int64_t>(reinterpret_cast<const int64_t*>(c.data.data()), base, in, n_in, dense_in, out, b.p.op, b.p.lo_i, b.p.hi_i);
 }
-struct DenseAgg { __int128 sum_i = 0; double sum_f = 0; uint64_t count = 0; uint64_t cnt_f = 0; };
+struct DenseAgg { __int128 sum_i = 0; double sum_f = 0; uint32_t count = 0; uint32_t cnt_f = 0; };   // 32 B: one group = half a cache line
 }  // namespace
 
 extern "C" {
@@ -1222,9 +1223,18 @@ int orc_filter_groupby(orc_segment* const* segs, size_t n_segs, const orc_pred* 
     if (kc->has_stats) { kmin = std::min(kmin, kc->mn); kmax = std::max(kmax, kc->mx); }
   }
   if (kmin > kmax) { *n_out = 0; return 0; }
+  { uint64_t all_rows = 0; for (size_t si = 0; si < n_segs; ++si) all_rows += find_col(*segs[si], key_field)->rows; if (all_rows >> 32) return -3; }   // 32-bit group counts
   const bool dense = (unsigned __int128)((__int128)kmax - kmin) < ((unsigned __int128)1 << 24);
   const uint64_t span = dense ? uint64_t(kmax - kmin) + 1 : 0;
-  std::vector<std::vector<DenseAgg>> dpart(dense ? size_t(threads) : 0);
+  // Thread-local aggregate states come from a pool that outlives the call (an engine keeps its buffers; first-touch
+  // page faults of ~3 MB x threads would otherwise dominate a 100 M-row scan). A table is zeroed by the worker that
+  // uses it, the first time it claims a row group in this call.
+  static std::vector<std::vector<DenseAgg>> pool;
+  static std::mutex pool_mu;
+  std::lock_guard<std::mutex> pool_lock(pool_mu);
+  if (dense && pool.size() < size_t(threads)) pool.resize(size_t(threads));
+  std::vector<std::vector<DenseAgg>>& dpart = pool;
+  std::vector<uint8_t> used(size_t(threads), 0);
   std::vector<std::unordered_map<int64_t, DenseAgg>> hpart(dense ? 0 : size_t(threads));
   for (size_t si = 0; si < n_segs; ++si) {
     const orc_segment& s = *segs[si];
@@ -1234,7 +1244,12 @@ int orc_filter_groupby(orc_segment* const* segs, size_t n_segs, const orc_pred* 
     const Column* ic = find_col(s, sum_int_field);
     const Column* fc = find_col(s, avg_f64_field);
     parallel_chunks(kc->rows, threads, kRowGroup, [&](int t, uint64_t b, uint64_t e) {
-      if (dense && dpart[size_t(t)].empty()) dpart[size_t(t)].resize(span);
+      if (dense && !used[size_t(t)]) {
+        auto& tab = dpart[size_t(t)];
+        if (tab.size() < span) tab.resize(span);
+        std::fill(tab.begin(), tab.begin() + span, DenseAgg{});
+        used[size_t(t)] = 1;
+      }
       uint16_t sel_a[kVec], sel_b[kVec];
       for (uint64_t base = b; base < e; base += kVec) {
         uint32_t n = uint32_t(std::min<uint64_t>(kVec, e - base));
@@ -1274,7 +1289,7 @@ int orc_filter_groupby(orc_segment* const* segs, size_t n_segs, const orc_pred* 
         uint64_t groups = 0;
         for (uint64_t i = lo; i < hi; ++i) {
           DenseAgg tot;
-          for (auto& p : dpart) if (!p.empty()) { const DenseAgg& a = p[i]; tot.count += a.count; tot.sum_i += a.sum_i; tot.sum_f += a.sum_f; tot.cnt_f += a.cnt_f; }
+          for (size_t ti = 0; ti < size_t(threads); ++ti) if (used[ti]) { const DenseAgg& a = dpart[ti][i]; tot.count += a.count; tot.sum_i += a.sum_i; tot.sum_f += a.sum_f; tot.cnt_f += a.cnt_f; }
           merged[i] = tot;
           groups += tot.count ? 1 : 0;
         }

@@ -157,7 +157,7 @@ __device__ __forceinline__ void add128u(unsigned long long& lo, long long& hi, u
 
 __global__ void __launch_bounds__(256)
 filter_count_sum_kernel(const PredSet ps, const ColDev sum_col, int has_sum, uint64_t rows,
-                        CountSumOut* __restrict__ partials, unsigned int* __restrict__ done_counter) {
+                        CountSumOut* __restrict__ partials, unsigned int* __restrict__ done_counter, CountSumOut* host_out) {
   unsigned long long cnt = 0, lo = 0;
   long long hi = 0;
   double sf = 0.0;
@@ -203,15 +203,37 @@ filter_count_sum_kernel(const PredSet ps, const ColDev sum_col, int has_sum, uin
     s_last = atomicAdd(done_counter, 1u) == gridDim.x - 1u;
   }
   __syncthreads();
-  if (s_last && threadIdx.x == 0) {
+  if (s_last) {
+    // Last block to finish: combine the block partials with all 256 threads (thread i takes partials i, i + 256, ... in
+    // index order, then a fixed shuffle / shared-memory tree): one pass of parallel loads instead of gridDim.x dependent
+    // ones, and still a deterministic double sum for a given grid. The result also goes to `host_out` (mapped pinned
+    // memory) when given, so a point query needs no device-to-host copy after the launch.
     __threadfence();
     CountSumOut t = {0, 0, 0, 0.0};
-    for (uint32_t b = 0; b < gridDim.x; ++b) {
+    for (uint32_t b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
       const volatile CountSumOut* p = partials + b;
       t.count += p->count; add128u(t.sum_lo, t.sum_hi, p->sum_lo, p->sum_hi); t.sum_f += p->sum_f;
     }
-    partials[gridDim.x] = t;
-    *done_counter = 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      t.count += __shfl_xor_sync(kFull, t.count, o);
+      const unsigned long long olo = __shfl_xor_sync(kFull, t.sum_lo, o);
+      const long long ohi = __shfl_xor_sync(kFull, t.sum_hi, o);
+      add128u(t.sum_lo, t.sum_hi, olo, ohi);
+      t.sum_f += __shfl_xor_sync(kFull, t.sum_f, o);
+    }
+    __syncthreads();                       // s[] is free again (thread 0 read it before the counter increment)
+    if (lane == 0) s[warp] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      CountSumOut r = s[0];
+      for (uint32_t w = 1; w < blockDim.x / 32u; ++w) {
+        r.count += s[w].count; add128u(r.sum_lo, r.sum_hi, s[w].sum_lo, s[w].sum_hi); r.sum_f += s[w].sum_f;
+      }
+      partials[gridDim.x] = r;
+      if (host_out != nullptr) { *host_out = r; __threadfence_system(); }
+      *done_counter = 0u;
+    }
   }
 }
 

@@ -70,6 +70,10 @@ struct sdbg_ctx {
   bool topk_attr_set = false;
   void* nccl_comm = nullptr;   // ncclComm_t once sdbg_dist_init ran
   unsigned long long* h_oor = nullptr;   // pinned: out-of-range key count of the last deferred GROUP BY partial
+  void* h_result = nullptr;     // mapped pinned memory the point-query kernels write their result into (no D2H copy)
+  void* d_result = nullptr;     // its device address
+  size_t h_result_cap = 0;
+  bool counter_zeroed = false;  // scratch[10] starts at zero; every kernel that uses it leaves it at zero
   bool oor_pending = false;
   int dist_rank = 0, dist_world = 1;
   bool merge_attr_set = false;
@@ -211,6 +215,7 @@ extern "C" void sdbg_destroy(sdbg_ctx* c) {
   for (auto& b : c->scratch) if (b.p) cudaFree(b.p);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->h_oor) cudaFreeHost(c->h_oor);
+  if (c->h_result) cudaFreeHost(c->h_result);
   if (c->flush) cudaFree(c->flush);
   cudaStreamSynchronize(c->stream2);
   sdbg_dist_destroy(c);
@@ -310,6 +315,8 @@ extern "C" void sdbg_segment_destroy(sdbg_segment* s) {
   for (auto& kv : s->cols) free_column(kv.second);
   delete s;
 }
+
+extern "C" sdbg_ctx* sdbg_segment_context(const sdbg_segment* s) { return s ? s->ctx : nullptr; }
 
 extern "C" int sdbg_segment_set_wand_b(sdbg_segment* s, float wand_b) {
   if (!s) return SDBG_EINVAL;
@@ -1214,9 +1221,20 @@ extern "C" int sdbg_filter_count_sum(sdbg_segment* const* segs, size_t n_segs, c
   const unsigned grid = unsigned(c->sm_count) * 4u;
   int rc;
   if ((rc = ensure(c, c->scratch[9], (size_t(grid) + 1) * sizeof(CountSumOut) * n_segs + 64))) return rc;
-  if ((rc = ensure(c, c->scratch[10], 16))) return rc;
-  CU(c, cudaMemsetAsync(c->scratch[10].p, 0, 16, c->stream));
-  if ((rc = ensure_pinned(c, n_segs * sizeof(CountSumOut)))) return rc;
+  // Point-query latency: ONE launch per segment and one stream synchronisation. The completion counter is zeroed once
+  // (the kernel leaves it at zero), and the final partial is written by the kernel straight into mapped pinned memory.
+  if (!c->counter_zeroed || c->scratch[15].cap < 16) {
+    if ((rc = ensure(c, c->scratch[15], 16))) return rc;
+    CU(c, cudaMemsetAsync(c->scratch[15].p, 0, 16, c->stream));
+    c->counter_zeroed = true;
+  }
+  if (c->h_result_cap < n_segs * sizeof(CountSumOut)) {
+    if (c->h_result) { cudaStreamSynchronize(c->stream); cudaFreeHost(c->h_result); c->h_result = nullptr; }
+    const size_t want = std::max<size_t>(n_segs * sizeof(CountSumOut), 4096);
+    CU(c, cudaHostAlloc(&c->h_result, want, cudaHostAllocMapped));
+    CU(c, cudaHostGetDevicePointer(&c->d_result, c->h_result, 0));
+    c->h_result_cap = want;
+  }
   for (size_t si = 0; si < n_segs; ++si) {
     sdbg_segment* s = segs[si];
     PredSet ps; uint64_t rows = 0;
@@ -1226,20 +1244,22 @@ extern "C" int sdbg_filter_count_sum(sdbg_segment* const* segs, size_t n_segs, c
       uint64_t r = 0;
       if ((rc = col_view(s, sum_field, &sc, &r))) return rc;
       if (!rows) rows = r;
+      if (r != rows) return fail(c, SDBG_EINVAL, "columns of one segment differ in length");
       has_sum = 1;
     }
     if (!rows) rows = s->n_docs;
     auto* part = static_cast<CountSumOut*>(c->scratch[9].p) + si * (size_t(grid) + 1);
+    const unsigned g2 = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(grid, (rows + 2047) / 2048)));   // 8 rows per thread at least
     { ProfScope ps_(c, kProfCountSum);
-      filter_count_sum_kernel<<<grid, 256, 0, c->stream>>>(ps, sc, has_sum, rows, part, static_cast<unsigned int*>(c->scratch[10].p)); }
+      filter_count_sum_kernel<<<g2, 256, 0, c->stream>>>(ps, sc, has_sum, rows, part, static_cast<unsigned int*>(c->scratch[15].p),
+                                                         static_cast<CountSumOut*>(c->d_result) + si); }
     ++c->launches;
     CU(c, cudaGetLastError());
-    CU(c, cudaMemcpyAsync(static_cast<CountSumOut*>(c->h_pinned) + si, part + grid, sizeof(CountSumOut), cudaMemcpyDeviceToHost, c->stream));
   }
   CU(c, cudaStreamSynchronize(c->stream));
   unsigned __int128 tot = 0; uint64_t cnt = 0; double sf = 0;
   for (size_t si = 0; si < n_segs; ++si) {
-    const CountSumOut& o = static_cast<const CountSumOut*>(c->h_pinned)[si];
+    const CountSumOut& o = static_cast<const CountSumOut*>(c->h_result)[si];
     cnt += o.count; sf += o.sum_f;
     tot += (static_cast<unsigned __int128>(static_cast<uint64_t>(o.sum_hi)) << 64) | o.sum_lo;
   }

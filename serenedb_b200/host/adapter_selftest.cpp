@@ -9,6 +9,7 @@
 
 namespace {
 struct ListCollector final : irs::ScoreCollector {  // a trivial ScoreCollector: keeps what it is fed
+  ListCollector() : irs::ScoreCollector(Tag::Generic) {}
   std::vector<irs::ScoreDoc> docs;
   void Add(irs::score_t s, irs::doc_id_t d) override { docs.push_back({s, d, 0}); }
   void AddWindow(const irs::score_t*, const uint64_t*, irs::doc_id_t, size_t, bool) override {}
@@ -39,7 +40,20 @@ int main(int argc, char** argv) {
   it.Collect(sf, fetcher, col);
   std::printf("{\"topk\": [");
   for (size_t i = 0; i < col.docs.size(); ++i) std::printf("%s[%u, %.9g]", i ? ", " : "", col.docs[i].doc, double(col.docs[i].score));
-  std::printf("], \"total\": %llu, \"threshold\": %.9g}\n", static_cast<unsigned long long>(it.total_matches()), double(it.threshold().value));
+  // attributes through the reference's accessor, and the bitmap window of the first 4096 docs
+  const auto* thr = irs::get<irs::ScoreThresholdAttr>(it);
+  const auto* cost = irs::get<irs::CostAttr>(it);
+  sdbg_host::GpuTopKIterator it2(seg, SDBG_QUERY_OR, terms, 1.2f, 0.75f, 100, &filt);
+  std::vector<uint64_t> mask(64, 0);
+  std::vector<irs::score_t> window(4096, 0.f);
+  irs::FillBlockScoreContext sc; sc.score_window = window.data(); sc.merge_type = irs::ScoreMergeType::Sum;
+  const auto fb = it2.FillBlock(1, 4097, mask.data(), sc, irs::FillBlockMatchContext{});
+  unsigned bits = 0; double wsum = 0;
+  for (uint64_t w : mask) bits += unsigned(__builtin_popcountll(w));
+  for (float w : window) wsum += w;
+  std::printf("], \"total\": %llu, \"threshold\": %.9g, \"attr_threshold\": %.9g, \"attr_cost\": %llu, \"fill_bits\": %u, \"fill_sum\": %.9g, \"fill_next\": %u}\n",
+              static_cast<unsigned long long>(it.total_matches()), double(it.threshold().value), double(thr ? thr->value : -1.f),
+              static_cast<unsigned long long>(cost ? cost->estimate() : 0), bits, wsum, fb.first);
   // --- aggregate scan through the table-function adapter ---
   for (uint64_t f = 10; f <= 14; ++f) sdbg_synth_column(seg, f, f, int(f - 10), 0, n_docs);
   std::vector<sdbg_col_pred> preds(2);

@@ -31,7 +31,7 @@ void GpuTopKIterator::run() {
   by_doc_ = hits_;
   std::sort(by_doc_.begin(), by_doc_.end(), [](const sdbg_hit& a, const sdbg_hit& b) { return a.doc < b.doc; });
   if (n == k_ && thr_out > threshold_.value) threshold_.value = thr_out;  // raise the caller-visible threshold
-  cost_.value = total_;
+  cost_.reset(total_);
   ran_ = true;
 }
 
@@ -66,6 +66,35 @@ uint32_t GpuTopKIterator::EmitDocs(irs::doc_id_t* out, irs::doc_id_t min, irs::d
 
 uint32_t GpuTopKIterator::count() { run(); return uint32_t(total_); }
 
+irs::Attribute* GpuTopKIterator::GetMutable(irs::TypeInfo::type_id type) noexcept {
+  if (type == irs::Type<irs::ScoreThresholdAttr>::id()) return &threshold_;
+  if (type == irs::Type<irs::CostAttr>::id()) return &cost_;
+  return nullptr;
+}
+
+std::pair<irs::doc_id_t, bool> GpuTopKIterator::FillBlock(irs::doc_id_t min, irs::doc_id_t max, uint64_t* mask,
+                                                          irs::FillBlockScoreContext score, irs::FillBlockMatchContext match) {
+  run();
+  bool empty = true;
+  while (pos_ < by_doc_.size() && by_doc_[pos_].doc < min) ++pos_;
+  for (; pos_ < by_doc_.size() && by_doc_[pos_].doc < max; ++pos_) {
+    const uint32_t off = by_doc_[pos_].doc - min;
+    bool set = true;
+    if (match.matches) set = ++match.matches[off] >= match.min_match_count;   // TrackMatch: bit only when the threshold is met
+    if (set) { mask[off >> 6] |= uint64_t(1) << (off & 63); empty = false; }
+    if (score.score_window) {
+      irs::score_t& w = score.score_window[off];
+      switch (score.merge_type) {
+        case irs::ScoreMergeType::Sum: w += by_doc_[pos_].score; break;
+        case irs::ScoreMergeType::Max: w = std::max(w, by_doc_[pos_].score); break;
+        default: w = by_doc_[pos_].score; break;
+      }
+    }
+  }
+  _doc = pos_ < by_doc_.size() ? by_doc_[pos_].doc : irs::doc_limits::eof();
+  return {_doc, match.matches ? empty : false};
+}
+
 irs::doc_id_t GpuTopKIterator::advance() {
   run();
   if (_doc != irs::doc_limits::invalid() && pos_ < by_doc_.size() && by_doc_[pos_].doc == _doc) ++pos_;
@@ -91,8 +120,8 @@ void GpuAggScan::Scan(duckdb::DataChunkMock& output) {
       groups_.resize(cap);
       const int rc = sdbg_filter_groupby(segs_.data(), segs_.size(), preds_.data(), preds_.size(), key_, hint_, sum_i_, avg_f_,
                                          groups_.data(), cap, &n);
-      if (rc == SDBG_ECAPACITY) { cap = n; continue; }  // the call reports how many groups exist
-      check(rc, "sdbg_filter_groupby");
+      if (rc == SDBG_ECAPACITY && n > cap) { cap = n; continue; }  // the call reports how many groups exist: one retry with room for them
+      if (rc != SDBG_OK) throw GpuError(rc, std::string("sdbg_filter_groupby: ") + sdbg_last_error(sdbg_segment_context(segs_[0])));
       break;
     }
     groups_.resize(n);

@@ -46,9 +46,18 @@ class GpuTopKIterator final : public irs::DocIterator {
   uint32_t count() override;  // total matches (exhaustive, like DocIterator::count)
   irs::doc_id_t advance() override;
   irs::doc_id_t seek(irs::doc_id_t target) override;
+  // Bitmap + score window of [min, max) for callers that merge iterators (Conjunction / MaxScore windows,
+  // iterators.hpp:322-337): bit (doc - min) per hit, score accumulated into score.score_window per merge_type,
+  // match counts when match.matches is given. The hits are this iterator's top-k (its whole result set).
+  std::pair<irs::doc_id_t, bool> FillBlock(irs::doc_id_t min, irs::doc_id_t max, uint64_t* mask, irs::FillBlockScoreContext score,
+                                           irs::FillBlockMatchContext match) override;
+  void FetchScoreArgs(uint16_t) override {}   // score arguments never leave the GPU
+  // AttributeProvider: ScoreThresholdAttr (the caller seeds / reads the running threshold through it,
+  // doc_collector.hpp:124-130, duckdb_search_full_scan.cpp:1910-1914) and CostAttr (conjunction ordering).
+  irs::Attribute* GetMutable(irs::TypeInfo::type_id type) noexcept override;
 
-  irs::ScoreThresholdAttr& threshold() noexcept { return threshold_; }   // GetMutable<ScoreThresholdAttr>
-  const irs::CostAttr& cost() const noexcept { return cost_; }           // GetMutable<CostAttr>
+  irs::ScoreThresholdAttr& threshold() noexcept { return threshold_; }
+  const irs::CostAttr& cost() const noexcept { return cost_; }
   uint64_t total_matches() const noexcept { return total_; }
 
  private:

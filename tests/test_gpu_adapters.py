@@ -32,6 +32,14 @@ def test_adapters_match_oracle():
     assert np.array_equal(np.array([s for _, s in topk["topk"]], np.float32), oh["score"])
     assert topk["total"] == ototal
     assert np.float32(topk["threshold"]) == oh["score"][-1]      # threshold raised to the k-th score
+    # the reference's accessors: irs::get<ScoreThresholdAttr> / irs::get<CostAttr> through AttributeProvider::GetMutable
+    assert np.float32(topk["attr_threshold"]) == oh["score"][-1] and topk["attr_cost"] == ototal
+    # FillBlock over docs [1, 4097): one bit and one score per hit in the window, value() = first hit beyond it
+    inwin = oh[oh["doc"] < 4097]
+    later = oh["doc"][oh["doc"] >= 4097]
+    assert topk["fill_bits"] == len(inwin)
+    assert topk["fill_sum"] == pytest.approx(float(inwin["score"].astype(np.float64).sum()), rel=1e-6)
+    assert topk["fill_next"] == (int(later.min()) if len(later) else 0xFFFFFFFF)
     # ---- GpuAggScan chunks vs oracle GROUP BY ----
     cols = {10: (10, 0), 11: (11, 1), 12: (12, 2), 13: (13, 3), 14: (14, 4)}
     for f, (stream, kind) in cols.items():

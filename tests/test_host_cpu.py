@@ -141,3 +141,19 @@ def test_cpp_adapters_build_and_fail_loudly_without_gpu():
         pytest.skip("GPU present: covered by tests/test_gpu_adapters.py")
     res = subprocess.run([exe, "1000"], capture_output=True, text=True)
     assert res.returncode == 3 and '"error": -2' in res.stdout
+
+
+def test_mock_headers_match_the_reference():
+    """Every `//@ref file:lines` block of host/irs_mock.hpp repeats the cited reference declarations token for token, so the
+    adapters override the real virtual surface (FillBlock, GetMutable, FetchScoreArgs, ScoreCollector(Tag) included).
+    Needs the reference tree: skipped on boxes without it."""
+    import importlib.util
+    import os
+    import pytest
+    if not os.path.isdir("/root/reference/libs/iresearch"):
+        pytest.skip("no reference tree on this box")
+    spec = importlib.util.spec_from_file_location("check_mock", os.path.join(os.path.dirname(__file__), "..", "tools", "check_mock.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    blocks, decls, problems = m.check("/root/reference")
+    assert blocks >= 6 and decls >= 60 and not problems, problems
