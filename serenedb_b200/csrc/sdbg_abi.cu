@@ -1067,16 +1067,27 @@ extern "C" int sdbg_topk_merge_gathered(sdbg_ctx* c, const void* d_keys_all, uin
   CU(c, cudaStreamSynchronize(c->stream));
   const auto* keys = reinterpret_cast<const unsigned long long*>(h);
   const auto* cnt = reinterpret_cast<const uint32_t*>(h + kb);
-  for (size_t q = 0; q < nq; ++q) {
-    n_out[q] = cnt[q];
-    for (uint32_t i = 0; i < cnt[q]; ++i) {
-      const unsigned long long key = keys[q * k + i];
-      const uint32_t bits = uint32_t(key >> 32), ordinal = ~uint32_t(key);
-      sdbg_hit& h2 = out[q * k + i];
-      std::memcpy(&h2.score, &bits, 4);
-      h2.seg = ordinal >> 28;             // rank slot
-      h2.doc = ordinal & ((1u << 28) - 1);  // ordinal within the rank (segment base + doc)
+  auto convert = [&](size_t q0, size_t q1) {
+    for (size_t q = q0; q < q1; ++q) {
+      n_out[q] = cnt[q];
+      for (uint32_t i = 0; i < cnt[q]; ++i) {
+        const unsigned long long key = keys[q * k + i];
+        const uint32_t bits = uint32_t(key >> 32), ordinal = ~uint32_t(key);
+        sdbg_hit& h2 = out[q * k + i];
+        std::memcpy(&h2.score, &bits, 4);
+        h2.seg = ordinal >> 28;             // rank slot
+        h2.doc = ordinal & ((1u << 28) - 1);  // ordinal within the rank (segment base + doc)
+      }
     }
+  };
+  // a few ns per hit; a large batch (millions of hits) is split over host threads like sdbg_bm25_topk_batch does
+  const size_t n_thr = std::min<size_t>(size_t(env_int("SDBG_HOST_THREADS", 8)), (nq * size_t(k)) / 65536);
+  if (n_thr <= 1) {
+    convert(0, nq);
+  } else {
+    std::vector<std::thread> pool;
+    for (size_t t = 0; t < n_thr; ++t) pool.emplace_back(convert, nq * t / n_thr, nq * (t + 1) / n_thr);
+    for (auto& th : pool) th.join();
   }
   return SDBG_OK;
 }
