@@ -433,8 +433,12 @@ def main():
         crow = min(args.cpu_rows, rows)
         cols = {f: host[f].numpy() for f in COLS}
         cres, ctimes = cpu_groupby(cols, crow, threads, 3)
-        best = min(ctimes)
-        cpu_gb = {"value": round(crow / best / 1e6, 2), "unit": "Mrows/s", "cores": threads, "kind": "port",
+        best, best_thr = min(ctimes), threads
+        for thr2 in (max(1, threads // 2), max(1, threads // 4)):   # hyper-threads / NUMA: the port may peak below the full thread count
+            c2, t2 = cpu_groupby(cols, crow, thr2, 2)
+            if min(t2) < best:
+                best, best_thr = min(t2), thr2
+        cpu_gb = {"value": round(crow / best / 1e6, 2), "unit": "Mrows/s", "cores": best_thr, "kind": "port",
                   "sample": "%d rows of the same table, best of 3 (oracle restatement of the scan+DuckDB aggregate)" % crow}
         if crow == rows:  # the CPU leg doubles as a full-size parity check of this very run
             assert np.array_equal(cres["key"], res["key"]) and np.array_equal(cres["count"], res["count"])

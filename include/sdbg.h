@@ -105,6 +105,8 @@ int sdbg_stage_docs_mask(sdbg_segment*, const uint32_t* deleted_docs, size_t n);
    0.75). Block-max pruning is used only for queries whose scorer has the same b -- the check Scorer::equals makes in
    PostingsReaderImpl::WandIterator (formats/posting/reader.hpp:457-501); any other scorer is evaluated exhaustively. */
 int sdbg_segment_set_wand_b(sdbg_segment*, float wand_b);
+/* Zonemap effect of the last GROUP BY scan: 2048-row blocks judged / proven dead from their min-max (never read). */
+int sdbg_scan_stats(sdbg_ctx*, uint64_t* blocks_total, uint64_t* blocks_skipped);
 /* The context a segment was created in (for sdbg_last_error after a failed call that only has segments at hand). */
 sdbg_ctx* sdbg_segment_context(const sdbg_segment*);
 typedef struct { uint8_t byte_size; uint32_t row_count; uint64_t file_offset; } sdbg_norm_rg; /* norm_writer.hpp:41-48 */

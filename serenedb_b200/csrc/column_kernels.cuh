@@ -371,7 +371,12 @@ struct TmaGroupByParams {
   uint64_t rows;
   GroupSlot* table;
   unsigned long long* out_of_range;
+  // Zonemap verdicts (or null): skip[b] != 0 means no row of the 2048-row block b can pass the pushed predicates
+  // (per-block min / max against every predicate's range: ColFilterChain::FilterWindow / DeadUntil,
+  // irs/index/table_filter_iterator.cpp:147-286). Such tiles are neither copied nor looked at.
+  const uint8_t* skip;
 };
+constexpr uint32_t kZoneRows = 2048;   // rows per zonemap block = the reference's filter window (STANDARD_VECTOR_SIZE)
 
 // Order-preserving map from the bits of a double to int64 (negative doubles reversed). -0.0 maps just
 // below +0.0 (the host widens range ends that are zeros accordingly); NaNs land beyond +-inf, outside
@@ -451,8 +456,10 @@ filter_groupby_tma_kernel(const TmaGroupByParams P) {
     // ===== producer: one thread keeps the ring full =====
     if (lane == 0) {
       uint32_t it = 0;
-      for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (P.skip != nullptr && P.skip[(tile * kTileRows) / kZoneRows]) continue;   // zonemap: nothing in this tile can pass
         const uint32_t st = it % kStages, use = it / kStages;
+        ++it;
         mbar_wait(&empty_bar[st], (use & 1u) ^ 1u);           // consumers released the previous use of this stage
         const uint64_t row0 = tile * kTileRows;
         const uint32_t nrows = uint32_t(min(static_cast<unsigned long long>(kTileRows), static_cast<unsigned long long>(P.rows - row0)));
@@ -477,8 +484,10 @@ filter_groupby_tma_kernel(const TmaGroupByParams P) {
   // 16-byte (8-byte for int32) shared load per lane and the column type is a warp-uniform switch
   // outside the per-row work.
   uint32_t it = 0;
-  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    if (P.skip != nullptr && P.skip[(tile * kTileRows) / kZoneRows]) continue;       // same verdict as the producer's
     const uint32_t st = it % kStages, use = it / kStages;
+    ++it;
     mbar_wait(&full_bar[st], use & 1u);
     const unsigned char* base = smem + size_t(st) * stage_bytes;
     const uint64_t row0 = tile * kTileRows;
@@ -590,6 +599,63 @@ filter_groupby_tma_kernel(const TmaGroupByParams P) {
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[st]);   // this warp is done reading the stage
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Zonemaps: min / max per 2048-row block of a NOT NULL column, in the int64 key space the predicates are resolved into
+// (integers as they are, doubles through fkey()). Built once per column on first use (the reference keeps them in
+// ColumnBlockMeta::statistics, irs/formats/column/column_reader.hpp:90-96). One warp per block.
+// ------------------------------------------------------------------------------------------
+template <int kType>
+__global__ void __launch_bounds__(256)
+zonemap_kernel(const unsigned char* __restrict__ values, uint64_t rows, long long* __restrict__ zone /* [blocks][2] */) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t n_blocks = (rows + kZoneRows - 1) / kZoneRows;
+  for (uint64_t b = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; b < n_blocks; b += (uint64_t(gridDim.x) * blockDim.x) >> 5) {
+    long long mn = 0x7FFFFFFFFFFFFFFFll, mx = -0x7FFFFFFFFFFFFFFFll - 1;
+    const uint64_t r0 = b * kZoneRows, r1 = min(rows, r0 + kZoneRows);
+    for (uint64_t r = r0 + lane; r < r1; r += 32u) {
+      long long v;
+      if (kType == 2) v = reinterpret_cast<const int*>(values)[r];
+      else v = reinterpret_cast<const long long*>(values)[r];
+      if (kType == 1) v = fkey(v);
+      mn = min(mn, v); mx = max(mx, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(kFull, mn, o)); mx = max(mx, __shfl_xor_sync(kFull, mx, o)); }
+    if (lane == 0) { zone[2 * b] = mn; zone[2 * b + 1] = mx; }
+  }
+}
+
+struct ZoneVerdictParams {
+  const long long* zone[kMaxPreds];   // per predicate: the column's zonemap (null: no verdict from this predicate)
+  long long lo[kMaxPreds];
+  unsigned long long span[kMaxPreds];
+  int negate[kMaxPreds];
+  int n_preds;
+  uint64_t n_blocks;
+};
+// skip[b] = 1 when some predicate's range [lo, lo + span] misses the block's [min, max] entirely (a negated predicate,
+// SQL <>, only when the whole block equals the excluded value). counter += number of skipped blocks.
+__global__ void __launch_bounds__(256)
+zone_verdict_kernel(const ZoneVerdictParams Z, uint8_t* __restrict__ skip, unsigned long long* __restrict__ counter) {
+  unsigned long long mine = 0;
+  for (uint64_t b = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; b < Z.n_blocks; b += uint64_t(gridDim.x) * blockDim.x) {
+    bool dead = false;
+    for (int i = 0; i < Z.n_preds; ++i) {
+      if (Z.zone[i] == nullptr) continue;
+      const long long mn = Z.zone[i][2 * b], mx = Z.zone[i][2 * b + 1];
+      const long long lo = Z.lo[i];
+      const bool hi_below = static_cast<unsigned long long>(mn - lo) > Z.span[i] && mn > lo;   // block starts beyond lo + span
+      const bool lo_above = mx < lo;                                                             // block ends before lo
+      if (Z.negate[i]) dead |= Z.span[i] == 0ull && mn == lo && mx == lo;
+      else dead |= hi_below || lo_above;
+    }
+    skip[b] = dead ? 1 : 0;
+    mine += dead ? 1ull : 0ull;
+  }
+  mine = warp_sum64(mine);
+  if ((threadIdx.x & 31u) == 0u && mine) atomicAdd(counter, mine);
 }
 
 // ------------------------------------------------------------------------------------------

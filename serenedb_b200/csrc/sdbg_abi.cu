@@ -47,6 +47,7 @@ struct ColumnObj {
   bool owned = true;
   bool has_minmax = false;
   int64_t mn = 0, mx = 0;
+  long long* d_zone = nullptr;  // zonemap: {min, max} per 2048-row block in predicate key space (NOT NULL columns, built on first use)
   bool has_absmax = false;      // double columns: bits of the largest |value| (>= 0x7FF0... when NaN / inf occur)
   uint64_t absmax_bits = 0;
 };
@@ -75,6 +76,8 @@ struct sdbg_ctx {
   size_t h_result_cap = 0;
   bool counter_zeroed = false;  // scratch[10] starts at zero; every kernel that uses it leaves it at zero
   bool oor_pending = false;
+  uint64_t zone_blocks_total = 0;   // last GROUP BY scan: 2048-row blocks seen / proven dead by their zonemaps
+  unsigned long long* d_zone_skipped = nullptr;
   int dist_rank = 0, dist_world = 1;
   bool merge_attr_set = false;
   // optional per-kernel timing: CUDA events recorded on `stream` around the hot kernels
@@ -215,6 +218,7 @@ extern "C" void sdbg_destroy(sdbg_ctx* c) {
   for (auto& b : c->scratch) if (b.p) cudaFree(b.p);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->h_oor) cudaFreeHost(c->h_oor);
+  if (c->d_zone_skipped) cudaFree(c->d_zone_skipped);
   if (c->h_result) cudaFreeHost(c->h_result);
   if (c->flush) cudaFree(c->flush);
   cudaStreamSynchronize(c->stream2);
@@ -299,6 +303,7 @@ void free_postings(sdbg_segment* s) {
   s->d_arena = s->d_blocks = s->d_blkmax = nullptr;
 }
 void free_column(ColumnObj& c) {
+  if (c.d_zone) { cudaFree(c.d_zone); c.d_zone = nullptr; }
   if (c.owned && c.d_values) cudaFree(c.d_values);
   if (c.d_validity) cudaFree(c.d_validity);
   c.d_values = nullptr; c.d_validity = nullptr;
@@ -317,6 +322,20 @@ extern "C" void sdbg_segment_destroy(sdbg_segment* s) {
 }
 
 extern "C" sdbg_ctx* sdbg_segment_context(const sdbg_segment* s) { return s ? s->ctx : nullptr; }
+
+// Zonemap effect of the last GROUP BY scan on this context: 2048-row blocks looked at by the verdict pass and how many
+// of them were proven dead (never copied, never evaluated). Synchronises the stream.
+extern "C" int sdbg_scan_stats(sdbg_ctx* c, uint64_t* blocks_total, uint64_t* blocks_skipped) {
+  if (!c) return SDBG_EINVAL;
+  unsigned long long skipped = 0;
+  if (c->d_zone_skipped) {
+    CU(c, cudaMemcpyAsync(&skipped, c->d_zone_skipped, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+  }
+  if (blocks_total) *blocks_total = c->zone_blocks_total;
+  if (blocks_skipped) *blocks_skipped = skipped;
+  return SDBG_OK;
+}
 
 extern "C" int sdbg_segment_set_wand_b(sdbg_segment* s, float wand_b) {
   if (!s) return SDBG_EINVAL;
@@ -1453,6 +1472,43 @@ int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred
         T.pred_lo[k] = lo; T.pred_span[k] = static_cast<uint64_t>(hi) - static_cast<uint64_t>(lo);
       }
       if (never) continue;   // WHERE is false for every row of this segment
+      // Zonemap verdicts: blocks whose min / max miss a predicate's range are skipped by producer and consumers alike.
+      T.skip = nullptr;
+      if (T.n_preds && env_int("SDBG_ZONEMAP", 1) != 0) {
+        ZoneVerdictParams Z;
+        std::memset(&Z, 0, sizeof Z);
+        Z.n_preds = T.n_preds;
+        Z.n_blocks = (rows + kZoneRows - 1) / kZoneRows;
+        bool any_zone = false;
+        for (int k2 = 0; k2 < T.n_preds; ++k2) {
+          Z.lo[k2] = T.pred_lo[k2]; Z.span[k2] = T.pred_span[k2]; Z.negate[k2] = T.pred_negate[k2];
+          ColumnObj* co = nullptr;
+          for (auto& kv : s->cols) if (kv.second.d_values == T.src[stream_idx[k2]]) { co = &kv.second; break; }
+          if (!co || co->d_validity) continue;
+          if (!co->d_zone) {
+            CU(c, cudaMalloc(reinterpret_cast<void**>(&co->d_zone), Z.n_blocks * 16));
+            const unsigned zg = unsigned(std::min<uint64_t>((Z.n_blocks + 7) / 8, uint64_t(c->sm_count) * 8));
+            const auto* vals = static_cast<const unsigned char*>(co->d_values);
+            if (co->type == SDBG_F64) zonemap_kernel<1><<<zg, 256, 0, c->stream>>>(vals, rows, co->d_zone);
+            else if (co->type == SDBG_I32) zonemap_kernel<2><<<zg, 256, 0, c->stream>>>(vals, rows, co->d_zone);
+            else zonemap_kernel<0><<<zg, 256, 0, c->stream>>>(vals, rows, co->d_zone);
+            ++c->launches;
+          }
+          Z.zone[k2] = co->d_zone;
+          any_zone = true;
+        }
+        if (any_zone) {
+          DevBuf& b_skip = c->scratch[13];
+          if ((rc = ensure(c, b_skip, Z.n_blocks + 16))) return rc;
+          if (!c->d_zone_skipped) CU(c, cudaMalloc(reinterpret_cast<void**>(&c->d_zone_skipped), 8));
+          if (si == 0) { CU(c, cudaMemsetAsync(c->d_zone_skipped, 0, 8, c->stream)); c->zone_blocks_total = 0; }
+          const unsigned vg = unsigned(std::min<uint64_t>((Z.n_blocks + 255) / 256, uint64_t(c->sm_count) * 4));
+          zone_verdict_kernel<<<vg, 256, 0, c->stream>>>(Z, static_cast<uint8_t*>(b_skip.p), c->d_zone_skipped);
+          ++c->launches;
+          c->zone_blocks_total += Z.n_blocks;
+          T.skip = static_cast<const uint8_t*>(b_skip.p);
+        }
+      }
       const int key_s = stream_of(P.key);
       const int sum_i_s = P.has_sum_i ? stream_of(P.sum_i) : -1;
       const int sum_f_s = P.has_sum_f ? stream_of(P.sum_f) : -1;

@@ -29,16 +29,38 @@ def _ptr(a):
 
 
 def pred(field, op, lo=0, hi=0):
-    """One pushed column predicate (duckdb TableFilter). Float bounds select a double comparison."""
+    """One pushed column predicate (duckdb TableFilter). Float bounds select a double comparison on a double column;
+    on an integer column the kernels compare integers, so the integer bounds are the tightest integers with the same
+    truth set (v < 2.5 <=> v < 3, v >= 2.5 <=> v >= 3, v <= 2.5 <=> v <= 2, v > 2.5 <=> v > 2)."""
+    import math
     p = N.ColPred()
     p.field = int(field)
     p.op = OPS[op] if isinstance(op, str) else int(op)
     is_float = isinstance(lo, float) or isinstance(hi, float)
     p.is_float = 1 if is_float else 0
-    p.lo_i, p.hi_i = (0, 0) if is_float else (int(lo), int(hi))
     p.lo_f, p.hi_f = float(lo), float(hi)
     if not is_float:
-        p.lo_f, p.hi_f = float(lo), float(hi)
+        p.lo_i, p.hi_i = int(lo), int(hi)
+        return p
+    name = {v: k for k, v in OPS.items()}.get(p.op, "")
+    big = (1 << 62)
+    clamp = lambda x: int(max(-big, min(big, x)))
+    lo_f, hi_f = float(lo), float(hi)
+    if math.isnan(lo_f) or math.isinf(lo_f) or math.isnan(hi_f) or math.isinf(hi_f):
+        p.lo_i, p.hi_i = clamp(-big if lo_f < 0 else big) if not math.isnan(lo_f) else 0, 0
+        return p
+    if name in ("LT", "GE"):
+        p.lo_i = clamp(math.ceil(lo_f))
+    elif name in ("LE", "GT"):
+        p.lo_i = clamp(math.floor(lo_f))
+    elif name == "BETWEEN":
+        p.lo_i, p.hi_i = clamp(math.ceil(lo_f)), clamp(math.floor(hi_f))
+    elif name in ("EQ", "NE"):
+        # = / <> with a fractional constant on an integer column is a constant predicate the planner folds away
+        # (DuckDB does); it is not representable here, so reject it instead of comparing with a rounded value
+        if lo_f != math.floor(lo_f):
+            raise ValueError("fold '= / <> fractional constant' on an integer column before pushing it down")
+        p.lo_i = clamp(lo_f)
     return p
 
 
@@ -88,6 +110,12 @@ class Context:
 
     def profile(self, on=True):
         N.check(N.lib().sdbg_profile_enable(self._h, 1 if on else 0), self._h)
+
+    def scan_stats(self):
+        """(2048-row blocks judged by the zonemap pass of the last GROUP BY scan, blocks proven dead = never read)."""
+        a, b = C.c_uint64(), C.c_uint64()
+        N.check(N.lib().sdbg_scan_stats(self._h, C.byref(a), C.byref(b)), self._h)
+        return a.value, b.value
 
     # ---- collectives (NCCL behind the C ABI; the host only has to ship the 128-byte id to every rank) ----
     @staticmethod

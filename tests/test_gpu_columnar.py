@@ -299,3 +299,46 @@ def test_groupby_reference_goldens_on_gpu():
     for col, names, exp in (("category", "category_names", "expect_category"), ("brand", "brand_names", "expect_brand"), ("band", "band_names", "expect_band")):
         out = run(g["rows"][col])
         assert {g[names][int(k)]: int(c) for k, c in zip(out["key"], out["count"])} == g[exp]
+
+
+def test_zonemaps_skip_dead_blocks_and_keep_results():
+    """Per-block min / max verdicts (ColFilterChain::FilterWindow / DeadUntil, table_filter_iterator.cpp:147-286): on a
+    clustered column most 2048-row blocks cannot pass a selective range and are never read; results stay those of the
+    oracle, and an unclustered column skips nothing."""
+    rows = 1_000_000
+    rng = np.random.default_rng(11)
+    k = rng.integers(0, 1000, rows).astype(np.int64)
+    a = (np.arange(rows) // 100).astype(np.int64)            # clustered: 0 .. 9999
+    b = rng.random(rows)
+    v = rng.integers(-1000, 1001, rows).astype(np.int64)
+    w = rng.random(rows) * 1000.0
+    oseg = orc.Segment(rows, has_wand=False)
+    gseg = sdb.Segment(ctx(), rows)
+    for f, arr in {1: k, 2: a, 3: b, 4: v, 5: w}.items():
+        oseg.add_column(f, arr)
+        gseg.stage_column(f, arr)
+    scan = sdb.IResearchScan([gseg])
+    cases = [([("LT", 2, 1000)], 0.85), ([("BETWEEN", 2, 5000, 5100)], 0.95), ([("GE", 2, 9990), ("GEF", 3, 0.25)], 0.95),
+             ([("NE", 2, 7)], 0.0), ([("GEF", 3, 0.25)], 0.0), ([("EQ", 2, 123456)], 1.0)]
+    for spec, min_skipped in cases:
+        gp, op = [], []
+        for sp in spec:
+            if sp[0] == "GEF":
+                gp.append(sdb.pred(sp[1], "GE", sp[2])); op.append(orc.make_pred(sp[1], "GE", sp[2], is_float=True))
+            elif sp[0] == "BETWEEN":
+                gp.append(sdb.pred(sp[1], "BETWEEN", sp[2], sp[3])); op.append(orc.make_pred(sp[1], "BETWEEN", sp[2], sp[3]))
+            else:
+                gp.append(sdb.pred(sp[1], sp[0], sp[2])); op.append(orc.make_pred(sp[1], sp[0], sp[2]))
+        got = scan.groupby(gp, 1, sum_int_field=4, avg_f64_field=5)
+        exp = orc.filter_groupby([oseg], op, 1, 4, 5, cap=2000)
+        assert len(got) == len(exp)
+        for f in ("key", "count", "sum_lo", "sum_hi"):
+            assert np.array_equal(got[f], exp[f]), (spec, f)
+        if len(exp):
+            assert np.allclose(got["sum_f64"], exp["sum_f64"], rtol=1e-9)
+        total, skipped = ctx().scan_stats()
+        if min_skipped > 0:
+            assert total == (rows + 2047) // 2048 and skipped >= min_skipped * total, (spec, total, skipped)
+        elif len(exp):
+            assert skipped == 0, (spec, skipped)
+    gseg.close()
