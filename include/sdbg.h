@@ -162,10 +162,17 @@ int sdbg_bm25_topk(sdbg_segment* const* segs, size_t n_segs, int kind, const sdb
                    sdbg_hit* out, uint32_t* n_out, uint64_t* total_matches, float* threshold_out);
 /* A batch of independent queries in one launch set (the benchmark-game / many-workers shape).
  * Query q uses terms[term_off[q] .. term_off[q+1]); out holds n_queries*k hits, n_out/total per query. */
+/* k1 = -1 is reserved: it selects the TFIDF scorer (b != 0: normalised) -- sdbg_tfidf_topk_batch is the named entry. */
 int sdbg_bm25_topk_batch(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25_term* terms,
                          const uint32_t* term_off, size_t n_queries, float k1, float b, const sdbg_col_pred* filt,
                          uint32_t k, float threshold_in, sdbg_hit* out, uint32_t* n_out,
                          uint64_t* total_matches);
+/* TFIDF (irs::TFIDF, search/tfidf.cpp): statistics (:149-150; only .idf and .boost of the term are used) and the same
+ * batched scan scored with sqrt(freq) * boost * idf [/ sqrt(doc length) when normalize] (:59-80). Always exhaustive. */
+int sdbg_tfidf_collect(uint64_t docs_with_field, uint64_t docs_with_term, sdbg_bm25_term* out);
+int sdbg_tfidf_topk_batch(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25_term* terms,
+                          const uint32_t* term_off, size_t n_queries, int normalize, const sdbg_col_pred* filt, uint32_t k,
+                          float threshold_in, sdbg_hit* out, uint32_t* n_out, uint64_t* total_matches);
 /* Multi-GPU: leave each query's top-k on the device as sortable 64-bit keys + a base ordinal so a
  * collective can gather them; merge gathered keys from `n_ranks` ranks. */
 int sdbg_bm25_topk_batch_device(sdbg_segment* const* segs, size_t n_segs, int kind,

@@ -616,10 +616,14 @@ void bm25_collect(uint64_t docs_with_field, uint64_t total_term_freq, uint64_t d
     st->norm_length = kb;
   }
 }
-inline float bm25_num(float k, float boost, float idf) { return boost * (k + 1) * idf; }  // :224
+// TFIDF is selected with the sentinel k1 = -1 (b != 0: normalised by sqrt(doc length), b == 0: not): its scorer has no k / b.
+inline float bm25_num(float k, float boost, float idf) { return k == -1.f ? boost * idf : boost * (k + 1) * idf; }  // bm25.cpp:224; tfidf.cpp:101 (idf{boost * idf.value})
 // The scoring form BM25::PrepareScorer picks (bm25.cpp:312-365): k == 0 -> Bm1Score, b == 0 -> Bm15Score, else Bm25Score.
-enum ScoreForm { kFormBm25 = 0, kFormBm15 = 1, kFormBm1 = 2 };
-inline int score_form(float k, float b) { return k == 0.f ? kFormBm1 : b == 0.f ? kFormBm15 : kFormBm25; }
+enum ScoreForm { kFormBm25 = 0, kFormBm15 = 1, kFormBm1 = 2, kFormTfidf = 3, kFormTfidfNorm = 4 };
+inline int score_form(float k, float b) {
+  if (k == -1.f) return b == 0.f ? kFormTfidf : kFormTfidfNorm;
+  return k == 0.f ? kFormBm1 : b == 0.f ? kFormBm15 : kFormBm25;
+}
 // Bm25<MergeType,false> :90-107; Bm15<MergeType,false> :70-87 (c1 = norm_const = k, norms unused);
 // Bm1Score without a filter boost zero-fills (:118-126).
 // g_contract: the reference is built with clang (-ffp-contract=on is clang's default for C++) for haswell, which has FMA
@@ -633,6 +637,9 @@ int g_contract = 0;
 inline float bm25_one(uint32_t freq, uint32_t norm, float c0, float norm_const, float norm_length, int form = kFormBm25) {
   if (form == kFormBm1) return 0.f;
   if (form == kFormBm15) return c0 - c0 / (1.f + float(freq) / norm_const);
+  // TfIdf<MergeType, HasNorm, false> (search/tfidf.cpp:59-80): sqrt(freq) * idf, divided by sqrt(norm) when normalised
+  if (form == kFormTfidf) return std::sqrt(float(freq)) * c0;
+  if (form == kFormTfidfNorm) return std::sqrt(float(freq)) * c0 / std::sqrt(float(norm));
   const float c1 = g_contract ? std::fmaf(norm_length, float(norm), norm_const) : norm_const + norm_length * float(norm);
   return c0 - c0 * c1 / (c1 + float(freq));
 }
@@ -1323,6 +1330,11 @@ int orc_filter_groupby(orc_segment* const* segs, size_t n_segs, const orc_pred* 
 // Deterministic synthetic inputs. splitmix64 finaliser over seed ^ (stream<<48) ^ index.
 // ==========================================================================================
 void orc_set_contract(int on) { g_contract = on ? 1 : 0; }
+
+// TFIDF::collect (search/tfidf.cpp:149-150): idf = (float) log1p((docs_with_field + 1.0) / (docs_with_term + 1.0))
+float orc_tfidf_idf(uint64_t docs_with_field, uint64_t docs_with_term) {
+  return static_cast<float>(std::log1p((double(docs_with_field) + 1.0) / (double(docs_with_term) + 1.0)));
+}
 
 uint64_t orc_synth_hash(uint64_t stream, uint64_t index) {
   uint64_t z = (UINT64_C(0x5EDB2026) ^ (stream << 48) ^ index) + UINT64_C(0x9E3779B97F4A7C15);

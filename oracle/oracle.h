@@ -160,6 +160,8 @@ int orc_filter_groupby(orc_segment* const* segs, size_t n_segs, const orc_pred* 
 /* 1: evaluate c1 = norm_const + norm_length * norm of the BM25 form as one fused multiply-add (what a clang -mfma
    build of bm25.cpp:105 does); 0 (default): the source order without contraction. Test-only switch. */
 void orc_set_contract(int on);
+/* TFIDF statistics (search/tfidf.cpp:149-150). The top-k entry points select TFIDF with k1 = -1 (b != 0: normalised). */
+float orc_tfidf_idf(uint64_t docs_with_field, uint64_t docs_with_term);
 uint64_t orc_synth_hash(uint64_t stream, uint64_t index);
 /* kind: 0 k=h%100000, 1 a=h%1e6, 2 b in [0,1), 3 v=(h%2001)-1000, 4 w in [0,1000), 5.. raw int64 */
 void orc_synth_column(uint64_t stream, int kind, uint64_t row0, uint64_t rows, void* out);

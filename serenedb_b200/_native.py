@@ -71,6 +71,8 @@ SIGNATURES = {
     "sdbg_stage_docs_mask": (C.c_int, [_vp, _vp, _sz]),
     "sdbg_segment_set_wand_b": (C.c_int, [_vp, C.c_float]),
     "sdbg_segment_context": (_vp, [_vp]),
+    "sdbg_tfidf_collect": (C.c_int, [C.c_uint64, C.c_uint64, _vp]),
+    "sdbg_tfidf_topk_batch": (C.c_int, [_vp, _sz, C.c_int, _vp, _vp, _sz, C.c_int, _vp, C.c_uint32, C.c_float, _vp, _vp, _vp]),
     "sdbg_scan_stats": (C.c_int, [_vp, _u64p, _u64p]),
     "sdbg_dist_unique_id": (C.c_int, [_vp]),
     "sdbg_dist_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),

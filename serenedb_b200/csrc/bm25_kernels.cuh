@@ -192,6 +192,13 @@ __device__ __forceinline__ uint32_t load_norm(const uint8_t* norms, uint32_t wid
 // the BM15 form (b == 0, bm25.cpp:70-87: c0 - c0 / (1 + freq / c1) with c1 = k, norms unused); the test is
 // uniform per posting list. BM1 (k == 0) arrives as c0 == 0 and scores 0 through the BM25 form.
 __device__ __forceinline__ float bm25(uint32_t freq, uint32_t norm, float c0, float nc, float nl) {
+  if (nc != nc) {
+    // TFIDF (search/tfidf.cpp:59-80): a NaN norm_const is the host's marker; c0 = boost * idf, nl != 0 = normalised.
+    // sqrt(freq) * idf [/ sqrt(norm)], every operation correctly rounded like the reference's std::sqrt / * / /.
+    float r = __fmul_rn(__fsqrt_rn(static_cast<float>(freq)), c0);
+    if (nl != 0.f) r = __fdiv_rn(r, __fsqrt_rn(static_cast<float>(norm)));
+    return r;
+  }
   if (nl != nl) return __fsub_rn(c0, __fdiv_rn(c0, __fadd_rn(1.f, __fdiv_rn(static_cast<float>(freq), nc))));
   const float c1 = __fadd_rn(nc, __fmul_rn(nl, static_cast<float>(norm)));
   return __fsub_rn(c0, __fdiv_rn(__fmul_rn(c0, c1), __fadd_rn(c1, static_cast<float>(freq))));

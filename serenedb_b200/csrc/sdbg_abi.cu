@@ -554,6 +554,8 @@ int filter_view(sdbg_segment* s, const sdbg_col_pred* f, FilterDev* out) {
   return SDBG_OK;
 }
 
+constexpr float kTfidfK1 = -1.f;   // internal selector of the TFIDF scorer (it has no k / b): see sdbg_tfidf_topk_batch
+
 struct TopkPlan {
   uint32_t G, cap, k, budget;
   size_t smem;
@@ -615,14 +617,14 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
   struct WorkItem { uint32_t q, lo, len, list; uint64_t weight; uint32_t cls; };
   constexpr uint32_t kClsMerge = 2, kClsStream = 2 + kStreamMaxTerms, kClsAnd = 2 + 2 * kStreamMaxTerms, kClsSlice = kClsAnd + 1,
                      kClsLead = kClsAnd + 2, kClasses = kClsAnd + 3;
-  const bool level2 = c->wand >= 2 && kind != SDBG_QUERY_AND && k1 != 0.f && b != 0.f;
-  const bool stream_ok = env_int("SDBG_STREAM", 1) != 0 && k1 != 0.f && b != 0.f &&
+  const bool level2 = c->wand >= 2 && kind != SDBG_QUERY_AND && k1 != 0.f && k1 != kTfidfK1 && b != 0.f;
+  const bool stream_ok = env_int("SDBG_STREAM", 1) != 0 && k1 != 0.f && b != 0.f && k1 != kTfidfK1 &&
                          size_t(pl.cap) * 8 + size_t(kStreamMaxTerms) * (kLutFreqs * 1024 + kTopkWarps * kStreamTermBytes) <= 200 * 1024;
   const bool lead_ok = env_int("SDBG_STREAM_LEAD", 1) != 0;
   // The staged block-max pairs are maximisers for BM25 with the index-time b only (FreqNormProducer::CmpBm25,
   // wand_writer.hpp:142-175; the order of two pairs does not depend on k); the reference enables WAND only when
   // Scorer::equals matches (PostingsReaderImpl::WandIterator, reader.hpp:457-501). Any other b: exhaustive.
-  auto seg_wand = [&](const sdbg_segment* s) { return (c->wand && s->has_wand && k1 != 0.f && b != 0.f && b == s->wand_b) ? c->wand : 0; };
+  auto seg_wand = [&](const sdbg_segment* s) { return (c->wand && s->has_wand && k1 != 0.f && k1 != kTfidfK1 && b != 0.f && b == s->wand_b) ? c->wand : 0; };
   std::vector<std::array<size_t, kClasses>> n_cls(n_segs);
   for (auto& a : n_cls) a.fill(0);
   std::vector<std::vector<WorkItem>> seg_work(n_segs);
@@ -732,7 +734,12 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
         d.nblk = s->term_blk_begin[t.term + 1] - d.blk_begin;
         d.c0 = t.boost * (k1 + 1) * t.idf;  // bm25.cpp:224
         d.norm_const = t.norm_const; d.norm_length = t.norm_length;
-        if (k1 == 0.f) d.c0 = 0.f;                                            // BM1: Bm1Score without a filter boost scores 0 (bm25.cpp:118-126)
+        if (k1 == kTfidfK1) {                                                  // TFIDF (tfidf.cpp:59-80, 101): c0 = boost * idf
+          d.c0 = t.boost * t.idf;
+          d.norm_const = std::numeric_limits<float>::quiet_NaN();               // device-side marker, see bm25()
+          d.norm_length = b != 0.f ? 1.f : 0.f;                                 // normalised by sqrt(doc length) or not
+        }
+        else if (k1 == 0.f) d.c0 = 0.f;                                       // BM1: Bm1Score without a filter boost scores 0 (bm25.cpp:118-126)
         else if (b == 0.f) d.norm_length = std::numeric_limits<float>::quiet_NaN();   // BM15 form (device-side marker, see bm25())
         d.docs_count = s->term_docs[t.term];
         d.root_freq = s->term_max[t.term].freq & 0x7FFFFFFFu; d.root_norm = s->term_max[t.term].norm;
@@ -949,6 +956,26 @@ extern "C" int sdbg_bm25_collect(uint64_t docs_with_field, uint64_t total_term_f
   }
   out->boost = 1.f;
   return SDBG_OK;
+}
+
+// TFIDF (search/tfidf.cpp): idf = (float) log1p((docs_with_field + 1.0) / (docs_with_term + 1.0)), :149-150.
+extern "C" int sdbg_tfidf_collect(uint64_t docs_with_field, uint64_t docs_with_term, sdbg_bm25_term* out) {
+  if (!out) return SDBG_EINVAL;
+  out->idf = float(std::log1p((double(docs_with_field) + 1.0) / (double(docs_with_term) + 1.0)));
+  out->norm_const = 0.f; out->norm_length = 0.f; out->boost = 1.f;
+  return SDBG_OK;
+}
+
+extern "C" int sdbg_bm25_topk_batch(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25_term* terms,
+                                    const uint32_t* term_off, size_t nq, float k1, float b, const sdbg_col_pred* filt,
+                                    uint32_t k, float threshold_in, sdbg_hit* out, uint32_t* n_out, uint64_t* total_matches);
+// Same scan, scored with TFIDF: sqrt(freq) * boost * idf, divided by sqrt(doc length) when `normalize` (tfidf.cpp:59-80).
+// Exhaustive (the segment's block-max entries belong to BM25).
+extern "C" int sdbg_tfidf_topk_batch(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25_term* terms,
+                                     const uint32_t* term_off, size_t nq, int normalize, const sdbg_col_pred* filt, uint32_t k,
+                                     float threshold_in, sdbg_hit* out, uint32_t* n_out, uint64_t* total_matches) {
+  return sdbg_bm25_topk_batch(segs, n_segs, kind, terms, term_off, nq, kTfidfK1, normalize ? 1.f : 0.f, filt, k, threshold_in, out, n_out,
+                              total_matches);
 }
 
 extern "C" int sdbg_bm25_topk_batch(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25_term* terms,

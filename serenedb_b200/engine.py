@@ -345,6 +345,26 @@ class BM25:
         return np.float32(np.float32(np.float32(term.boost) * np.float32(self.k + np.float32(1))) * np.float32(term.idf))
 
 
+class TFIDF:
+    """irs::TFIDF (search/tfidf.cpp): sqrt(freq) * boost * idf, divided by sqrt(doc length) when `normalize`; idf from
+    TFIDF::collect (:149-150). Runs through the same scan entry points: k = -1 is the ABI's reserved selector for it
+    (sdbg_tfidf_topk_batch forwards exactly that), b != 0 means normalised. Always exhaustive."""
+
+    def __init__(self, normalize=False):
+        self.normalize = bool(normalize)
+        self.k, self.b = -1.0, (1.0 if normalize else 0.0)
+
+    def collect(self, docs_with_field, total_term_freq, docs_with_term, term=0, boost=1.0):
+        t = N.BM25Term()
+        N.check(N.lib().sdbg_tfidf_collect(int(docs_with_field), int(docs_with_term), C.byref(t)))
+        t.term = int(term)
+        t.boost = float(boost)
+        return t
+
+    def num(self, term):
+        return np.float32(np.float32(term.boost) * np.float32(term.idf))
+
+
 class IndexReader:
     """The segments of one snapshot on one GPU plus corpus-wide field statistics
     (FieldCollector / TermCollector sums over all segments, search/collectors.cpp:30-52)."""

@@ -132,6 +132,8 @@ def lib():
                                        C.POINTER(C.c_double)]
     L.orc_filter_groupby.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64,
                                      C.c_int, vp, C.c_uint64, u64p]
+    L.orc_tfidf_idf.argtypes = [C.c_uint64, C.c_uint64]
+    L.orc_tfidf_idf.restype = C.c_float
     L.orc_set_contract.argtypes = [C.c_int]
     L.orc_set_contract.restype = None
     L.orc_synth_hash.argtypes = [C.c_uint64, C.c_uint64]
@@ -193,6 +195,10 @@ def bm25_stats(docs_with_field, total_term_freq, docs_with_term, k=1.2, b=0.75):
     st = BM25Stats()
     lib().orc_bm25_collect(docs_with_field, total_term_freq, docs_with_term, k, b, C.byref(st))
     return st
+
+
+def tfidf_idf(docs_with_field, docs_with_term):
+    return float(lib().orc_tfidf_idf(int(docs_with_field), int(docs_with_term)))
 
 
 def set_contract(on):

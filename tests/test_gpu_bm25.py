@@ -299,3 +299,33 @@ def test_docs_mask(corpus):
         corpus["gseg"].stage_docs_mask(None)
     hits, total = sdb.ExecuteTopK(corpus["reader"], [3], sdb.OR, scorer, 10)
     assert total == len(corpus["lists"][3][0])
+
+
+@pytest.mark.parametrize("normalize", [False, True])
+@pytest.mark.parametrize("kind,tis,k", [("OR", [3, 5], 100), ("OR", [0], 50), ("AND", [0, 1, 4], 100), ("OR", [2, 6, 7, 8], 200)])
+def test_tfidf_scorer(corpus, normalize, kind, tis, k):
+    """irs::TFIDF (search/tfidf.cpp:59-80, 149-150) on the same scan: sqrt(freq) * idf [/ sqrt(doc length)], bit-exact
+    against the oracle's restatement (no sqllogic value in the reference tree pins TFIDF: restated, no golden)."""
+    scorer = sdb.TFIDF(normalize=normalize)
+    hits, total = sdb.ExecuteTopK(corpus["reader"], tis, sdb.AND if kind == "AND" else sdb.OR, scorer, k)
+    terms = []
+    for t in tis:
+        x = orc.BM25Term()
+        x.idf = orc.tfidf_idf(corpus["reader"].docs_with_field, int(corpus["reader"].docs_with_term[t]))
+        x.norm_const, x.norm_length, x.boost, x.term = 0.0, 0.0, 1.0, t
+        terms.append(x)
+    oh, ototal, _ = orc.bm25_topk([corpus["oseg"]], kind, terms, k, k1=-1.0, b=1.0 if normalize else 0.0, mode=1)
+    assert_hits_equal(hits, oh)
+    assert total == ototal
+    # spot value: the top hit's score recomputed in float32 with numpy (sqrt, *, / are all correctly rounded)
+    d0 = int(oh["doc"][0])
+    s = np.float32(0)
+    for t, x in sorted(zip(tis, terms), key=lambda p: len(corpus["lists"][p[0]][0])):
+        docs, freqs = corpus["lists"][t]
+        i = np.searchsorted(docs, d0)
+        if i < len(docs) and docs[i] == d0:
+            v = np.float32(np.sqrt(np.float32(freqs[i]))) * np.float32(x.idf)
+            if normalize:
+                v = np.float32(v / np.float32(np.sqrt(np.float32(corpus["dl"][d0 - 1]))))
+            s = np.float32(s + v)
+    assert s == oh["score"][0]
