@@ -173,6 +173,14 @@ int sdbg_tfidf_collect(uint64_t docs_with_field, uint64_t docs_with_term, sdbg_b
 int sdbg_tfidf_topk_batch(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25_term* terms,
                           const uint32_t* term_off, size_t n_queries, int normalize, const sdbg_col_pred* filt, uint32_t k,
                           float threshold_in, sdbg_hit* out, uint32_t* n_out, uint64_t* total_matches);
+/* Streaming mode of the search scan (server/connector/duckdb_search_full_scan.cpp:2370-2403 RunStreamingScan, which
+ * drains DocIterator::EmitScoredDocs, iterators.hpp:202-204): EVERY match of one query in docs [doc_min, doc_max) of
+ * one segment with its BM25 score, ascending by doc id. Disjunctions of 1..4 terms, conjunctions of 1..16, hybrid
+ * filter and deleted-doc mask honoured. *n_out = number of matches; SDBG_ECAPACITY when cap is too small (*n_out then
+ * says how much room is needed; cap = 0 with NULL outputs is the count-only form). */
+int sdbg_bm25_scan(sdbg_segment*, int kind, const sdbg_bm25_term* terms, size_t n_terms, float k1, float b,
+                   const sdbg_col_pred* filt, uint32_t doc_min, uint32_t doc_max, uint32_t* out_docs, float* out_scores,
+                   uint64_t cap, uint64_t* n_out);
 /* Multi-GPU: leave each query's top-k on the device as sortable 64-bit keys + a base ordinal so a
  * collective can gather them; merge gathered keys from `n_ranks` ranks. */
 int sdbg_bm25_topk_batch_device(sdbg_segment* const* segs, size_t n_segs, int kind,

@@ -87,6 +87,8 @@ SIGNATURES = {
                                        _vp, _vp, _vp]),
     "sdbg_bm25_topk_batch_device": (C.c_int, [_vp, _sz, C.c_int, _vp, _vp, _sz, C.c_float, C.c_float, _vp, C.c_uint32,
                                               C.c_float, C.c_uint32, _vp, _vp]),
+    "sdbg_bm25_scan": (C.c_int, [_vp, C.c_int, _vp, _sz, C.c_float, C.c_float, _vp, C.c_uint32, C.c_uint32, _vp, _vp, C.c_uint64,
+                                 _u64p]),
     "sdbg_topk_merge_gathered": (C.c_int, [_vp, _vp, C.c_uint32, _sz, C.c_uint32, _vp, _vp]),
     "sdbg_decode_score_term": (C.c_int, [_vp, C.c_uint32, C.c_float, C.c_float, C.c_float, _vp, _vp, _vp]),
     "sdbg_filter_bitmap": (C.c_int, [_vp, _vp, _sz, _vp]),

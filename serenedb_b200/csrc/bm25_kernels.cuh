@@ -301,6 +301,13 @@ struct TopkParams {
   // first CTA to arrive looks at the query's threshold, decides, and records 1 = merge / 2 = lead here; the other
   // one reads the verdict and exits.
   uint32_t* claim;
+  // Scored scan (the reference's streaming mode, duckdb_search_full_scan.cpp RunStreamingScan): when emit_docs is set the
+  // stream kernel writes EVERY match (segment-local doc, score) through a global cursor instead of keeping a top-k;
+  // emit_count keeps counting past emit_cap so that the host can report the room needed.
+  uint32_t* emit_docs = nullptr;
+  float* emit_scores = nullptr;
+  unsigned long long* emit_count = nullptr;
+  unsigned long long emit_cap = 0;
   uint32_t k;
   uint32_t cap;                // candidate buffer capacity, power of two, > k
   int32_t conjunction;         // 0 OR, 1 AND

@@ -66,6 +66,19 @@ __device__ __forceinline__ void unpack4s(const uint4* p, uint32_t b, uint32_t la
 }
 
 // StreamVByte 1234 from shared memory (tails only): control byte `lane` describes this lane's four values.
+// Scored scan: every match goes out through a global cursor, one atomic per warp.
+__device__ __noinline__ void stream_emit(uint32_t* docs, float* scores, unsigned long long* count, unsigned long long cap,
+                                         bool alive, uint32_t dv, float sv) {
+  const uint32_t bal = __ballot_sync(kFull, alive);
+  if (!bal) return;
+  const uint32_t lane = threadIdx.x & 31u;
+  unsigned long long base = 0ull;
+  if (lane == uint32_t(__ffs(int(bal)) - 1)) base = atomicAdd(count, static_cast<unsigned long long>(__popc(bal)));
+  base = __shfl_sync(kFull, base, __ffs(int(bal)) - 1);
+  const unsigned long long pos = base + __popc(bal & ((1u << lane) - 1u));
+  if (alive && pos < cap) { docs[pos] = dv; scores[pos] = sv; }
+}
+
 __device__ __noinline__ void svb4s(const uint4* p, uint32_t len, uint32_t lane, uint32_t* v_out /* shared: 128 u32 */) {
   const uint8_t* bytes = reinterpret_cast<const uint8_t*>(p);
   const uint32_t nctl = (len + 3u) >> 2;
@@ -492,6 +505,7 @@ bm25_stream_kernel(const __grid_constant__ TopkParams P) {
       return filter_pass(P.filt, d);
     };
     auto test_and_append = [&](bool alive, uint32_t dv, float sv) {
+      if (P.emit_docs != nullptr) { stream_emit(P.emit_docs, P.emit_scores, P.emit_count, P.emit_cap, alive, dv, sv); return; }
       bool want = alive && __float_as_uint(sv) >= theta_hi;
       if (__any_sync(kFull, want)) {
         unsigned long long key = 0ull;

@@ -2,6 +2,7 @@
 // preparation and kernel launches. Host code only orchestrates; all per-posting / per-row work is
 // in bm25_kernels.cuh and column_kernels.cuh. There is no CPU fallback anywhere in this file.
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 #include <dlfcn.h>
 #include <nccl.h>   // types only: the library is resolved at run time (sdbg_dist_init)
 
@@ -68,6 +69,7 @@ struct sdbg_ctx {
   size_t h_pinned_cap = 0;
   void* flush = nullptr;
   size_t flush_bytes = 0;
+  bool scan_attr_set = false;
   bool topk_attr_set = false;
   void* nccl_comm = nullptr;   // ncclComm_t once sdbg_dist_init ran
   unsigned long long* h_oor = nullptr;   // pinned: out-of-range key count of the last deferred GROUP BY partial
@@ -556,6 +558,24 @@ int filter_view(sdbg_segment* s, const sdbg_col_pred* f, FilterDev* out) {
 
 constexpr float kTfidfK1 = -1.f;   // internal selector of the TFIDF scorer (it has no k / b): see sdbg_tfidf_topk_batch
 
+// Device-side descriptor of one query term over one segment (the caller has checked the term id).
+void fill_qterm(const sdbg_segment* s, const sdbg_bm25_term& t, float k1, float b, QTermDev& d) {
+  d.blk_begin = s->term_blk_begin[t.term];
+  d.nblk = s->term_blk_begin[t.term + 1] - d.blk_begin;
+  d.c0 = t.boost * (k1 + 1) * t.idf;  // bm25.cpp:224
+  d.norm_const = t.norm_const; d.norm_length = t.norm_length;
+  if (k1 == kTfidfK1) {                                                  // TFIDF (tfidf.cpp:59-80, 101): c0 = boost * idf
+    d.c0 = t.boost * t.idf;
+    d.norm_const = std::numeric_limits<float>::quiet_NaN();               // device-side marker, see bm25()
+    d.norm_length = b != 0.f ? 1.f : 0.f;                                 // normalised by sqrt(doc length) or not
+  }
+  else if (k1 == 0.f) d.c0 = 0.f;                                       // BM1: Bm1Score without a filter boost scores 0 (bm25.cpp:118-126)
+  else if (b == 0.f) d.norm_length = std::numeric_limits<float>::quiet_NaN();   // BM15 form (device-side marker, see bm25())
+  d.docs_count = s->term_docs[t.term];
+  d.root_freq = s->term_max[t.term].freq & 0x7FFFFFFFu; d.root_norm = s->term_max[t.term].norm;
+  if (t.term < s->term_probe.size() && s->term_probe[t.term]) d.root_freq |= 0x80000000u;   // probe-friendly list (driver mode)
+}
+
 struct TopkPlan {
   uint32_t G, cap, k, budget;
   size_t smem;
@@ -729,21 +749,7 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
       for (uint32_t i = t_begin; i < t_end; ++i) {
         const sdbg_bm25_term& t = terms[i];
         if (t.term + 1 >= s->term_blk_begin.size()) return fail(c, SDBG_EINVAL, "term id out of range");
-        QTermDev& d = dst[i];
-        d.blk_begin = s->term_blk_begin[t.term];
-        d.nblk = s->term_blk_begin[t.term + 1] - d.blk_begin;
-        d.c0 = t.boost * (k1 + 1) * t.idf;  // bm25.cpp:224
-        d.norm_const = t.norm_const; d.norm_length = t.norm_length;
-        if (k1 == kTfidfK1) {                                                  // TFIDF (tfidf.cpp:59-80, 101): c0 = boost * idf
-          d.c0 = t.boost * t.idf;
-          d.norm_const = std::numeric_limits<float>::quiet_NaN();               // device-side marker, see bm25()
-          d.norm_length = b != 0.f ? 1.f : 0.f;                                 // normalised by sqrt(doc length) or not
-        }
-        else if (k1 == 0.f) d.c0 = 0.f;                                       // BM1: Bm1Score without a filter boost scores 0 (bm25.cpp:118-126)
-        else if (b == 0.f) d.norm_length = std::numeric_limits<float>::quiet_NaN();   // BM15 form (device-side marker, see bm25())
-        d.docs_count = s->term_docs[t.term];
-        d.root_freq = s->term_max[t.term].freq & 0x7FFFFFFFu; d.root_norm = s->term_max[t.term].norm;
-        if (t.term < s->term_probe.size() && s->term_probe[t.term]) d.root_freq |= 0x80000000u;   // probe-friendly list (driver mode)
+        fill_qterm(s, t, k1, b, dst[i]);
       }
       std::stable_sort(dst + t_begin, dst + t_end, [](const QTermDev& x, const QTermDev& y) { return x.docs_count < y.docs_count; });
     }
@@ -1017,6 +1023,131 @@ extern "C" int sdbg_bm25_topk_batch(sdbg_segment* const* segs, size_t n_segs, in
     for (size_t t = 0; t < n_thr; ++t) pool.emplace_back(convert, nq * t / n_thr, nq * (t + 1) / n_thr);
     for (auto& th : pool) th.join();
   }
+  return SDBG_OK;
+}
+
+// Streaming mode (duckdb_search_full_scan.cpp RunStreamingScan :2370-2403; DocIterator::EmitScoredDocs,
+// iterators.hpp:202-204): every match of one query in docs [doc_min, doc_max) of one segment with its score, ascending
+// by doc. Same stream kernel as the top-k scan with pruning off; its sink writes through a global cursor and the
+// pairs are then radix-sorted by doc id on the device.
+extern "C" int sdbg_bm25_scan(sdbg_segment* s, int kind, const sdbg_bm25_term* terms, size_t n_terms, float k1, float b,
+                              const sdbg_col_pred* filt, uint32_t doc_min, uint32_t doc_max, uint32_t* out_docs, float* out_scores,
+                              uint64_t cap, uint64_t* n_out) {
+  if (!s || !terms || !n_terms || !n_out || (cap && (!out_docs || !out_scores))) return SDBG_EINVAL;
+  sdbg_ctx* c = s->ctx;
+  CU(c, cudaSetDevice(c->device));
+  if (!s->d_blocks) return fail(c, SDBG_EINVAL, "segment has no staged postings");
+  const bool conj = kind == SDBG_QUERY_AND;
+  if (n_terms > (conj ? size_t(kMaxQueryTerms) : size_t(kStreamMaxTerms)))
+    return fail(c, SDBG_EUNSUPPORTED, "scored scan: disjunctions take 1..4 terms, conjunctions 1..16");
+  if (k1 == 0.f || b == 0.f || k1 == kTfidfK1) return fail(c, SDBG_EUNSUPPORTED, "scored scan: BM25 form only");
+  *n_out = 0;
+  doc_min = std::max(doc_min, 1u);                                   // doc ids start at doc_limits::min()
+  doc_max = uint32_t(std::min<uint64_t>(doc_max, uint64_t(s->n_docs) + 1u));
+  if (doc_min >= doc_max) return SDBG_OK;
+  const uint32_t range = doc_max - doc_min;
+  const uint32_t T = uint32_t(n_terms);
+  const uint32_t scan_cap = 1024;                                    // candidate buffer of the kernel: unused here, kept minimal
+  const uint32_t g = std::max(1u, std::min(uint32_t(c->sm_count) * 3u, range / 4096u));
+  const uint32_t chunk = (range + g - 1) / g;
+  // descriptors: [QTermDev x T][term_off x 2][pad][work x g]
+  const size_t qt_bytes = size_t(T) * sizeof(QTermDev), off_bytes = 2 * sizeof(uint32_t);
+  const size_t qt_pad = (qt_bytes + off_bytes + 15) & ~size_t(15), work_bytes = size_t(g) * sizeof(uint4);
+  int rc = ensure_pinned(c, qt_pad + work_bytes);
+  if (rc) return rc;
+  auto* h_qt = static_cast<QTermDev*>(c->h_pinned);
+  for (uint32_t i = 0; i < T; ++i) {
+    if (terms[i].term + 1 >= s->term_blk_begin.size()) return fail(c, SDBG_EINVAL, "term id out of range");
+    fill_qterm(s, terms[i], k1, b, h_qt[i]);
+  }
+  std::stable_sort(h_qt, h_qt + T, [](const QTermDev& x, const QTermDev& y) { return x.docs_count < y.docs_count; });
+  auto* h_off = reinterpret_cast<uint32_t*>(static_cast<char*>(c->h_pinned) + qt_bytes);
+  h_off[0] = 0; h_off[1] = T;
+  auto* h_work = reinterpret_cast<uint4*>(static_cast<char*>(c->h_pinned) + qt_pad);
+  for (uint32_t j = 0; j < g; ++j) {
+    const uint32_t lo = doc_min + j * chunk;
+    h_work[j] = make_uint4(0u, lo, lo < doc_max ? std::min(chunk, doc_max - lo) : 0u, j);
+    if (lo >= doc_max) h_work[j].y = s->n_docs + 1u;               // empty chain
+  }
+  DevBuf& b_qt = c->scratch[0]; DevBuf& b_theta = c->scratch[1]; DevBuf& b_cand = c->scratch[2]; DevBuf& b_candn = c->scratch[3];
+  DevBuf& b_emit = c->scratch[12];
+  const uint64_t room = std::max<uint64_t>(cap, 1);
+  size_t sort_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, static_cast<const uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr),
+                                  static_cast<const float*>(nullptr), static_cast<float*>(nullptr), room, 0, 32, c->stream);
+  const size_t pair_bytes = (size_t(room) * 4 + 255) & ~size_t(255);
+  if ((rc = ensure(c, b_qt, qt_pad + work_bytes))) return rc;
+  if ((rc = ensure(c, b_theta, 32))) return rc;                      // theta | total | cursor
+  if ((rc = ensure(c, b_cand, size_t(g) * scan_cap * 8))) return rc;
+  if ((rc = ensure(c, b_candn, size_t(g) * 4))) return rc;
+  if ((rc = ensure(c, b_emit, 4 * pair_bytes + sort_bytes))) return rc;
+  CU(c, cudaMemcpyAsync(b_qt.p, c->h_pinned, qt_pad + work_bytes, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemsetAsync(b_theta.p, 0, 32, c->stream));
+  TopkParams P;
+  P.seg = postings_view(s, 0);
+  if ((rc = filter_view(s, filt, &P.filt))) return rc;
+  P.qterms = static_cast<const QTermDev*>(b_qt.p);
+  P.qterm_off = reinterpret_cast<const uint32_t*>(static_cast<const char*>(b_qt.p) + qt_bytes);
+  P.work = reinterpret_cast<const uint4*>(static_cast<const char*>(b_qt.p) + qt_pad);
+  P.theta = static_cast<unsigned long long*>(b_theta.p);
+  P.total = P.theta + 1;
+  P.emit_count = P.theta + 2;
+  P.cand = static_cast<unsigned long long*>(b_cand.p);
+  P.cand_n = static_cast<uint32_t*>(b_candn.p);
+  P.claim = nullptr;
+  P.k = 1; P.cap = scan_cap; P.conjunction = conj ? 1 : 0; P.wand = 0;
+  char* e = static_cast<char*>(b_emit.p);
+  P.emit_docs = reinterpret_cast<uint32_t*>(e);
+  P.emit_scores = reinterpret_cast<float*>(e + pair_bytes);
+  P.emit_cap = cap;
+  auto* sorted_docs = reinterpret_cast<uint32_t*>(e + 2 * pair_bytes);
+  auto* sorted_scores = reinterpret_cast<float*>(e + 3 * pair_bytes);
+  const bool lut = s->norm_width == 1 && env_int("SDBG_STREAM_LUT", 1) != 0;
+  const uint32_t Tl = conj ? 1u : T;
+  const size_t sm = size_t(scan_cap) * 8 + (lut ? size_t(Tl) * kLutFreqs * 1024 : 0) + size_t(kTopkWarps) * (Tl * kStreamTermBytes + (conj ? 1024 : 0));
+  if (!c->scan_attr_set) {
+#define SDBG_SCAN_ATTR(TT) \
+    CU(c, cudaFuncSetAttribute(bm25_stream_kernel<TT, false, 3, kModeOr>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+    CU(c, cudaFuncSetAttribute(bm25_stream_kernel<TT, true, 3, kModeOr>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))
+    SDBG_SCAN_ATTR(1); SDBG_SCAN_ATTR(2); SDBG_SCAN_ATTR(3); SDBG_SCAN_ATTR(4);
+#undef SDBG_SCAN_ATTR
+    CU(c, cudaFuncSetAttribute(bm25_stream_kernel<1, false, 3, kModeAnd>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(c, cudaFuncSetAttribute(bm25_stream_kernel<1, true, 3, kModeAnd>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    c->scan_attr_set = true;
+  }
+  {
+    ProfScope ps_(c, kProfTopk);
+    if (conj) {
+      if (lut) bm25_stream_kernel<1, true, 3, kModeAnd><<<g, kTopkThreads, sm, c->stream>>>(P);
+      else bm25_stream_kernel<1, false, 3, kModeAnd><<<g, kTopkThreads, sm, c->stream>>>(P);
+    } else {
+#define SDBG_SCAN_LAUNCH(TT) \
+      if (lut) bm25_stream_kernel<TT, true, 3, kModeOr><<<g, kTopkThreads, sm, c->stream>>>(P); \
+      else bm25_stream_kernel<TT, false, 3, kModeOr><<<g, kTopkThreads, sm, c->stream>>>(P)
+      switch (T) {
+        case 1: SDBG_SCAN_LAUNCH(1); break;
+        case 2: SDBG_SCAN_LAUNCH(2); break;
+        case 3: SDBG_SCAN_LAUNCH(3); break;
+        default: SDBG_SCAN_LAUNCH(4); break;
+      }
+#undef SDBG_SCAN_LAUNCH
+    }
+  }
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  unsigned long long found = 0;
+  CU(c, cudaMemcpyAsync(&found, P.emit_count, 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  *n_out = found;
+  if (found > cap) return fail(c, SDBG_ECAPACITY, "scored scan: more matches than the output has room for (*n_out = needed)");
+  if (!found) return SDBG_OK;
+  cub::DeviceRadixSort::SortPairs(e + 4 * pair_bytes, sort_bytes, P.emit_docs, sorted_docs, P.emit_scores, sorted_scores, found, 0, 32,
+                                  c->stream);
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  CU(c, cudaMemcpyAsync(out_docs, sorted_docs, size_t(found) * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(out_scores, sorted_scores, size_t(found) * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
   return SDBG_OK;
 }
 

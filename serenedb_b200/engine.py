@@ -400,6 +400,32 @@ def ExecuteTopKBatch(reader, queries, kind, scorer, k, filt=None, threshold=FLT_
     return hits, n_out, total
 
 
+def StreamScoredDocs(reader, seg_idx, query, kind, scorer, filt=None, doc_min=1, doc_max=None):
+    """The search scan's streaming mode (duckdb_search_full_scan.cpp:2370 RunStreamingScan over
+    DocIterator::EmitScoredDocs): every match of `query` in docs [doc_min, doc_max) of segment `seg_idx` with its score,
+    ascending by doc id. Returns (docs u32, scores f32)."""
+    seg = reader.segments[seg_idx]
+    terms = (N.BM25Term * len(query))(*[reader.stats(scorer, t) for t in query])
+    fp = C.byref(filt) if filt is not None else None
+    hi = int(doc_max) if doc_max is not None else 0xFFFFFFFF
+    n = C.c_uint64(0)
+    cap = 0
+    docs = scores = None
+    for _ in range(2):   # count-only call first, then one with exactly the room needed
+        rc = N.lib().sdbg_bm25_scan(seg._h, int(kind), terms, len(query), scorer.k, scorer.b, fp, int(doc_min), hi,
+                                    _ptr(docs) if docs is not None else None, _ptr(scores) if scores is not None else None,
+                                    cap, C.byref(n))
+        if rc == -6 and n.value > cap:
+            cap = n.value
+            docs, scores = np.zeros(cap, np.uint32), np.zeros(cap, np.float32)
+            continue
+        N.check(rc, seg.ctx._h)
+        break
+    if docs is None:
+        return np.zeros(0, np.uint32), np.zeros(0, np.float32)
+    return docs[:n.value], scores[:n.value]
+
+
 def _flatten_queries(reader, queries, scorer):
     flat = [reader.stats(scorer, t) for q in queries for t in q]
     terms = (N.BM25Term * max(len(flat), 1))()

@@ -329,3 +329,54 @@ def test_tfidf_scorer(corpus, normalize, kind, tis, k):
                 v = np.float32(v / np.float32(np.sqrt(np.float32(corpus["dl"][d0 - 1]))))
             s = np.float32(s + v)
     assert s == oh["score"][0]
+
+
+STREAM_QUERIES = [("OR", [3]), ("OR", [0, 4]), ("OR", [2, 5, 6]), ("OR", [0, 1, 2, 3]), ("AND", [0, 1, 2]), ("AND", [0, 8]),
+                  ("AND", [0, 1, 2, 3, 4]), ("OR", [8])]
+
+
+@pytest.mark.parametrize("kind,tis", STREAM_QUERIES)
+def test_stream_scored_docs(corpus, kind, tis):
+    """Streaming mode (RunStreamingScan / EmitScoredDocs): every match with its score, ascending by doc, equals the
+    oracle's exhaustive result re-sorted by doc -- bit-exact; doc windows partition the stream."""
+    scorer = sdb.BM25()
+    knd = sdb.AND if kind == "AND" else sdb.OR
+    docs, scores = sdb.StreamScoredDocs(corpus["reader"], 0, tis, knd, scorer)
+    oh, ototal, _ = orc.bm25_topk([corpus["oseg"]], kind, oracle_terms(corpus["reader"], scorer, tis), corpus["n"], mode=0)
+    order = np.argsort(oh["doc"], kind="stable")
+    assert len(docs) == ototal == len(oh)
+    assert np.array_equal(docs, oh["doc"][order])
+    assert np.array_equal(scores.view(np.uint32), oh["score"][order].view(np.uint32))
+    assert np.all(np.diff(docs.astype(np.int64)) > 0)
+    # chunked like the scan's EmitChunk windows: [1, a) + [a, b) + [b, end) == the whole stream
+    a, b = 77_777, 200_001
+    parts = [sdb.StreamScoredDocs(corpus["reader"], 0, tis, knd, scorer, doc_min=lo, doc_max=hi) for lo, hi in ((1, a), (a, b), (b, None))]
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), docs)
+    assert np.array_equal(np.concatenate([p[1] for p in parts]).view(np.uint32), scores.view(np.uint32))
+
+
+def test_stream_scored_docs_filter_and_mask(corpus):
+    scorer = sdb.BM25()
+    n = corpus["n"]
+    deleted = np.unique(np.random.default_rng(5).integers(1, n + 1, size=n // 5)).astype(np.uint32)
+    corpus["oseg"].set_docs_mask(deleted)
+    corpus["gseg"].stage_docs_mask(deleted)
+    try:
+        for kind, tis in (("OR", [0, 1]), ("AND", [0, 1, 2])):
+            docs, scores = sdb.StreamScoredDocs(corpus["reader"], 0, tis, sdb.AND if kind == "AND" else sdb.OR, scorer,
+                                                filt=sdb.pred(9, "BETWEEN", 250000, 749999))
+            oh, ototal, _ = orc.bm25_topk([corpus["oseg"]], kind, oracle_terms(corpus["reader"], scorer, tis), n,
+                                          filt=orc.make_pred(9, "BETWEEN", 250000, 749999), mode=0)
+            order = np.argsort(oh["doc"], kind="stable")
+            assert len(docs) == ototal and ototal > 0
+            assert np.array_equal(docs, oh["doc"][order])
+            assert np.array_equal(scores.view(np.uint32), oh["score"][order].view(np.uint32))
+            assert not np.isin(docs, deleted).any()
+    finally:
+        corpus["oseg"].set_docs_mask([])
+        corpus["gseg"].stage_docs_mask(None)
+    # empty window and unsupported shapes
+    d, s = sdb.StreamScoredDocs(corpus["reader"], 0, [3], sdb.OR, scorer, doc_min=50, doc_max=50)
+    assert len(d) == 0 and len(s) == 0
+    with pytest.raises(Exception, match="EUNSUPPORTED"):
+        sdb.StreamScoredDocs(corpus["reader"], 0, [0, 1, 2, 3, 4], sdb.OR, scorer)
