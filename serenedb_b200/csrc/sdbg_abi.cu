@@ -1390,6 +1390,7 @@ extern "C" int sdbg_filter_bitmap(sdbg_segment* s, const sdbg_col_pred* preds, s
   int rc = pred_set(s, preds, n_preds, &ps, &rows);
   if (rc) return rc;
   if (!rows) rows = s->n_docs;
+  if (rows > s->n_docs) return fail(c, SDBG_EINVAL, "filter column longer than the segment: mask_out holds (docs_count + 63) / 64 words");
   const size_t words = (rows + 63) / 64;
   if ((rc = ensure(c, c->scratch[9], words * 8))) return rc;
   const unsigned grid = unsigned(std::min<size_t>((words * 32 + 255) / 256, size_t(c->sm_count) * 8));
@@ -1554,11 +1555,13 @@ int groupby_launch(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred
     if (r != rows) return fail(c, SDBG_EINVAL, "key column length differs");
     if (sum_int_field != UINT64_MAX) {
       if ((rc = col_view(s, sum_int_field, &P.sum_i, &r))) return rc;
+      if (r != rows) return fail(c, SDBG_EINVAL, "sum_int column length differs");
       if (P.sum_i.type == SDBG_F64) return fail(c, SDBG_EINVAL, "sum_int_field is a float column");
       P.has_sum_i = 1;
     }
     if (avg_f64_field != UINT64_MAX) {
       if ((rc = col_view(s, avg_f64_field, &P.sum_f, &r))) return rc;
+      if (r != rows) return fail(c, SDBG_EINVAL, "avg_f64 column length differs");
       if (P.sum_f.type != SDBG_F64) return fail(c, SDBG_EINVAL, "avg_f64_field is not a float column");
       P.has_sum_f = 1;
     }
@@ -1779,9 +1782,16 @@ int groupby_hash(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred* 
       if (P.key.validity) return fail(c, SDBG_EUNSUPPORTED, "nullable GROUP BY key");
       if (P.key.type == SDBG_F64) return fail(c, SDBG_EUNSUPPORTED, "float GROUP BY key");
       if (!rows) rows = r;
-      if (sum_int_field != UINT64_MAX) { if ((rc = col_view(s, sum_int_field, &P.sum_i, &r))) return rc; P.has_sum_i = 1; }
+      if (r != rows) return fail(c, SDBG_EINVAL, "key column length differs");
+      if (sum_int_field != UINT64_MAX) {
+        if ((rc = col_view(s, sum_int_field, &P.sum_i, &r))) return rc;
+        if (r != rows) return fail(c, SDBG_EINVAL, "sum_int column length differs");
+        if (P.sum_i.type == SDBG_F64) return fail(c, SDBG_EINVAL, "sum_int_field is a float column");
+        P.has_sum_i = 1;
+      }
       if (avg_f64_field != UINT64_MAX) {
         if ((rc = col_view(s, avg_f64_field, &P.sum_f, &r))) return rc;
+        if (r != rows) return fail(c, SDBG_EINVAL, "avg_f64 column length differs");
         if (P.sum_f.type != SDBG_F64) return fail(c, SDBG_EINVAL, "avg_f64_field is not a float column");
         P.has_sum_f = 1;
       }

@@ -24,8 +24,9 @@ def global_term_stats(dist, docs_with_term, total_term_freq, docs_with_field):
 
 def merge_groupby_partials(dist, part_i64, part_f64):
     """SUM all-reduce of dense partial aggregates. part_i64 = [count | sum_lo | sum_hi | cnt_f64]
-    (4*span int64): SUM(int) travels as two limbs whose per-rank partial sums cannot overflow int64,
-    so the reduction is exact; part_f64 = float64 sums (order of addition differs from one GPU: AVG
+    (4*span int64). torch.distributed fallback of sdbg_dist_groupby_merge (the C path, which also normalises the
+    SUM(int) limbs to lo < 2^32 before the all-reduce so that no number of ranks can wrap them). Here the limbs travel
+    as the kernels left them: exact while world_size * rows_per_gpu < 2^31; part_f64 = float64 sums (order of addition differs from one GPU: AVG
     agrees to ~1e-15 relative, far inside the 1e-5 bar)."""
     if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(part_i64)

@@ -54,6 +54,22 @@ int main(int argc, char** argv) {
   std::printf("], \"total\": %llu, \"threshold\": %.9g, \"attr_threshold\": %.9g, \"attr_cost\": %llu, \"fill_bits\": %u, \"fill_sum\": %.9g, \"fill_next\": %u}\n",
               static_cast<unsigned long long>(it.total_matches()), double(it.threshold().value), double(thr ? thr->value : -1.f),
               static_cast<unsigned long long>(cost ? cost->estimate() : 0), bits, wsum, fb.first);
+  // --- streaming mode: drain EmitScoredDocs in STANDARD_VECTOR_SIZE-bounded windows like StreamScanLocalState::EmitChunk ---
+  {
+    sdbg_host::GpuTopKIterator st(seg, SDBG_QUERY_OR, terms, 1.2f, 0.75f, 0, &filt);
+    std::vector<irs::doc_id_t> d(2048);
+    std::vector<irs::score_t> sc(2048);
+    uint64_t n = 0, chunks = 0, doc_sum = 0; double score_sum = 0; bool ordered = true; irs::doc_id_t last = 0;
+    for (irs::doc_id_t lo = 1; lo <= n_docs; lo += 2048) {      // a 2048-doc window can hold at most 2048 matches
+      const uint32_t got = st.EmitScoredDocs(d.data(), sc.data(), lo + 2048, sf, &fetcher, lo);
+      if (got) ++chunks;
+      for (uint32_t i = 0; i < got; ++i) { ordered = ordered && d[i] > last; last = d[i]; doc_sum += d[i]; score_sum += sc[i]; }
+      n += got;
+    }
+    std::printf("{\"stream_n\": %llu, \"stream_chunks\": %llu, \"stream_doc_sum\": %llu, \"stream_score_sum\": %.12g, \"stream_ordered\": %d, \"stream_count\": %u}\n",
+                static_cast<unsigned long long>(n), static_cast<unsigned long long>(chunks), static_cast<unsigned long long>(doc_sum), score_sum,
+                ordered ? 1 : 0, st.count());
+  }
   // --- aggregate scan through the table-function adapter ---
   for (uint64_t f = 10; f <= 14; ++f) sdbg_synth_column(seg, f, f, int(f - 10), 0, n_docs);
   std::vector<sdbg_col_pred> preds(2);

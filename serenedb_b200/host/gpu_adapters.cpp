@@ -20,6 +20,24 @@ GpuTopKIterator::GpuTopKIterator(sdbg_segment* segment, int kind, std::vector<sd
 
 void GpuTopKIterator::run() {
   if (ran_) return;
+  if (k_ == 0) {                   // streaming mode: every match, already in doc order
+    uint64_t n = 0, cap = 0;
+    std::vector<uint32_t> docs;
+    std::vector<float> scores;
+    for (;;) {
+      const int rc = sdbg_bm25_scan(seg_, kind_, terms_.data(), terms_.size(), k1_, b_, has_filter_ ? &filter_ : nullptr, 1, UINT32_MAX,
+                                    docs.data(), scores.data(), cap, &n);
+      if (rc == SDBG_ECAPACITY && n > cap) { cap = n; docs.resize(n); scores.resize(n); continue; }   // count-only call, then one with room
+      check(rc, "sdbg_bm25_scan");
+      break;
+    }
+    by_doc_.resize(n);
+    for (uint64_t i = 0; i < n; ++i) by_doc_[i] = sdbg_hit{scores[i], docs[i], 0};
+    total_ = n;
+    cost_.reset(total_);
+    ran_ = true;
+    return;
+  }
   hits_.assign(k_, sdbg_hit{});
   uint32_t n = 0;
   float thr_out = 0;
@@ -37,6 +55,7 @@ void GpuTopKIterator::run() {
 
 void GpuTopKIterator::Collect(const irs::ScoreFunction&, irs::ColumnArgsFetcher&, irs::ScoreCollector& collector) {
   run();
+  if (k_ == 0) hits_ = by_doc_;    // a streaming iterator asked to Collect feeds everything it has
   if (hits_.empty()) { _doc = irs::doc_limits::eof(); return; }
   std::vector<irs::doc_id_t> docs(hits_.size());
   std::vector<irs::score_t> scores(hits_.size());

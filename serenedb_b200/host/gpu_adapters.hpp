@@ -34,12 +34,14 @@ class GpuTopKIterator final : public irs::DocIterator {
  public:
   GpuTopKIterator(sdbg_segment* segment, int kind /* SDBG_QUERY_OR | SDBG_QUERY_AND */,
                   std::vector<sdbg_bm25_term> terms /* BM25Stats per term + boost */, float k1 /* BM25::k() */,
-                  float b /* BM25::b() */, uint32_t k,
+                  float b /* BM25::b() */, uint32_t k /* 0 = streaming mode: every match, see EmitScoredDocs */,
                   const sdbg_col_pred* table_filter /* nullable: the ColFilter wrap */);
 
   // Scored top-k: the hot path.
   void Collect(const irs::ScoreFunction&, irs::ColumnArgsFetcher&, irs::ScoreCollector& collector) override;
-  // Windowed variant used by TableFilterDocIterator / streaming callers: hits with doc in [min, max).
+  // Windowed variant used by TableFilterDocIterator / streaming callers (RunStreamingScan,
+  // duckdb_search_full_scan.cpp:2370-2403): hits with doc in [min, max). With k = 0 the iterator holds every match
+  // of the segment (sdbg_bm25_scan), so draining it window by window is the reference's streaming scan.
   uint32_t EmitScoredDocs(irs::doc_id_t* out, irs::score_t* scores, irs::doc_id_t max, const irs::ScoreFunction&,
                           irs::ColumnArgsFetcher*, irs::doc_id_t min) override;
   uint32_t EmitDocs(irs::doc_id_t* out, irs::doc_id_t min, irs::doc_id_t max) override;

@@ -16,7 +16,7 @@ def test_adapters_match_oracle():
     n = 200_000
     res = subprocess.run([exe, str(n)], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
-    topk, agg = [json.loads(l) for l in res.stdout.strip().splitlines()]
+    topk, stream, agg = [json.loads(l) for l in res.stdout.strip().splitlines()]
     # ---- GpuTopKIterator::Collect vs oracle (2-term OR + INCLUDE-column range filter, k = 100) ----
     oseg, dc, sum_dl = orc.synth_segment_mt(n, 0, 8, threads=4)
     nn = orc.synth_column(2, 1, 1, n).astype(np.int32)
@@ -40,6 +40,14 @@ def test_adapters_match_oracle():
     assert topk["fill_bits"] == len(inwin)
     assert topk["fill_sum"] == pytest.approx(float(inwin["score"].astype(np.float64).sum()), rel=1e-6)
     assert topk["fill_next"] == (int(later.min()) if len(later) else 0xFFFFFFFF)
+    # ---- streaming mode (k = 0): EmitScoredDocs windows drain every match in doc order ----
+    allh, alltotal, _ = orc.bm25_topk([oseg], "OR", terms, n, filt=orc.make_pred(9, "BETWEEN", 250000, 749999), mode=0)
+    assert stream["stream_n"] == alltotal == len(allh) == stream["stream_count"]
+    assert stream["stream_ordered"] == 1
+    assert stream["stream_doc_sum"] == int(allh["doc"].astype(np.uint64).sum())
+    by_doc = allh[np.argsort(allh["doc"], kind="stable")]
+    assert stream["stream_score_sum"] == pytest.approx(float(by_doc["score"].astype(np.float64).sum()), rel=1e-10)
+    assert stream["stream_chunks"] == len(np.unique((by_doc["doc"] - 1) // 2048))
     # ---- GpuAggScan chunks vs oracle GROUP BY ----
     cols = {10: (10, 0), 11: (11, 1), 12: (12, 2), 13: (13, 3), 14: (14, 4)}
     for f, (stream, kind) in cols.items():
