@@ -195,6 +195,11 @@ int sdbg_topk_merge_gathered(sdbg_ctx*, const void* d_keys_all /* n_ranks*n_quer
 int sdbg_decode_score_term(sdbg_segment*, uint32_t term, float c0, float norm_const, float norm_length,
                            uint32_t* docs, uint32_t* freqs, float* scores);
 
+/* Late materialisation (HitBatcher::MaterializeColumn, irs/index/hit_batcher.hpp:39; FinalizeBatch of the search scan):
+ * out_values[i] = column[docs[i] - 1] for n hit docs of the segment (element width = the staged type's), out_valid[i]
+ * (nullable) = 0 for NULL or out-of-range rows, whose value is written as 0. */
+int sdbg_gather_column(sdbg_segment*, uint64_t field, const uint32_t* docs, size_t n, void* out_values, uint8_t* out_valid);
+
 /* ---- columnar filter / aggregate (boundary B3, iresearch_scan) ---- */
 int sdbg_filter_bitmap(sdbg_segment*, const sdbg_col_pred* preds, size_t n_preds, uint64_t* mask_out);
 int sdbg_filter_count_sum(sdbg_segment* const* segs, size_t n_segs, const sdbg_col_pred* preds,

@@ -1354,6 +1354,7 @@ void orc_synth_column(uint64_t stream, int kind, uint64_t row0, uint64_t rows, v
       case 2: of[i] = double(h >> 11) * 0x1.0p-53; break;
       case 3: oi[i] = int64_t(h % 2001) - 1000; break;
       case 4: of[i] = double(h >> 11) * 0x1.0p-53 * 1000.0; break;
+      case 7: oi[i] = int64_t((row0 + i) / 100); break;   // clustered (an insertion timestamp)
       default: oi[i] = int64_t(h); break;
     }
   }

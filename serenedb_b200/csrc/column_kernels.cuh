@@ -157,7 +157,8 @@ __device__ __forceinline__ void add128u(unsigned long long& lo, long long& hi, u
 
 __global__ void __launch_bounds__(256)
 filter_count_sum_kernel(const PredSet ps, const ColDev sum_col, int has_sum, uint64_t rows,
-                        CountSumOut* __restrict__ partials, unsigned int* __restrict__ done_counter, CountSumOut* host_out) {
+                        CountSumOut* __restrict__ partials, unsigned int* __restrict__ done_counter, CountSumOut* host_out,
+                        unsigned long long* host_seq, unsigned long long seq) {
   unsigned long long cnt = 0, lo = 0;
   long long hi = 0;
   double sf = 0.0;
@@ -231,7 +232,12 @@ filter_count_sum_kernel(const PredSet ps, const ColDev sum_col, int has_sum, uin
         r.count += s[w].count; add128u(r.sum_lo, r.sum_hi, s[w].sum_lo, s[w].sum_hi); r.sum_f += s[w].sum_f;
       }
       partials[gridDim.x] = r;
-      if (host_out != nullptr) { *host_out = r; __threadfence_system(); }
+      if (host_out != nullptr) {
+        *host_out = r;
+        __threadfence_system();
+        // the caller spins on this word instead of synchronising the stream: the result above is visible before it
+        if (host_seq != nullptr) *reinterpret_cast<volatile unsigned long long*>(host_seq) = seq;
+      }
       *done_counter = 0u;
     }
   }
@@ -822,8 +828,24 @@ synth_column_kernel(unsigned long long stream, int kind, uint64_t row0, uint64_t
       case 3: static_cast<long long*>(out)[i] = static_cast<long long>(h % 2001ull) - 1000ll; break;
       case 4: static_cast<double*>(out)[i] = static_cast<double>(h >> 11) * 0x1.0p-53 * 1000.0; break;
       case 6: static_cast<int*>(out)[i] = static_cast<int>(h % 1000000ull); break;
+      case 7: static_cast<long long*>(out)[i] = static_cast<long long>((row0 + i) / 100ull); break;   // clustered (an insertion timestamp)
       default: static_cast<long long*>(out)[i] = static_cast<long long>(h); break;
     }
+  }
+}
+
+// Late materialisation of hit rows (HitBatcher::MaterializeColumn, index/hit_batcher.hpp: the projected columns are fetched
+// for the surviving doc ids only): out[i] = column[docs[i] - 1], validity bit i when the column is nullable.
+template <typename T>
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const T* __restrict__ values, const unsigned long long* __restrict__ validity, const uint32_t* __restrict__ docs,
+                   uint64_t n, uint64_t rows, T* __restrict__ out, unsigned char* __restrict__ out_valid) {
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
+    const uint64_t r = uint64_t(docs[i]) - 1ull;              // doc ids start at 1
+    const bool inside = r < rows;
+    const bool ok = inside && (validity == nullptr || ((validity[r >> 6] >> (r & 63ull)) & 1ull));
+    out[i] = ok ? values[r] : T(0);
+    if (out_valid != nullptr) out_valid[i] = ok ? 1u : 0u;
   }
 }
 

@@ -75,6 +75,7 @@ struct sdbg_ctx {
   unsigned long long* h_oor = nullptr;   // pinned: out-of-range key count of the last deferred GROUP BY partial
   void* h_result = nullptr;     // mapped pinned memory the point-query kernels write their result into (no D2H copy)
   void* d_result = nullptr;     // its device address
+  unsigned long long result_seq = 0;   // completion word value of the last point query
   size_t h_result_cap = 0;
   bool counter_zeroed = false;  // scratch[10] starts at zero; every kernel that uses it leaves it at zero
   bool oor_pending = false;
@@ -506,6 +507,38 @@ extern "C" int sdbg_column_to_host(sdbg_segment* s, uint64_t field, void* host_d
   sdbg_ctx* c = s->ctx;
   CU(c, cudaSetDevice(c->device));
   CU(c, cudaMemcpyAsync(host_dst, it->second.d_values, rows * type_width(it->second.type), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return SDBG_OK;
+}
+
+// Values of one column for a set of hit docs (late materialisation: HitBatcher::MaterializeColumn, hit_batcher.hpp:39;
+// FinalizeBatch in duckdb_search_full_scan.cpp fetches the projected columns for the emitted doc ids only).
+extern "C" int sdbg_gather_column(sdbg_segment* s, uint64_t field, const uint32_t* docs, size_t n, void* out_values, uint8_t* out_valid) {
+  if (!s || (n && (!docs || !out_values))) return SDBG_EINVAL;
+  sdbg_ctx* c = s->ctx;
+  auto it = s->cols.find(field);
+  if (it == s->cols.end()) return fail(c, SDBG_ENOTFOUND, "unknown column");
+  if (!n) return SDBG_OK;
+  CU(c, cudaSetDevice(c->device));
+  const ColumnObj& co = it->second;
+  const size_t w = type_width(co.type);
+  const size_t docs_bytes = (n * 4 + 255) & ~size_t(255), val_bytes = (n * w + 255) & ~size_t(255);
+  DevBuf& buf = c->scratch[12];
+  int rc = ensure(c, buf, docs_bytes + val_bytes + n);
+  if (rc) return rc;
+  char* base = static_cast<char*>(buf.p);
+  auto* d_docs = reinterpret_cast<uint32_t*>(base);
+  void* d_out = base + docs_bytes;
+  auto* d_valid = reinterpret_cast<unsigned char*>(base + docs_bytes + val_bytes);
+  CU(c, cudaMemcpyAsync(d_docs, docs, n * 4, cudaMemcpyHostToDevice, c->stream));
+  const unsigned grid = unsigned(std::min<size_t>((n + 255) / 256, size_t(c->sm_count) * 8));
+  const auto* valid = reinterpret_cast<const unsigned long long*>(co.d_validity);
+  if (w == 4) gather_rows_kernel<uint32_t><<<grid, 256, 0, c->stream>>>(static_cast<const uint32_t*>(co.d_values), valid, d_docs, n, co.rows, static_cast<uint32_t*>(d_out), out_valid ? d_valid : nullptr);
+  else gather_rows_kernel<unsigned long long><<<grid, 256, 0, c->stream>>>(static_cast<const unsigned long long*>(co.d_values), valid, d_docs, n, co.rows, static_cast<unsigned long long*>(d_out), out_valid ? d_valid : nullptr);
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  CU(c, cudaMemcpyAsync(out_values, d_out, n * w, cudaMemcpyDeviceToHost, c->stream));
+  if (out_valid) CU(c, cudaMemcpyAsync(out_valid, d_valid, n, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   return SDBG_OK;
 }
@@ -1417,13 +1450,18 @@ extern "C" int sdbg_filter_count_sum(sdbg_segment* const* segs, size_t n_segs, c
     CU(c, cudaMemsetAsync(c->scratch[15].p, 0, 16, c->stream));
     c->counter_zeroed = true;
   }
-  if (c->h_result_cap < n_segs * sizeof(CountSumOut)) {
+  const size_t seq_off = (n_segs * sizeof(CountSumOut) + 63) & ~size_t(63);   // [results | completion words]
+  if (c->h_result_cap < seq_off + n_segs * 8) {
     if (c->h_result) { cudaStreamSynchronize(c->stream); cudaFreeHost(c->h_result); c->h_result = nullptr; }
-    const size_t want = std::max<size_t>(n_segs * sizeof(CountSumOut), 4096);
+    const size_t want = std::max<size_t>(seq_off + n_segs * 8, 4096);
     CU(c, cudaHostAlloc(&c->h_result, want, cudaHostAllocMapped));
     CU(c, cudaHostGetDevicePointer(&c->d_result, c->h_result, 0));
+    std::memset(c->h_result, 0, want);
     c->h_result_cap = want;
   }
+  const unsigned long long seq = ++c->result_seq;
+  auto* h_seq = reinterpret_cast<volatile unsigned long long*>(static_cast<char*>(c->h_result) + seq_off);
+  auto* d_seq = reinterpret_cast<unsigned long long*>(static_cast<char*>(c->d_result) + seq_off);
   for (size_t si = 0; si < n_segs; ++si) {
     sdbg_segment* s = segs[si];
     PredSet ps; uint64_t rows = 0;
@@ -1441,11 +1479,29 @@ extern "C" int sdbg_filter_count_sum(sdbg_segment* const* segs, size_t n_segs, c
     const unsigned g2 = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(grid, (rows + 2047) / 2048)));   // 8 rows per thread at least
     { ProfScope ps_(c, kProfCountSum);
       filter_count_sum_kernel<<<g2, 256, 0, c->stream>>>(ps, sc, has_sum, rows, part, static_cast<unsigned int*>(c->scratch[15].p),
-                                                         static_cast<CountSumOut*>(c->d_result) + si); }
+                                                         static_cast<CountSumOut*>(c->d_result) + si, d_seq + si, seq); }
     ++c->launches;
     CU(c, cudaGetLastError());
   }
-  CU(c, cudaStreamSynchronize(c->stream));
+  // Wait on the completion words the kernels write into mapped host memory after their result (a PCIe write, ~1 us
+  // after the last block finishes) instead of synchronising the stream; the stream is only queried now and then so
+  // that a failed launch cannot spin forever.
+  for (size_t si = 0; si < n_segs; ++si) {
+    uint32_t spins = 0;
+    while (__atomic_load_n(const_cast<const unsigned long long*>(&h_seq[si]), __ATOMIC_ACQUIRE) != seq) {
+      if ((++spins & 0x3FFFu) == 0u) {
+        const cudaError_t q = cudaStreamQuery(c->stream);
+        if (q != cudaErrorNotReady && q != cudaSuccess) { CU(c, q); }
+        if (q == cudaSuccess && __atomic_load_n(const_cast<const unsigned long long*>(&h_seq[si]), __ATOMIC_ACQUIRE) != seq) {
+          CU(c, cudaStreamSynchronize(c->stream));   // finished without the word (cannot happen unless the write was lost)
+          break;
+        }
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+  }
   unsigned __int128 tot = 0; uint64_t cnt = 0; double sf = 0;
   for (size_t si = 0; si < n_segs; ++si) {
     const CountSumOut& o = static_cast<const CountSumOut*>(c->h_result)[si];

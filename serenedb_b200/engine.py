@@ -270,6 +270,15 @@ class Segment:
         N.check(N.lib().sdbg_column_device_ptr(self._h, int(field), C.byref(p), C.byref(r)), self.ctx._h)
         return p.value, r.value
 
+    def gather(self, field, docs, dtype):
+        """Column values of the given hit docs (late materialisation, HitBatcher::MaterializeColumn): (values, valid)."""
+        docs = np.ascontiguousarray(docs, dtype=np.uint32)
+        out = np.zeros(len(docs), dtype)
+        valid = np.zeros(len(docs), np.uint8)
+        N.check(N.lib().sdbg_gather_column(self._h, int(field), _ptr(docs) if len(docs) else None, len(docs),
+                                           _ptr(out) if len(docs) else None, _ptr(valid) if len(docs) else None), self.ctx._h)
+        return out, valid.astype(bool)
+
     def column_to_host(self, field, host_ptr, rows):
         N.check(N.lib().sdbg_column_to_host(self._h, int(field), C.c_void_p(int(host_ptr)), int(rows)), self.ctx._h)
 
@@ -519,6 +528,22 @@ class IResearchScan:
                                               C.byref(cnt), s128, C.byref(sf)), self.ctx._h)
         si = (int(s128[1]) << 64) | (int(s128[0]) & 0xFFFFFFFFFFFFFFFF)
         return cnt.value, si, sf.value
+
+    def prepare_count_sum(self, preds, sum_field=None):
+        """The same call with its arguments marshalled once (a point query is ~10 us on the device side; building the
+        ctypes arrays per call costs about as much). Returns a callable -> (count, sum_int, sum_f64)."""
+        segs, n_segs, pa, n_preds = _seg_array(self.segments), len(self.segments), _pred_array(preds), len(preds)
+        field = NO_FIELD if sum_field is None else int(sum_field)
+        cnt, s128, sf = C.c_uint64(), (C.c_int64 * 2)(), C.c_double()
+        pc, psf = C.byref(cnt), C.byref(sf)
+        fn, h = N.lib().sdbg_filter_count_sum, self.ctx._h
+
+        def run():
+            rc = fn(segs, n_segs, pa, n_preds, field, pc, s128, psf)
+            if rc:
+                N.check(rc, h)
+            return cnt.value, (int(s128[1]) << 64) | (int(s128[0]) & 0xFFFFFFFFFFFFFFFF), sf.value
+        return run
 
     def groupby(self, preds, key_field, sum_int_field=None, avg_f64_field=None, cap=None, n_groups_hint=0):
         cap = int(cap if cap is not None else max(n_groups_hint, 1 << 20))

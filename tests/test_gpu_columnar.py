@@ -342,3 +342,31 @@ def test_zonemaps_skip_dead_blocks_and_keep_results():
         elif len(exp):
             assert skipped == 0, (spec, skipped)
     gseg.close()
+
+
+def test_gather_hit_rows():
+    """Late materialisation (HitBatcher::MaterializeColumn): projected column values for hit docs only -- int64, float64,
+    int32, a nullable column, unsorted / repeated / out-of-range doc ids."""
+    rows = 200_000
+    rng = np.random.default_rng(3)
+    a = rng.integers(-2**40, 2**40, rows).astype(np.int64)
+    b = rng.random(rows)
+    c32 = rng.integers(-10**6, 10**6, rows).astype(np.int32)
+    valid = rng.random(rows) < 0.8
+    gseg = sdb.Segment(ctx(), rows)
+    gseg.stage_column(1, a)
+    gseg.stage_column(2, b)
+    gseg.stage_column(3, c32)
+    words = np.packbits(np.concatenate([valid, np.zeros((-rows) % 64, bool)]), bitorder="little").view(np.uint64)
+    gseg.stage_column(4, a, validity=words)
+    docs = np.concatenate([rng.integers(1, rows + 1, 5000), [1, rows, rows, 7, 7]]).astype(np.uint32)
+    for f, col, dt in ((1, a, np.int64), (2, b, np.float64), (3, c32, np.int32)):
+        v, ok = gseg.gather(f, docs, dt)
+        assert ok.all() and np.array_equal(v, col[docs - 1])
+    v, ok = gseg.gather(4, docs, np.int64)
+    assert np.array_equal(ok, valid[docs - 1]) and np.array_equal(v, np.where(valid[docs - 1], a[docs - 1], 0))
+    v, ok = gseg.gather(1, np.array([rows + 5, 3], np.uint32), np.int64)
+    assert list(ok) == [False, True] and v[0] == 0 and v[1] == a[2]
+    v, ok = gseg.gather(1, np.zeros(0, np.uint32), np.int64)
+    assert len(v) == 0
+    gseg.close()
