@@ -69,6 +69,7 @@ struct sdbg_ctx {
   size_t h_pinned_cap = 0;
   void* flush = nullptr;
   size_t flush_bytes = 0;
+  cudaEvent_t ev_copy[16] = {};   // one per host conversion thread (sdbg_bm25_topk_batch)
   bool scan_attr_set = false;
   bool topk_attr_set = false;
   void* nccl_comm = nullptr;   // ncclComm_t once sdbg_dist_init ran
@@ -228,6 +229,7 @@ extern "C" void sdbg_destroy(sdbg_ctx* c) {
   sdbg_dist_destroy(c);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
   cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
+  for (cudaEvent_t e : c->ev_copy) if (e) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream2);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -589,6 +591,7 @@ int filter_view(sdbg_segment* s, const sdbg_col_pred* f, FilterDev* out) {
   return SDBG_OK;
 }
 
+constexpr int kMaxCopyEvents = 16;
 constexpr float kTfidfK1 = -1.f;   // internal selector of the TFIDF scorer (it has no k / b): see sdbg_tfidf_topk_batch
 
 // Device-side descriptor of one query term over one segment (the caller has checked the term id).
@@ -968,6 +971,16 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
 
 // keys -> hits on the host. `bases` = first ordinal of each segment.
 void keys_to_hits(const unsigned long long* keys, uint32_t n, const std::vector<uint64_t>& bases, sdbg_hit* out) {
+  if (bases.size() == 1) {                      // one segment: no search for the owner of an ordinal
+    const uint32_t b0 = uint32_t(bases[0]);
+    for (uint32_t i = 0; i < n; ++i) {
+      const uint32_t bits = uint32_t(keys[i] >> 32);
+      std::memcpy(&out[i].score, &bits, 4);
+      out[i].seg = 0;
+      out[i].doc = ~uint32_t(keys[i]) - b0;
+    }
+    return;
+  }
   for (uint32_t i = 0; i < n; ++i) {
     const uint32_t bits = uint32_t(keys[i] >> 32);
     const uint32_t ordinal = ~uint32_t(keys[i]);
@@ -1030,10 +1043,20 @@ extern "C" int sdbg_bm25_topk_batch(sdbg_segment* const* segs, size_t n_segs, in
   // results come back through a dedicated pinned block (the query descriptors are done with by now)
   if ((rc = ensure_pinned(c, kb + nb + tb + 64))) return rc;
   char* h = static_cast<char*>(c->h_pinned);
-  CU(c, cudaMemcpyAsync(h, dev.keys, kb, cudaMemcpyDeviceToHost, c->stream));
+  // key -> {segment, doc, score} is a few ns per hit; a large batch (millions of hits) is cut into per-thread query
+  // ranges whose keys are copied back one after the other, each followed by an event: a thread converts its range as
+  // soon as it has landed, while the later ranges are still on the wire.
+  const size_t n_thr = std::max<size_t>(1, std::min<size_t>({size_t(env_int("SDBG_HOST_THREADS", 16)), (nq * size_t(k)) / 65536, size_t(kMaxCopyEvents)}));
   CU(c, cudaMemcpyAsync(h + kb, dev.total, tb, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaMemcpyAsync(h + kb + tb, dev.n_out, nb, cudaMemcpyDeviceToHost, c->stream));
-  CU(c, cudaStreamSynchronize(c->stream));
+  for (size_t t = 0; t < n_thr; ++t) {
+    const size_t q0 = nq * t / n_thr, q1 = nq * (t + 1) / n_thr;
+    CU(c, cudaMemcpyAsync(h + q0 * k * 8, dev.keys + q0 * k, (q1 - q0) * k * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (n_thr > 1) {
+      if (!c->ev_copy[t]) CU(c, cudaEventCreateWithFlags(&c->ev_copy[t], cudaEventDisableTiming));
+      CU(c, cudaEventRecord(c->ev_copy[t], c->stream));
+    }
+  }
   std::vector<uint64_t> bases(n_segs);
   uint64_t ord0 = 0;
   for (size_t si = 0; si < n_segs; ++si) { bases[si] = ord0; ord0 += segs[si]->n_docs; }
@@ -1047,14 +1070,20 @@ extern "C" int sdbg_bm25_topk_batch(sdbg_segment* const* segs, size_t n_segs, in
       if (total_matches) total_matches[q] = tot[q];
     }
   };
-  // key -> {segment, doc, score} is a few ns per hit; a large batch (millions of hits) is split over host threads
-  const size_t n_thr = std::min<size_t>(size_t(env_int("SDBG_HOST_THREADS", 8)), (nq * size_t(k)) / 65536);
   if (n_thr <= 1) {
+    CU(c, cudaStreamSynchronize(c->stream));
     convert(0, nq);
   } else {
+    std::atomic<int> err{0};
     std::vector<std::thread> pool;
-    for (size_t t = 0; t < n_thr; ++t) pool.emplace_back(convert, nq * t / n_thr, nq * (t + 1) / n_thr);
+    for (size_t t = 0; t < n_thr; ++t)
+      pool.emplace_back([&, t] {
+        if (cudaSetDevice(c->device) != cudaSuccess || cudaEventSynchronize(c->ev_copy[t]) != cudaSuccess) { err = 1; return; }
+        convert(nq * t / n_thr, nq * (t + 1) / n_thr);
+      });
     for (auto& th : pool) th.join();
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (err) return fail(c, SDBG_ECUDA, "copying the hits back failed");
   }
   return SDBG_OK;
 }
