@@ -204,6 +204,7 @@ bm25_merge_kernel(const TopkParams P) {
 
     // Makes block cur[t] the live block of term t: wait for its payload, decode, gather norms, score, publish.
     auto advance = [&](const uint32_t t, uint32_t plo) {
+      __syncwarp();                                                // every lane is done reading the block being replaced
       uint32_t* ld = live_docs(t);
       float* ls = live_scores(t);
       bool have = cur[t] < s_qt[t].nblk;

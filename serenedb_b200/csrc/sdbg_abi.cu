@@ -809,7 +809,7 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
 
   // shared memory of the stream kernel: candidates | score table | per warp (live blocks + prefetch slots)
   bool use_lut[n_segs ? n_segs : 1];
-  for (size_t si = 0; si < n_segs; ++si) use_lut[si] = segs[si]->norm_width == 1 && env_int("SDBG_STREAM_LUT", 1) != 0;
+  for (size_t si = 0; si < n_segs; ++si) use_lut[si] = segs[si]->norm_width == 1 && env_int("SDBG_STREAM_LUT", 0) != 0;
   auto stream_smem = [&](uint32_t T, bool lut, bool conj) {
     return size_t(pl.cap) * 8 + (lut ? size_t(T) * kLutFreqs * 1024 : 0) + size_t(kTopkWarps) * (T * kStreamTermBytes + (conj ? 1024 : 0));
   };
@@ -1164,7 +1164,7 @@ extern "C" int sdbg_bm25_scan(sdbg_segment* s, int kind, const sdbg_bm25_term* t
   P.emit_cap = cap;
   auto* sorted_docs = reinterpret_cast<uint32_t*>(e + 2 * pair_bytes);
   auto* sorted_scores = reinterpret_cast<float*>(e + 3 * pair_bytes);
-  const bool lut = s->norm_width == 1 && env_int("SDBG_STREAM_LUT", 1) != 0;
+  const bool lut = s->norm_width == 1 && env_int("SDBG_STREAM_LUT", 0) != 0;
   const uint32_t Tl = conj ? 1u : T;
   const size_t sm = size_t(scan_cap) * 8 + (lut ? size_t(Tl) * kLutFreqs * 1024 : 0) + size_t(kTopkWarps) * (Tl * kStreamTermBytes + (conj ? 1024 : 0));
   if (!c->scan_attr_set) {

@@ -157,3 +157,28 @@ def test_collectives_at_world_size_one(corpus):
     hl, nl, _ = batch.run_host()
     assert np.array_equal(nd, nl) and np.array_equal(hd["doc"], hl["doc"]) and np.array_equal(hd["score"].view(np.uint32), hl["score"].view(np.uint32))
     seg.close(); g.close(); c.close()
+
+
+@pytest.mark.parametrize("wand", [0, 2])
+def test_score_table_path_is_bit_identical(corpus, wand):
+    """SDBG_STREAM_LUT=1: scores come from the per-CTA table score[term][freq <= 8][norm byte] instead of being computed per
+    posting. The table is filled with the same arithmetic, so hits (docs, order, fp32 bits) must not change; measured 6 %
+    slower than computing on configs[2], hence opt-in -- this keeps the path covered."""
+    scorer = sdb.BM25()
+    ctx().set_wand(wand)
+    cases = [(sdb.OR, [81, 1], 100), (sdb.OR, [5, 59], 1000), (sdb.OR, [0, 1, 2], 100), (sdb.OR, [3, 40, 70, 90], 500),
+             (sdb.AND, [0, 1, 2], 50), (sdb.OR, [95], 1000)]
+    try:
+        for kind, tis, k in cases:
+            os.environ["SDBG_STREAM_LUT"] = "0"
+            a, ta = sdb.ExecuteTopK(corpus["reader"], tis, kind, scorer, k)
+            os.environ["SDBG_STREAM_LUT"] = "1"
+            b, tb = sdb.ExecuteTopK(corpus["reader"], tis, kind, scorer, k)
+            assert_hits_equal(a, b)
+            if wand == 0:
+                assert ta == tb
+            oh, _, _ = orc.bm25_topk([corpus["oseg"]], "AND" if kind == sdb.AND else "OR", oracle_terms(corpus["reader"], scorer, tis), k, mode=1)
+            assert_hits_equal(b, oh)
+    finally:
+        os.environ.pop("SDBG_STREAM_LUT", None)
+        ctx().set_wand(2)
