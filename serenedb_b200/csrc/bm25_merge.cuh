@@ -75,10 +75,18 @@ __device__ __forceinline__ void merge_decode_block_smem(const uint4* pd, const u
   }
 }
 
-// Dynamic shared memory: cand[cap] u64 | lut[T][kLutFreqs][256] f32 (kLut) | per warp: T x kStreamTermBytes.
+// per warp and term: docs[128] u32 | scores[128] f32 | slots[2][32] uint4 | descriptor window[16] uint4. The window is
+// half the stream kernel's: with the 16 KB candidate buffer that is 52 KB per 2-term CTA, so four CTAs fit an SM.
+constexpr uint32_t kMergeWin = 16u;
+constexpr uint32_t kMergeTermBytes = 512u + 512u + 1024u + kMergeWin * 16u;
+
+#ifndef SDBG_MERGE_MIN_BLOCKS
+#define SDBG_MERGE_MIN_BLOCKS 3
+#endif
+// Dynamic shared memory: cand[cap] u64 | lut[T][kLutFreqs][256] f32 (kLut) | per warp: T x kMergeTermBytes.
 // Terms are in ascending-cost order (the host sorts them); T-1 is the "top" term.
 template <uint32_t T, bool kLut>
-__global__ void __launch_bounds__(kTopkThreads, 3)
+__global__ void __launch_bounds__(kTopkThreads, SDBG_MERGE_MIN_BLOCKS)
 bm25_merge_kernel(const TopkParams P) {
   static_assert(T >= 1 && T <= kStreamMaxTerms, "1..4 terms");
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -91,11 +99,11 @@ bm25_merge_kernel(const TopkParams P) {
   __shared__ QTermDev s_qt[kStreamMaxTerms];
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  unsigned char* mine = warp_area + warp * (T * kStreamTermBytes);
-  auto live_docs = [&](uint32_t t) { return reinterpret_cast<uint32_t*>(mine + t * kStreamTermBytes); };
-  auto live_scores = [&](uint32_t t) { return reinterpret_cast<float*>(mine + t * kStreamTermBytes + 512u); };
-  auto slot_of = [&](uint32_t t, uint32_t s) { return reinterpret_cast<uint4*>(mine + t * kStreamTermBytes + 1024u + s * 512u); };
-  auto desc_win = [&](uint32_t t) { return reinterpret_cast<uint4*>(mine + t * kStreamTermBytes + 2048u); };
+  unsigned char* mine = warp_area + warp * (T * kMergeTermBytes);
+  auto live_docs = [&](uint32_t t) { return reinterpret_cast<uint32_t*>(mine + t * kMergeTermBytes); };
+  auto live_scores = [&](uint32_t t) { return reinterpret_cast<float*>(mine + t * kMergeTermBytes + 512u); };
+  auto slot_of = [&](uint32_t t, uint32_t s) { return reinterpret_cast<uint4*>(mine + t * kMergeTermBytes + 1024u + s * 512u); };
+  auto desc_win = [&](uint32_t t) { return reinterpret_cast<uint4*>(mine + t * kMergeTermBytes + 2048u); };
 
   const uint4 work = P.work[blockIdx.x];
   const uint32_t q = work.x, chunk = work.z;   // work item = {query, first doc, docs, candidate list}
@@ -198,7 +206,8 @@ bm25_merge_kernel(const TopkParams P) {
     auto load_window = [&](const uint32_t t, uint32_t first) {
       __syncwarp();
       wb[t] = first;
-      desc_win(t)[lane] = (first + lane <= s_qt[t].nblk) ? __ldg(P.seg.blocks + s_qt[t].blk_begin + first + lane) : make_uint4(0, 0, 0, 0);
+      if (lane < kMergeWin)
+        desc_win(t)[lane] = (first + lane <= s_qt[t].nblk) ? __ldg(P.seg.blocks + s_qt[t].blk_begin + first + lane) : make_uint4(0, 0, 0, 0);
       __syncwarp();
     };
 
@@ -210,7 +219,7 @@ bm25_merge_kernel(const TopkParams P) {
       bool have = cur[t] < s_qt[t].nblk;
       uint4 d = make_uint4(0, 0, 0, 0);
       if (have) {
-        if (cur[t] - wb[t] >= 28u) load_window(t, cur[t]);         // keeps cur .. cur + 3 inside the window
+        if (cur[t] - wb[t] >= kMergeWin - 4u) load_window(t, cur[t]);   // keeps cur .. cur + 3 inside the window
         d = desc_win(t)[cur[t] - wb[t]];
         have = d.z < hi_w;                                         // first doc of the block (prev_last + 1) inside the sub-range
       }

@@ -870,7 +870,7 @@ int topk_run(sdbg_segment* const* segs, size_t n_segs, int kind, const sdbg_bm25
       std::array<size_t, kClasses> cls_off{};
       { size_t o = 0; for (uint32_t cls = 0; cls < kClasses; ++cls) { cls_off[cls] = o; o += n_cls[si][cls]; } }
       auto launch_merge = [&](uint32_t T, size_t n, cudaStream_t st) {
-        const size_t sm = stream_smem(T, lut, false);
+        const size_t sm = size_t(pl.cap) * 8 + (lut ? size_t(T) * kLutFreqs * 1024 : 0) + size_t(kTopkWarps) * T * kMergeTermBytes;
 #define SDBG_MERGE_LAUNCH(TT) \
         if (lut) bm25_merge_kernel<TT, true><<<unsigned(n), kTopkThreads, sm, st>>>(P); \
         else bm25_merge_kernel<TT, false><<<unsigned(n), kTopkThreads, sm, st>>>(P)
