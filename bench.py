@@ -44,14 +44,41 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks line sampled while a timed region runs."""
+    """SM clock and clock-event reasons sampled while a timed region runs. The nvidia-smi clocks line of the profiling
+    recipe needs ~100 ms per sample, longer than a short timed region (10 steps of 1 ms), so the same counters are also read
+    straight from NVML by a thread every 2 ms; nvidia-smi rows are merged in when any arrive."""
 
     def __init__(self, device):
         self.device = device
         self.proc = None
         self.path = None
+        self.rows = []          # (sm_mhz, max_mhz, reasons bitmask) from NVML
+        self._stop = threading.Event()
+        self._thr = None
+        self._nv = None
+
+    def _nvml_loop(self):
+        nv, h = self._nv
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        while not self._stop.is_set():
+            try:
+                self.rows.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), mx, int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))))
+            except Exception:
+                break
+            self._stop.wait(0.002)
 
     def __enter__(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self._nv = (nv, nv.nvmlDeviceGetHandleByIndex(int(self.device)))
+            self._thr = threading.Thread(target=self._nvml_loop, daemon=True)
+            self._thr.start()
+        except Exception:
+            self._nv = None
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
@@ -66,6 +93,9 @@ class ClockSampler:
         return self
 
     def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=2)
         if self.proc is not None:
             time.sleep(0.15)
             self.proc.terminate()
@@ -75,20 +105,34 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        sm, reasons = [], set()
         try:
             rows = [l.strip().split(", ") for l in open(self.path) if l.strip()]
             os.unlink(self.path)
-            sm = [float(r[0]) for r in rows]
-            out["sm_mhz"] = float(np.median(sm)) if sm else None
-            out["sm_max_mhz"] = float(rows[0][1]) if rows else None
-            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            sm += [float(r[0]) for r in rows]
+            if rows:
+                out["sm_max_mhz"] = float(rows[0][1])
             for i, nme in enumerate(names):
                 if any(r[3 + i].strip().lower().startswith("active") for r in rows):
-                    out["reasons"].append(nme)
-            out["samples"] = len(rows)
+                    reasons.add(nme)
         except Exception:
             pass
+        if self.rows and self._nv is not None:
+            nv = self._nv[0]
+            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+            sm += [r[0] for r in self.rows]
+            if out["sm_max_mhz"] is None and self.rows[0][1] is not None:
+                out["sm_max_mhz"] = float(self.rows[0][1])
+            for nme, bit in bits.items():
+                if any(r[2] & bit for r in self.rows):
+                    reasons.add(nme)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["samples"] = len(sm)
+            out["reasons"] = [n for n in names if n in reasons]
         return out
 
 
