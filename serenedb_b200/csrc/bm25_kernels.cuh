@@ -204,6 +204,14 @@ __device__ __forceinline__ float bm25(uint32_t freq, uint32_t norm, float c0, fl
   return __fsub_rn(c0, __fdiv_rn(__fmul_rn(c0, c1), __fadd_rn(c1, static_cast<float>(freq))));
 }
 
+// The BM25 form alone (bm25.cpp:105-106), for kernels the host only dispatches with k != 0, b != 0 (bm25_merge_kernel,
+// bm25_stream_kernel): same operations as the last two lines of bm25(), without the per-posting form tests and without
+// the other forms' divides and square roots in the instruction stream.
+__device__ __forceinline__ float bm25_plain(uint32_t freq, uint32_t norm, float c0, float nc, float nl) {
+  const float c1 = __fadd_rn(nc, __fmul_rn(nl, static_cast<float>(norm)));
+  return __fsub_rn(c0, __fdiv_rn(__fmul_rn(c0, c1), __fadd_rn(c1, static_cast<float>(freq))));
+}
+
 __device__ __forceinline__ bool filter_pass(const FilterDev& f, uint32_t doc) {
   if (f.values == nullptr) return true;
   const size_t r = size_t(doc) - 1u;  // row = doc - 1 (index/column_extract.hpp:46-48)

@@ -245,12 +245,17 @@ bm25_merge_kernel(const TopkParams P) {
       prefetch(t, cur[t] + 2u);
       const uint32_t len = desc_len(d.w);
       uint32_t nrm[4];
+      if (len == 128u && norms_m1 != nullptr && P.seg.norm_width == 1u) {   // uniform: full block, byte norms -- no pads, no width switch
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const bool valid = 4u * lane + j < len;
-        if (!valid) { doc[j] = kNoDoc; f[j] = 1u; }
-        if constexpr (kLut) nrm[j] = (valid && norms_m1) ? __ldg(norms_m1 + doc[j]) : 1u;
-        else nrm[j] = valid ? load_norm(P.seg.norms, P.seg.norm_width, doc[j]) : 1u;
+        for (int j = 0; j < 4; ++j) nrm[j] = __ldg(norms_m1 + doc[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool valid = 4u * lane + j < len;
+          if (!valid) { doc[j] = kNoDoc; f[j] = 1u; }
+          if constexpr (kLut) nrm[j] = (valid && norms_m1) ? __ldg(norms_m1 + doc[j]) : 1u;
+          else nrm[j] = valid ? load_norm(P.seg.norms, P.seg.norm_width, doc[j]) : 1u;
+        }
       }
       float s[4];
       if constexpr (kLut) {
@@ -265,12 +270,12 @@ bm25_merge_kernel(const TopkParams P) {
           const float c0 = s_qt[t].c0, nc = s_qt[t].norm_const, nl = s_qt[t].norm_length;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (f[j] > kLutFreqs) s[j] = bm25(f[j], nrm[j], c0, nc, nl);
+            if (f[j] > kLutFreqs) s[j] = bm25_plain(f[j], nrm[j], c0, nc, nl);
         }
       } else {
         const float c0 = s_qt[t].c0, nc = s_qt[t].norm_const, nl = s_qt[t].norm_length;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) s[j] = bm25(f[j], nrm[j], c0, nc, nl);
+        for (int j = 0; j < 4; ++j) s[j] = bm25_plain(f[j], nrm[j], c0, nc, nl);
       }
       reinterpret_cast<uint4*>(ld)[lane] = make_uint4(doc[0], doc[1], doc[2], doc[3]);
       reinterpret_cast<float4*>(ls)[lane] = make_float4(s[0], s[1], s[2], s[3]);

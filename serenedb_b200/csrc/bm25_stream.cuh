@@ -291,7 +291,7 @@ __device__ __forceinline__ bool probe_term(const PostingsDev& S, const QTermDev&
   if (!freq_at(S.arena, desc, idx, f)) {               // StreamVByte frequencies: scalar walk
     f = svb_value_at(reinterpret_cast<const uint8_t*>(S.arena + desc.x + desc_fdelta(desc.w)), desc_len(desc.w), idx, false, false, 0u, &idx);
   }
-  score = bm25(f, load_norm(S.norms, S.norm_width, d), qt.c0, qt.norm_const, qt.norm_length);
+  score = bm25_plain(f, load_norm(S.norms, S.norm_width, d), qt.c0, qt.norm_const, qt.norm_length);
   return true;
 }
 
@@ -694,12 +694,12 @@ bm25_stream_kernel(const __grid_constant__ TopkParams P) {
           const float c0 = s_qt[t].c0, nc = s_qt[t].norm_const, nl = s_qt[t].norm_length;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (__any_sync(kFull, f[j] > kLutFreqs)) { if (f[j] > kLutFreqs) s[j] = bm25(f[j], nrm[j], c0, nc, nl); }
+            if (__any_sync(kFull, f[j] > kLutFreqs)) { if (f[j] > kLutFreqs) s[j] = bm25_plain(f[j], nrm[j], c0, nc, nl); }
         }
       } else {
         const float c0 = s_qt[t].c0, nc = s_qt[t].norm_const, nl = s_qt[t].norm_length;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) s[j] = bm25(f[j], nrm[j], c0, nc, nl);
+        for (int j = 0; j < 4; ++j) s[j] = bm25_plain(f[j], nrm[j], c0, nc, nl);
       }
       reinterpret_cast<uint4*>(ld)[lane] = make_uint4(doc[0], doc[1], doc[2], doc[3]);
       reinterpret_cast<float4*>(ls)[lane] = make_float4(s[0], s[1], s[2], s[3]);
