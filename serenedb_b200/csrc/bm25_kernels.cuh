@@ -881,6 +881,14 @@ topk_merge_kernel(const MergeParams P) {
   if (tid == 0) { s_n = 0u; s_kth = 0ull; }
   __syncthreads();
   const uint32_t l_begin = P.list_off ? P.list_off[q] : q * P.G, l_end = P.list_off ? P.list_off[q + 1] : (q + 1u) * P.G;
+  if (l_end - l_begin == 1u && P.cand_n != nullptr) {
+    // one chain: its list is already the query's answer (<= k keys, sorted descending by the chain's epilogue)
+    const unsigned long long* src = P.cand + size_t(l_begin) * P.stride;
+    const uint32_t n = min(min(P.cand_n[l_begin], P.stride), P.k);
+    for (uint32_t i = tid; i < P.k; i += blockDim.x) P.keys_out[size_t(q) * P.k + i] = i < n ? src[i] : 0ull;
+    if (tid == 0) P.n_out[q] = n;
+    return;
+  }
   for (uint32_t g = l_begin; g < l_end; ++g) {
     const unsigned long long* src = P.cand + size_t(g) * P.stride;
     const uint32_t n = P.cand_n ? min(P.cand_n[g], P.stride) : P.stride;
