@@ -195,6 +195,19 @@ int sdbg_topk_merge_gathered(sdbg_ctx*, const void* d_keys_all /* n_ranks*n_quer
 int sdbg_decode_score_term(sdbg_segment*, uint32_t term, float c0, float norm_const, float norm_length,
                            uint32_t* docs, uint32_t* freqs, float* scores);
 
+/* Encoded int64 columns: frame-of-reference bit-packing in groups of 2048 rows -- per group a base (the minimum) and a
+ * bit width, values stored as (v - base) in `bits` bits, little-endian, groups 8-byte aligned; bits = 0 is a constant
+ * group. This is the algorithm of DuckDB's `bitpacking` codec in FOR mode, which the reference's column blocks name in
+ * ColumnBlockMeta::codec (irs/formats/column/column_reader.hpp:90-96); DuckDB is not vendored in the reference tree, so
+ * the byte layout is this library's. sdbg_pack_for is the host-side writer (returns SDBG_ECAPACITY with *n_words = the
+ * room needed); sdbg_stage_column_for copies the packed stream to the GPU and decodes it there into a staged SDBG_I64
+ * column, so only the packed bytes cross PCIe. */
+typedef struct { int64_t base; uint32_t bits; uint32_t off8; } sdbg_for_block;
+int sdbg_pack_for(const int64_t* values, uint64_t rows, sdbg_for_block* headers /* (rows + 2047) / 2048 */, uint64_t* words,
+                  uint64_t cap_words, uint64_t* n_words);
+int sdbg_stage_column_for(sdbg_segment*, uint64_t field, const sdbg_for_block* headers, const uint64_t* words, uint64_t n_words,
+                          uint64_t rows);
+
 /* Late materialisation (HitBatcher::MaterializeColumn, irs/index/hit_batcher.hpp:39; FinalizeBatch of the search scan):
  * out_values[i] = column[docs[i] - 1] for n hit docs of the segment (element width = the staged type's), out_valid[i]
  * (nullable) = 0 for NULL or out-of-range rows, whose value is written as 0. */

@@ -8,10 +8,10 @@ import raises -- there is no Python or CPU fallback for any operation.
 from . import _native
 from .engine import (AND, OR, BM25, TFIDF, FLT_MIN, Context, ExecuteTopK, ExecuteTopKBatch, IndexReader,
                      IResearchScan, PostingsWriter, PreparedBatch, Segment, merge_gathered, pred,
-                     stage_parse_host, sum_i128, StreamScoredDocs)
+                     stage_parse_host, sum_i128, StreamScoredDocs, pack_for)
 
 _native.lib()  # fail loudly at import time when the CUDA extension is missing
 
 __all__ = ["AND", "OR", "BM25", "TFIDF", "FLT_MIN", "Context", "ExecuteTopK", "ExecuteTopKBatch", "IndexReader",
            "IResearchScan", "PostingsWriter", "PreparedBatch", "Segment", "merge_gathered", "pred",
-           "stage_parse_host", "sum_i128", "StreamScoredDocs"]
+           "stage_parse_host", "sum_i128", "StreamScoredDocs", "pack_for"]

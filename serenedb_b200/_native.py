@@ -65,6 +65,8 @@ SIGNATURES = {
     "sdbg_stage_column_device": (C.c_int, [_vp, C.c_uint64, C.c_int, _vp, C.c_uint64]),
     "sdbg_column_device_ptr": (C.c_int, [_vp, C.c_uint64, C.POINTER(_vp), _u64p]),
     "sdbg_column_to_host": (C.c_int, [_vp, C.c_uint64, _vp, C.c_uint64]),
+    "sdbg_pack_for": (C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_uint64, _u64p]),
+    "sdbg_stage_column_for": (C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_uint64, C.c_uint64]),
     "sdbg_gather_column": (C.c_int, [_vp, C.c_uint64, _vp, _sz, _vp, _vp]),
     "sdbg_segment_posting_stats": (C.c_int, [_vp, _u64p, _u64p, _u64p, _u64p]),
     "sdbg_segment_term_bytes": (C.c_int, [_vp, _vp, _sz]),

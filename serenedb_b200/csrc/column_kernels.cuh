@@ -849,4 +849,34 @@ gather_rows_kernel(const T* __restrict__ values, const unsigned long long* __res
   }
 }
 
+// Frame-of-reference bit-packed int64 column -> raw values (staging-time decode). One warp per 2048-row group:
+// value i of the group sits at bit i * bits of the group's word run, little-endian; bits == 0 is a constant group.
+struct ForBlockDev { long long base; uint32_t bits; uint32_t off8; };
+constexpr uint32_t kForGroupRows = 2048;
+
+__global__ void __launch_bounds__(256)
+for_unpack_kernel(const ForBlockDev* __restrict__ headers, const unsigned long long* __restrict__ words, uint64_t rows,
+                  long long* __restrict__ out) {
+  const uint64_t n_groups = (rows + kForGroupRows - 1) / kForGroupRows;
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint64_t g = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; g < n_groups; g += (uint64_t(gridDim.x) * blockDim.x) >> 5) {
+    const ForBlockDev h = headers[g];
+    const unsigned long long* w = words + h.off8;
+    const uint64_t row0 = g * kForGroupRows;
+    const uint32_t n = (rows - row0 < kForGroupRows) ? uint32_t(rows - row0) : kForGroupRows;
+    const unsigned long long mask = h.bits >= 64u ? ~0ull : ((1ull << h.bits) - 1ull);
+    for (uint32_t i = lane; i < n; i += 32u) {             // consecutive lanes -> consecutive values: coalesced stores
+      unsigned long long v = 0ull;
+      if (h.bits != 0u) {
+        const uint64_t bit = uint64_t(i) * h.bits;
+        const uint32_t sh = uint32_t(bit & 63ull);
+        const unsigned long long lo = w[bit >> 6] >> sh;
+        const unsigned long long hi = (sh != 0u && sh + h.bits > 64u) ? (w[(bit >> 6) + 1ull] << (64u - sh)) : 0ull;
+        v = (lo | hi) & mask;
+      }
+      out[row0 + i] = h.base + static_cast<long long>(v);   // two's complement wrap-around = the encoder's subtraction undone
+    }
+  }
+}
+
 }  // namespace sdbg

@@ -482,6 +482,104 @@ extern "C" int sdbg_stage_column(sdbg_segment* s, uint64_t field, sdbg_type t, c
   return SDBG_OK;  // asynchronous on the context stream; consumers run on the same stream
 }
 
+// ---- frame-of-reference bit-packed int64 columns (DuckDB's bitpacking codec in FOR mode is this algorithm: per group
+// of 2048 values a base and a bit width, formats/column/column_reader.hpp:90-96 ColumnBlockMeta::codec; DuckDB itself is
+// not vendored in the reference tree, so the byte layout below is this library's own) ----
+static_assert(sizeof(sdbg_for_block) == sizeof(ForBlockDev), "header layout");
+
+extern "C" int sdbg_pack_for(const int64_t* values, uint64_t rows, sdbg_for_block* headers, uint64_t* words, uint64_t cap_words,
+                             uint64_t* n_words) {
+  if (!values || !headers || !n_words || (cap_words && !words)) return SDBG_EINVAL;
+  const uint64_t n_groups = (rows + kForGroupRows - 1) / kForGroupRows;
+  // pass 1 (threaded): base = min, bits = width of max - min, word count per group
+  const size_t n_thr = std::max<size_t>(1, std::min<size_t>(size_t(env_int("SDBG_HOST_THREADS", 16)), n_groups / 64 + 1));
+  auto stats = [&](uint64_t g0, uint64_t g1) {
+    for (uint64_t g = g0; g < g1; ++g) {
+      const uint64_t r0 = g * kForGroupRows, r1 = std::min<uint64_t>(rows, r0 + kForGroupRows);
+      int64_t mn = values[r0], mx = values[r0];
+      for (uint64_t r = r0 + 1; r < r1; ++r) { mn = std::min(mn, values[r]); mx = std::max(mx, values[r]); }
+      const uint64_t span = uint64_t(mx) - uint64_t(mn);
+      headers[g].base = mn;
+      headers[g].bits = span == 0 ? 0u : uint32_t(64 - __builtin_clzll(span));
+    }
+  };
+  {
+    std::vector<std::thread> pool;
+    for (size_t t = 0; t < n_thr; ++t) pool.emplace_back(stats, n_groups * t / n_thr, n_groups * (t + 1) / n_thr);
+    for (auto& th : pool) th.join();
+  }
+  uint64_t off = 0;
+  for (uint64_t g = 0; g < n_groups; ++g) {
+    const uint64_t n = std::min<uint64_t>(kForGroupRows, rows - g * kForGroupRows);
+    if (off > 0xFFFFFFFFull) return SDBG_EUNSUPPORTED;            // 32-bit word offsets: 32 GiB of packed data per column
+    headers[g].off8 = uint32_t(off);
+    off += (n * headers[g].bits + 63) / 64;
+  }
+  *n_words = off + 1;                                             // one word of slack: the decoder may read one past a value
+  if (*n_words > cap_words) return SDBG_ECAPACITY;
+  auto pack = [&](uint64_t g0, uint64_t g1) {
+    for (uint64_t g = g0; g < g1; ++g) {
+      const uint32_t bits = headers[g].bits;
+      if (!bits) continue;
+      const uint64_t r0 = g * kForGroupRows, n = std::min<uint64_t>(kForGroupRows, rows - r0);
+      uint64_t* w = words + headers[g].off8;
+      const uint64_t nw = (n * bits + 63) / 64;
+      std::fill(w, w + nw, 0ull);
+      const uint64_t base = uint64_t(headers[g].base);
+      for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t v = uint64_t(values[r0 + i]) - base, bit = i * bits;
+        w[bit >> 6] |= v << (bit & 63);
+        if ((bit & 63) + bits > 64) w[(bit >> 6) + 1] |= v >> (64 - (bit & 63));
+      }
+    }
+  };
+  {
+    std::vector<std::thread> pool;
+    for (size_t t = 0; t < n_thr; ++t) pool.emplace_back(pack, n_groups * t / n_thr, n_groups * (t + 1) / n_thr);
+    for (auto& th : pool) th.join();
+  }
+  words[off] = 0;
+  return SDBG_OK;
+}
+
+extern "C" int sdbg_stage_column_for(sdbg_segment* s, uint64_t field, const sdbg_for_block* headers, const uint64_t* words,
+                                     uint64_t n_words, uint64_t rows) {
+  if (!s || !headers || !words || !rows || !n_words) return SDBG_EINVAL;
+  sdbg_ctx* c = s->ctx;
+  CU(c, cudaSetDevice(c->device));
+  const uint64_t n_groups = (rows + kForGroupRows - 1) / kForGroupRows;
+  for (uint64_t g = 0; g < n_groups; ++g) {                       // the stream is untrusted input: every group must lie inside it
+    const uint64_t n = std::min<uint64_t>(kForGroupRows, rows - g * kForGroupRows);
+    if (headers[g].bits > 64u || uint64_t(headers[g].off8) + (n * headers[g].bits + 63) / 64 + 1 > n_words)
+      return fail(c, SDBG_EFORMAT, "bit-packed column: group outside the word stream");
+  }
+  ColumnObj& col = s->cols[field];
+  const size_t bytes = rows * 8;
+  if (!(col.owned && col.d_values && col.rows == rows && col.type == SDBG_I64)) {
+    free_column(col);
+    col = ColumnObj{};
+    CU(c, cudaMalloc(&col.d_values, bytes + 64));
+    CU(c, cudaMemsetAsync(static_cast<char*>(col.d_values) + bytes, 0, 64, c->stream));
+  }
+  if (col.d_validity) { cudaFree(col.d_validity); col.d_validity = nullptr; }
+  col.type = SDBG_I64; col.rows = rows; col.owned = true; col.has_minmax = false; col.has_absmax = false;
+  if (col.d_zone) { cudaFree(col.d_zone); col.d_zone = nullptr; }
+  DevBuf& buf = c->scratch[12];
+  const size_t hdr_bytes = (n_groups * sizeof(ForBlockDev) + 255) & ~size_t(255);
+  int rc = ensure(c, buf, hdr_bytes + n_words * 8);
+  if (rc) return rc;
+  char* base = static_cast<char*>(buf.p);
+  CU(c, cudaMemcpyAsync(base, headers, n_groups * sizeof(ForBlockDev), cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(base + hdr_bytes, words, n_words * 8, cudaMemcpyHostToDevice, c->stream));
+  const unsigned grid = unsigned(std::min<uint64_t>((n_groups * 32 + 255) / 256, uint64_t(c->sm_count) * 16));
+  for_unpack_kernel<<<std::max(grid, 1u), 256, 0, c->stream>>>(reinterpret_cast<const ForBlockDev*>(base),
+                                                               reinterpret_cast<const unsigned long long*>(base + hdr_bytes), rows,
+                                                               static_cast<long long*>(col.d_values));
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  return SDBG_OK;   // asynchronous on the context stream, like sdbg_stage_column
+}
+
 extern "C" int sdbg_stage_column_device(sdbg_segment* s, uint64_t field, sdbg_type t, const void* d_values, uint64_t rows) {
   if (!s || !d_values || t < 0 || t > 2) return SDBG_EINVAL;
   if (rows & 1) return fail(s->ctx, SDBG_EINVAL, "borrowed device columns need an even row count (16-byte row pairs)");

@@ -256,6 +256,13 @@ class Segment:
             vv = _ptr(validity)
         N.check(N.lib().sdbg_stage_column(self._h, int(field), t, vp, vv, int(rows)), self.ctx._h)
 
+    def stage_column_for(self, field, packed):
+        """Stage an int64 column from its frame-of-reference bit-packed form (pack_for): only the packed bytes cross PCIe,
+        the values are unpacked on the GPU."""
+        headers, words, rows = packed
+        self._keep.append(packed)
+        N.check(N.lib().sdbg_stage_column_for(self._h, int(field), _ptr(headers), _ptr(words), len(words), int(rows)), self.ctx._h)
+
     def stage_docs_mask(self, deleted_docs):
         """DocumentMask of the segment: doc ids that queries must neither score nor count (None / empty clears)."""
         d = np.ascontiguousarray(deleted_docs if deleted_docs is not None else [], dtype=np.uint32)
@@ -407,6 +414,22 @@ def ExecuteTopKBatch(reader, queries, kind, scorer, k, filt=None, threshold=FLT_
                                          _ptr(off), nq, scorer.k, scorer.b, fp, int(k), float(threshold), _ptr(hits),
                                          _ptr(n_out), _ptr(total)), ctx._h)
     return hits, n_out, total
+
+
+FOR_BLOCK_DTYPE = np.dtype([("base", "<i8"), ("bits", "<u4"), ("off8", "<u4")])
+
+
+def pack_for(values, out_words=None):
+    """Host-side writer of the bit-packed column format (sdbg_pack_for): returns (headers, words, rows). `out_words` may be a
+    preallocated (e.g. pinned) uint64 array."""
+    values = np.ascontiguousarray(values, dtype=np.int64)
+    rows = len(values)
+    headers = np.zeros((rows + 2047) // 2048, FOR_BLOCK_DTYPE)
+    n = C.c_uint64(0)
+    words = out_words if out_words is not None else np.zeros(rows + 1, np.uint64)      # never larger than the raw column + slack
+    rc = N.lib().sdbg_pack_for(_ptr(values), rows, _ptr(headers), _ptr(words), len(words), C.byref(n))
+    N.check(rc)
+    return headers, words[:n.value], rows
 
 
 def StreamScoredDocs(reader, seg_idx, query, kind, scorer, filt=None, doc_min=1, doc_max=None):

@@ -157,3 +157,46 @@ def test_mock_headers_match_the_reference():
     spec.loader.exec_module(m)
     blocks, decls, problems = m.check("/root/reference")
     assert blocks >= 6 and decls >= 60 and not problems, problems
+
+
+def _for_decode(headers, words, rows):
+    """Independent (pure Python) decoder of the bit-packed column format described in include/sdbg.h."""
+    out = np.zeros(rows, np.int64)
+    for g, hd in enumerate(headers):
+        r0 = g * 2048
+        bits, base = int(hd["bits"]), int(hd["base"])
+        for i in range(min(2048, rows - r0)):
+            v = 0
+            if bits:
+                bit = i * bits
+                wi, sh = int(hd["off8"]) + (bit >> 6), bit & 63
+                x = (int(words[wi]) >> sh) | ((int(words[wi + 1]) << (64 - sh)) if sh and sh + bits > 64 else 0)
+                v = x & ((1 << bits) - 1)
+            u = (base + v) & 0xFFFFFFFFFFFFFFFF
+            out[r0 + i] = u - (1 << 64) if u >= (1 << 63) else u
+    return out
+
+
+def test_for_bitpacked_column_writer_round_trips():
+    """sdbg_pack_for (host-side writer, no GPU needed): frame-of-reference bit-packing in 2048-row groups; widths 0 (constant
+    group) .. 64, negative bases, the int64 extremes, ragged last group; capacity errors report the room needed."""
+    import ctypes as C
+    import serenedb_b200 as sdb
+    from serenedb_b200 import _native as N
+    rng = np.random.default_rng(1)
+    i64 = np.iinfo(np.int64)
+    cases = [rng.integers(0, 100000, 5000), rng.integers(-2**62, 2**62, 4097), np.full(3000, -7), np.array([i64.min, i64.max, 0]),
+             rng.integers(-1000, 1001, 2048), np.arange(10_000) // 100, np.array([5]), rng.integers(0, 2, 6000)]
+    for vals in cases:
+        vals = vals.astype(np.int64)
+        h, w, rows = sdb.pack_for(vals)
+        assert rows == len(vals) and len(h) == (rows + 2047) // 2048
+        assert np.array_equal(_for_decode(h, w, rows), vals)
+        span = [int(vals[g * 2048:(g + 1) * 2048].max()) - int(vals[g * 2048:(g + 1) * 2048].min()) for g in range(len(h))]
+        assert [int(b) for b in h["bits"]] == [s.bit_length() for s in span]          # the narrowest width that holds max - min
+    vals = cases[0].astype(np.int64)
+    n = C.c_uint64(0)
+    hdr = np.zeros(3, sdb.engine.FOR_BLOCK_DTYPE)
+    small = np.zeros(4, np.uint64)
+    rc = N.lib().sdbg_pack_for(vals.ctypes.data_as(C.c_void_p), len(vals), hdr.ctypes.data_as(C.c_void_p), small.ctypes.data_as(C.c_void_p), 4, C.byref(n))
+    assert rc == -6 and n.value == 1330                                                # ECAPACITY, room needed
