@@ -48,8 +48,9 @@ class ClockSampler:
     recipe needs ~100 ms per sample, longer than a short timed region (10 steps of 1 ms), so the same counters are also read
     straight from NVML by a thread every 2 ms; nvidia-smi rows are merged in when any arrive."""
 
-    def __init__(self, device):
+    def __init__(self, device, enabled=True):
         self.device = device
+        self.enabled = enabled    # multi-GPU runs sample on rank 0 only: eight pollers on one driver are eight too many
         self.proc = None
         self.path = None
         self.rows = []          # (sm_mhz, max_mhz, reasons bitmask) from NVML
@@ -68,9 +69,11 @@ class ClockSampler:
                 self.rows.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), mx, int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))))
             except Exception:
                 break
-            self._stop.wait(0.002)
+            self._stop.wait(0.004)
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         try:
             import pynvml as nv
             nv.nvmlInit()
@@ -410,7 +413,7 @@ def main():
     barrier()
     ctx.profile(True)
     launches0 = ctx.launches
-    with ClockSampler(local) as cs1:
+    with ClockSampler(local, rank == 0) as cs1:
         barrier()
         ctx.timer_start()
         for _ in range(args.steps):
@@ -584,7 +587,7 @@ def main():
             ctx.profile(True)
             l0 = ctx.launches
             tot = 0.0
-            with ClockSampler(local) as cs:
+            with ClockSampler(local, rank == 0) as cs:
                 for _ in range(steps):
                     ctx.flush_l2()        # evict the index between timed steps (the 256-term one is about L2-sized)
                     barrier()
