@@ -25,9 +25,10 @@
 //   * block payloads arrive through the TMA engine: per warp and term two 512-byte slots, filled two blocks ahead by
 //     cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes (SASS UBLKCP) and awaited on an mbarrier
 //     (SYNCS), so the decode reads shared memory and does not wait for L2 / HBM;
-//   * BM25 per posting is one shared-memory load: per CTA a table score[term][freq <= 8][norm byte] is built once with
-//     exactly the arithmetic of bm25() (so a table hit is bit-identical to computing it); rarer (freq, norm) pairs
-//     are computed.
+//   * BM25 per posting is computed (bm25_plain: the __f*_rn sequence of bm25.cpp:105-106). The kLut instantiations instead
+//     read a per-CTA table score[term][freq <= 8][norm byte], built once with exactly that arithmetic (so a table hit is
+//     bit-identical to computing it; rarer pairs are computed): measured 6-8 % SLOWER on the benchmark batch -- the lookup
+//     is a random 32-lane shared-memory gather -- and therefore opt-in (SDBG_STREAM_LUT=1), kept under test.
 // The term count is a run-time value and every per-term loop is rolled: the whole scan is ~2 k instructions, so the
 // eight warps of a CTA, which are all at different places of it, stay inside the instruction cache (the first
 // version unrolled everything per term: 17 k instructions for two terms and `no_instruction` as its top stall).
