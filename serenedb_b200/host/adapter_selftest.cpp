@@ -3,6 +3,7 @@
 // for tests/test_gpu_adapters.py to compare with the oracle. Needs a GPU at run time.
 #include <cstdio>
 #include <cstdlib>
+#include <thread>
 #include <vector>
 
 #include "gpu_adapters.hpp"
@@ -87,6 +88,35 @@ int main(int argc, char** argv) {
   }
   std::printf("{\"groups\": %llu, \"rows\": %llu, \"chunks\": %llu, \"sum_v\": %lld, \"avg_sum\": %.12g}\n", static_cast<unsigned long long>(groups),
               static_cast<unsigned long long>(rows), static_cast<unsigned long long>(chunks), static_cast<long long>(sum), avg_sum);
+  // --- the same scan mode driven by four concurrent workers (one global state, a local state each) ---
+  {
+    sdbg_host::GpuAggGlobalState gs({seg}, preds, 10, 13, 14, 100000);
+    constexpr int kWorkers = 4;
+    uint64_t w_groups[kWorkers] = {}, w_rows[kWorkers] = {}, w_chunks[kWorkers] = {};
+    long long w_sum[kWorkers] = {};
+    bool w_ok[kWorkers] = {};
+    std::vector<std::thread> pool;
+    for (int w = 0; w < kWorkers; ++w)
+      pool.emplace_back([&, w] {
+        sdbg_host::GpuAggLocalState ls;
+        duckdb::DataChunkMock out;
+        bool ok = true;
+        for (;;) {
+          sdbg_host::GpuAggScanFunction(gs, ls, out);
+          if (out.size == 0) break;
+          ok = ok && out.size <= duckdb::STANDARD_VECTOR_SIZE;
+          for (size_t i = 0; i < out.size; ++i) { ++w_groups[w]; w_rows[w] += uint64_t(out.count[i]); w_sum[w] += out.sum_lo[i]; }
+        }
+        w_chunks[w] = ls.chunks_claimed;
+        w_ok[w] = ok;
+      });
+    for (auto& th : pool) th.join();
+    uint64_t tg = 0, tr = 0, tc = 0; long long ts = 0; bool ok = true;
+    for (int w = 0; w < kWorkers; ++w) { tg += w_groups[w]; tr += w_rows[w]; tc += w_chunks[w]; ts += w_sum[w]; ok = ok && w_ok[w]; }
+    std::printf("{\"mt_groups\": %llu, \"mt_rows\": %llu, \"mt_chunks\": %llu, \"mt_sum_v\": %lld, \"mt_ok\": %d, \"mt_emitted\": %llu}\n",
+                static_cast<unsigned long long>(tg), static_cast<unsigned long long>(tr), static_cast<unsigned long long>(tc), ts, ok ? 1 : 0,
+                static_cast<unsigned long long>(gs.rows_emitted.load()));
+  }
   sdbg_segment_destroy(seg);
   sdbg_destroy(ctx);
   return 0;

@@ -160,4 +160,42 @@ void GpuAggScan::Scan(duckdb::DataChunkMock& output) {
   cursor_ += take;
 }
 
+GpuAggGlobalState::GpuAggGlobalState(std::vector<sdbg_segment*> segments, std::vector<sdbg_col_pred> pushed_filters, uint64_t key_field,
+                                     uint64_t sum_int_field, uint64_t avg_f64_field, uint32_t n_groups_hint)
+    : segs(std::move(segments)), preds(std::move(pushed_filters)), key(key_field), sum_i(sum_int_field), avg_f(avg_f64_field),
+      hint(n_groups_hint) {}
+
+void GpuAggScanFunction(GpuAggGlobalState& g, GpuAggLocalState& l, duckdb::DataChunkMock& output) {
+  output.Reset();
+  std::call_once(g.ran, [&] {                 // an exception here leaves the flag unset: the next worker retries and rethrows
+    uint64_t cap = std::max<uint64_t>(g.hint, 1024), n = 0;
+    std::vector<sdbg_group_row> rows;
+    for (;;) {
+      rows.resize(cap);
+      const int rc = sdbg_filter_groupby(g.segs.data(), g.segs.size(), g.preds.data(), g.preds.size(), g.key, g.hint, g.sum_i, g.avg_f,
+                                         rows.data(), cap, &n);
+      if (rc == SDBG_ECAPACITY && n > cap) { cap = n; continue; }
+      if (rc != SDBG_OK) throw GpuError(rc, std::string("sdbg_filter_groupby: ") + sdbg_last_error(sdbg_segment_context(g.segs[0])));
+      break;
+    }
+    rows.resize(n);
+    g.groups = std::move(rows);
+  });
+  const size_t chunk = g.next_chunk.fetch_add(1, std::memory_order_relaxed);
+  const size_t first = chunk * size_t(duckdb::STANDARD_VECTOR_SIZE);
+  if (first >= g.groups.size()) return;                      // cardinality 0
+  const size_t take = std::min<size_t>(duckdb::STANDARD_VECTOR_SIZE, g.groups.size() - first);
+  for (size_t i = 0; i < take; ++i) {
+    const sdbg_group_row& r = g.groups[first + i];
+    output.key.push_back(r.key);
+    output.count.push_back(int64_t(r.count));
+    output.sum_lo.push_back(r.sum_i128[0]);
+    output.sum_hi.push_back(r.sum_i128[1]);
+    output.avg.push_back(r.cnt_f64 ? r.sum_f64 / double(r.cnt_f64) : 0.0);
+  }
+  output.size = take;
+  ++l.chunks_claimed;
+  g.rows_emitted.fetch_add(take, std::memory_order_relaxed);
+}
+
 }  // namespace sdbg_host

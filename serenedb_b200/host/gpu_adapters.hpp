@@ -15,6 +15,8 @@
 // IoError / THROW_SQL_ERROR call sites.
 #pragma once
 
+#include <atomic>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -99,5 +101,28 @@ class GpuAggScan {
   bool ran_ = false;
   uint64_t rows_scanned_ = 0;
 };
+
+// The same scan mode under DuckDB's threading contract (duckdb_search_full_scan.hpp:85-255, .cpp:99-268): ONE global
+// state shared by all workers of the query -- touched through atomics only, like next_segment / next_unit there -- and
+// one local state per worker. The first worker to arrive runs the aggregation on the GPU (the others wait on the
+// once-flag, as they would wait for rows anyway); afterwards every worker claims chunks of <= STANDARD_VECTOR_SIZE
+// result rows from an atomic cursor and fills its own DataChunk. Cardinality 0 = this worker is done.
+struct GpuAggGlobalState {
+  GpuAggGlobalState(std::vector<sdbg_segment*> segments, std::vector<sdbg_col_pred> pushed_filters, uint64_t key_field,
+                    uint64_t sum_int_field, uint64_t avg_f64_field, uint32_t n_groups_hint);
+  std::vector<sdbg_segment*> segs;
+  std::vector<sdbg_col_pred> preds;
+  uint64_t key, sum_i, avg_f;
+  uint32_t hint;
+  std::once_flag ran;
+  std::vector<sdbg_group_row> groups;          // written once (under `ran`), read-only afterwards
+  std::atomic<size_t> next_chunk{0};           // claim cursor, in units of STANDARD_VECTOR_SIZE rows
+  std::atomic<uint64_t> rows_emitted{0};       // get_metrics hook
+};
+struct GpuAggLocalState {
+  uint64_t chunks_claimed = 0;
+};
+// Body of IResearchScanFunction for ScanMode::GpuAgg (:1645-1709): safe to call from many threads at once.
+void GpuAggScanFunction(GpuAggGlobalState& g, GpuAggLocalState& l, duckdb::DataChunkMock& output);
 
 }  // namespace sdbg_host

@@ -16,7 +16,7 @@ def test_adapters_match_oracle():
     n = 200_000
     res = subprocess.run([exe, str(n)], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
-    topk, stream, agg = [json.loads(l) for l in res.stdout.strip().splitlines()]
+    topk, stream, agg, mt = [json.loads(l) for l in res.stdout.strip().splitlines()]
     # ---- GpuTopKIterator::Collect vs oracle (2-term OR + INCLUDE-column range filter, k = 100) ----
     oseg, dc, sum_dl = orc.synth_segment_mt(n, 0, 8, threads=4)
     nn = orc.synth_column(2, 1, 1, n).astype(np.int32)
@@ -57,3 +57,6 @@ def test_adapters_match_oracle():
     assert agg["chunks"] == (len(exp) + 2047) // 2048           # <= STANDARD_VECTOR_SIZE rows per call
     assert agg["sum_v"] == int(exp["sum_lo"].astype(object).sum())
     assert agg["avg_sum"] == pytest.approx(float((exp["sum_f64"] / exp["cnt_f64"]).sum()), rel=1e-9)
+    # ---- the same mode under DuckDB's threading contract: four workers share one global state and claim chunks atomically ----
+    assert mt["mt_ok"] == 1 and mt["mt_groups"] == len(exp) == mt["mt_emitted"] and mt["mt_rows"] == int(exp["count"].sum())
+    assert mt["mt_chunks"] == (len(exp) + 2047) // 2048 and mt["mt_sum_v"] == int(exp["sum_lo"].astype(object).sum())
