@@ -199,6 +199,35 @@ def test_sequential_order_goldens_on_gpu():
         ctx().set_wand(0)
 
 
+def test_tfidf_sequential_order_goldens_on_gpu():
+    """tfidf_test.cpp:531,934,984,1032,1080 (rank orders under TFIDF without norms) through the GPU path, bit-exact against the
+    oracle that test_oracle_goldens pins to the same goldens."""
+    g, t = G["sequential_order"], G["tfidf_sequential_order"]
+    n = len(g["docs"])
+    dl = np.array([len(d["field"]) for d in g["docs"]], np.uint32)
+    oseg = orc.Segment(n, has_wand=True)
+    oseg.set_norms(dl)
+    for ti in range(10):
+        docs = [i + 1 for i, d in enumerate(g["docs"]) if str(ti) in d["field"]]
+        oseg.add_term(np.array(docs, np.uint32), np.array([g["docs"][i - 1]["field"].count(str(ti)) for i in docs], np.uint32))
+    gseg = to_gpu(oseg)
+    reader = sdb.IndexReader([gseg], n, int(dl.sum()), [oseg.term_meta(ti).docs_count for ti in range(10)])
+    scorer = sdb.TFIDF(normalize=t["normalize"])
+    for c in t["cases"]:
+        tis = [int(x) for x in c["terms"]]
+        hits, total = sdb.ExecuteTopK(reader, tis, sdb.OR, scorer, 8)
+        assert [g["docs"][d - 1]["seq"] for d in hits["doc"]] == c["expected_seq_order"], c["range"]
+        assert total == len(c["expected_seq_order"])
+        terms = []
+        for ti in tis:
+            x = orc.BM25Term()
+            x.idf = orc.tfidf_idf(n, int(reader.docs_with_term[ti]))
+            x.norm_const, x.norm_length, x.boost, x.term = 0.0, 0.0, 1.0, ti
+            terms.append(x)
+        oh, _, _ = orc.bm25_topk([oseg], "OR", terms, 8, k1=-1.0, b=0.0, mode=1)
+        assert_hits_equal(hits, oh)
+
+
 def test_collector_worst_case_increasing_scores():
     """Scores increasing with doc id defeat every threshold: the candidate buffer must keep compacting."""
     n = 200_000
@@ -305,7 +334,7 @@ def test_docs_mask(corpus):
 @pytest.mark.parametrize("kind,tis,k", [("OR", [3, 5], 100), ("OR", [0], 50), ("AND", [0, 1, 4], 100), ("OR", [2, 6, 7, 8], 200)])
 def test_tfidf_scorer(corpus, normalize, kind, tis, k):
     """irs::TFIDF (search/tfidf.cpp:59-80, 149-150) on the same scan: sqrt(freq) * idf [/ sqrt(doc length)], bit-exact
-    against the oracle's restatement (no sqllogic value in the reference tree pins TFIDF: restated, no golden)."""
+    against the oracle's restatement (pinned to the reference's rank-order goldens by test_tfidf_sequential_order_goldens)."""
     scorer = sdb.TFIDF(normalize=normalize)
     hits, total = sdb.ExecuteTopK(corpus["reader"], tis, sdb.AND if kind == "AND" else sdb.OR, scorer, k)
     terms = []

@@ -178,3 +178,23 @@ def test_fma_contraction_of_the_reference_build_stays_inside_the_bar():
         sc = {int(d): float(s) for d, s in zip(a["doc"], a["score"])}
         sc.update({int(d): float(s) for d, s in zip(b["doc"], b["score"])})
         assert all(abs(sc[d] - kth) <= 1e-5 * kth for d in only), (terms, sorted(only)[:5])   # membership differs only at the cut
+
+
+def test_tfidf_sequential_order_goldens():
+    """tfidf_test.cpp:531,934,984,1032,1080: rank orders of term / range queries under TFIDF without norms on the same eight
+    docs -- pins the oracle's TFIDF restatement (sqrt(freq) * idf per term, summed) to reference-held answers."""
+    g, seg, dl, docs_count = _sequential_order_segment()
+    t = G["tfidf_sequential_order"]
+    for c in t["cases"]:
+        terms = []
+        for tok in c["terms"]:
+            ti = int(tok)
+            q = orc.BM25Term()
+            q.idf = orc.tfidf_idf(len(dl), docs_count[ti])
+            q.norm_const, q.norm_length, q.boost, q.term = 0.0, 0.0, 1.0, ti
+            terms.append(q)
+        for mode in (0, 1, 2):
+            hits, total, _ = orc.bm25_topk([seg], "OR", terms, 8, k1=-1.0, b=1.0 if t["normalize"] else 0.0, mode=mode)
+            seqs = [g["docs"][d - 1]["seq"] for d in hits["doc"]]
+            assert seqs == c["expected_seq_order"], (c["range"], mode, seqs, hits["score"].tolist())
+            assert total == len(c["expected_seq_order"])
