@@ -199,6 +199,31 @@ def test_sequential_order_goldens_on_gpu():
         ctx().set_wand(0)
 
 
+def test_sequential_order_goldens_without_norm_column_on_gpu():
+    """bm25_test.cpp:506,908,958,1006,1054 (Bm25TestCase.test_query: the field has no Norm feature, every doc scores with
+    norm = 1, bm25.cpp:353-360) through the GPU path at every pruning level, bit-exact against the pinned oracle."""
+    g, t = G["sequential_order"], G["sequential_order_no_norms"]
+    n = len(g["docs"])
+    oseg = orc.Segment(n, has_wand=False)
+    for ti in range(10):
+        docs = [i + 1 for i, d in enumerate(g["docs"]) if str(ti) in d["field"]]
+        oseg.add_term(np.array(docs, np.uint32), np.array([g["docs"][i - 1]["field"].count(str(ti)) for i in docs], np.uint32))
+    gseg = to_gpu(oseg, has_wand=False)
+    reader = sdb.IndexReader([gseg], n, 52, [oseg.term_meta(ti).docs_count for ti in range(10)])
+    scorer = sdb.BM25(t["k"], t["b"])
+    try:
+        for level in (0, 2):
+            ctx().set_wand(level)
+            for c in t["cases"]:
+                tis = [int(x) for x in c["terms"]]
+                hits, total = sdb.ExecuteTopK(reader, tis, sdb.OR, scorer, 8)
+                assert [g["docs"][d - 1]["seq"] for d in hits["doc"]] == c["expected_seq_order"], (level, c["range"])
+                oh, _, _ = orc.bm25_topk([oseg], "OR", oracle_terms(reader, scorer, tis), 8, k1=t["k"], b=t["b"], mode=1)
+                assert_hits_equal(hits, oh)
+    finally:
+        ctx().set_wand(0)
+
+
 def test_tfidf_sequential_order_goldens_on_gpu():
     """tfidf_test.cpp:531,934,984,1032,1080 (rank orders under TFIDF without norms) through the GPU path, bit-exact against the
     oracle that test_oracle_goldens pins to the same goldens."""

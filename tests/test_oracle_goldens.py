@@ -198,3 +198,36 @@ def test_tfidf_sequential_order_goldens():
             seqs = [g["docs"][d - 1]["seq"] for d in hits["doc"]]
             assert seqs == c["expected_seq_order"], (c["range"], mode, seqs, hits["score"].tolist())
             assert total == len(c["expected_seq_order"])
+
+
+def _no_norm_segment():
+    g = G["sequential_order"]
+    n = len(g["docs"])
+    seg = orc.Segment(n, has_wand=False)          # no norm column: every doc scores with norm = 1 (bm25.cpp:353-360)
+    docs_count = []
+    for t in range(10):
+        docs = [i + 1 for i, d in enumerate(g["docs"]) if str(t) in d["field"]]
+        seg.add_term(np.array(docs, np.uint32), np.array([g["docs"][i - 1]["field"].count(str(t)) for i in docs], np.uint32))
+        docs_count.append(len(docs))
+    return g, seg, n, docs_count
+
+
+def test_sequential_order_goldens_without_norm_column():
+    """bm25_test.cpp:506,908,958,1006,1054 (Bm25TestCase.test_query): the same docs indexed WITHOUT the Norm feature -- BM25
+    with norm = 1 for every doc and avgdl from the field statistics; five more reference-held rank orders (the [6, 8]
+    order differs from the with-norms one, so this pins the default-norm branch specifically)."""
+    g, seg, n, docs_count = _no_norm_segment()
+    t = G["sequential_order_no_norms"]
+    for c in t["cases"]:
+        terms = []
+        for tok in c["terms"]:
+            ti = int(tok)
+            st = orc.bm25_stats(n, 52, docs_count[ti], t["k"], t["b"])
+            q = orc.BM25Term()
+            q.idf, q.norm_const, q.norm_length, q.boost, q.term = st.idf, st.norm_const, st.norm_length, 1.0, ti
+            terms.append(q)
+        for mode in (0, 1, 2):
+            hits, total, _ = orc.bm25_topk([seg], "OR", terms, 8, k1=t["k"], b=t["b"], mode=mode)
+            seqs = [g["docs"][d - 1]["seq"] for d in hits["doc"]]
+            assert seqs == c["expected_seq_order"], (c["range"], mode, seqs, hits["score"].tolist())
+            assert total == len(c["expected_seq_order"])
