@@ -231,3 +231,27 @@ def test_sequential_order_goldens_without_norm_column():
             seqs = [g["docs"][d - 1]["seq"] for d in hits["doc"]]
             assert seqs == c["expected_seq_order"], (c["range"], mode, seqs, hits["score"].tolist())
             assert total == len(c["expected_seq_order"])
+
+
+def test_multi_segment_term_query_uses_corpus_wide_statistics():
+    """bm25_test.cpp:545-652 (test_query, "by_term multi-segment"): the docs split into two segments by even / odd seq, term
+    "6", BM25 without a norm column; statistics are collected over BOTH segments (collectors.cpp:36-52) and the merged
+    descending-score order of seq values is {0, 2 (segment 0), 5 (segment 1)}."""
+    g = G["sequential_order"]
+    segs, maps = [], []
+    for parity in (0, 1):
+        docs = [d for d in g["docs"] if d["seq"] % 2 == parity]
+        seg = orc.Segment(len(docs), has_wand=False)
+        for t in range(10):
+            ids = [i + 1 for i, d in enumerate(docs) if str(t) in d["field"]]
+            seg.add_term(np.array(ids, np.uint32), np.array([docs[i - 1]["field"].count(str(t)) for i in ids], np.uint32))
+        segs.append(seg)
+        maps.append([d["seq"] for d in docs])
+    n_with_6 = sum(1 for d in g["docs"] if "6" in d["field"])
+    st = orc.bm25_stats(8, 52, n_with_6, 1.2, 0.75)
+    q = orc.BM25Term()
+    q.idf, q.norm_const, q.norm_length, q.boost, q.term = st.idf, st.norm_const, st.norm_length, 1.0, 6
+    for mode in (0, 1, 2):
+        hits, total, _ = orc.bm25_topk(segs, "OR", [q], 8, k1=1.2, b=0.75, mode=mode)
+        assert [maps[int(h["seg"])][int(h["doc"]) - 1] for h in hits] == [0, 2, 5], mode
+        assert total == 3
