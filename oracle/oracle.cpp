@@ -1336,6 +1336,9 @@ float orc_tfidf_idf(uint64_t docs_with_field, uint64_t docs_with_term) {
   return static_cast<float>(std::log1p((double(docs_with_field) + 1.0) / (double(docs_with_term) + 1.0)));
 }
 
+// test hook: SkipWriter::Prepare's level count (skip_list.cpp:38-41,50-51) as the writer above uses it
+uint32_t orc_count_max_levels(uint64_t skip_0, uint64_t skip_n, uint64_t count) { return count_max_levels(skip_0, skip_n, count); }
+
 uint64_t orc_synth_hash(uint64_t stream, uint64_t index) {
   uint64_t z = (UINT64_C(0x5EDB2026) ^ (stream << 48) ^ index) + UINT64_C(0x9E3779B97F4A7C15);
   z = (z ^ (z >> 30)) * UINT64_C(0xBF58476D1CE4E5B9);

@@ -162,6 +162,7 @@ int orc_filter_groupby(orc_segment* const* segs, size_t n_segs, const orc_pred* 
 void orc_set_contract(int on);
 /* TFIDF statistics (search/tfidf.cpp:149-150). The top-k entry points select TFIDF with k1 = -1 (b != 0: normalised). */
 float orc_tfidf_idf(uint64_t docs_with_field, uint64_t docs_with_term);
+uint32_t orc_count_max_levels(uint64_t skip_0, uint64_t skip_n, uint64_t count);
 uint64_t orc_synth_hash(uint64_t stream, uint64_t index);
 /* kind: 0 k=h%100000, 1 a=h%1e6, 2 b in [0,1), 3 v=(h%2001)-1000, 4 w in [0,1000), 5.. raw int64 */
 void orc_synth_column(uint64_t stream, int kind, uint64_t row0, uint64_t rows, void* out);

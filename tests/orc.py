@@ -136,6 +136,8 @@ def lib():
     L.orc_tfidf_idf.restype = C.c_float
     L.orc_set_contract.argtypes = [C.c_int]
     L.orc_set_contract.restype = None
+    L.orc_count_max_levels.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
+    L.orc_count_max_levels.restype = C.c_uint32
     L.orc_synth_hash.argtypes = [C.c_uint64, C.c_uint64]
     L.orc_synth_hash.restype = C.c_uint64
     L.orc_synth_column.argtypes = [C.c_uint64, C.c_int, C.c_uint64, C.c_uint64, vp]

@@ -255,3 +255,14 @@ def test_multi_segment_term_query_uses_corpus_wide_statistics():
         hits, total, _ = orc.bm25_topk(segs, "OR", [q], 8, k1=1.2, b=0.75, mode=mode)
         assert [maps[int(h["seg"])][int(h["doc"]) - 1] for h in hits] == [0, 2, 5], mode
         assert total == 3
+
+
+def test_skip_level_count_goldens():
+    """skip_list_test.cpp:152-188 (SkipWriterTest.Prepare) and the static_assert at skip_list.cpp:43-44: the number of skip
+    levels the writer prepares for a posting count -- the one piece of the skip-list layout the reference's tests hold
+    as a number."""
+    cml = orc.lib().orc_count_max_levels
+    assert min(10, cml(8, 8, 1923)) == 3
+    assert min(5, cml(8, 8, 1923000)) == 5
+    assert cml(8, 8, 7) == 0 and cml(8, 8, 0) == 0
+    assert cml(128, 32, 0xFFFFFFFF) == 5          # doc_limits::kBlockSize / kSkipSize / eof() -> kMaxSkipLevels
